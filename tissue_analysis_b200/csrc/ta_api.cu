@@ -1,0 +1,567 @@
+// C ABI of libtissue_b200.so (see include/tissue_b200.h).  Host-side context, buffers, launches.
+#include "../../include/tissue_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ta_common.cuh"
+#include "ta_kernels.cuh"
+#include "ta_scan.cuh"
+#include "ta_second_pass.cuh"
+
+struct ta_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    const void* vol = nullptr;   // device pointer in use
+    void* vol_owned = nullptr;   // our copy when bound from host memory
+    size_t vol_owned_bytes = 0;
+    int elem = 0;
+    long long nf = 0, nm = 0, ns = 0, own_lo = 0, own_hi = 0, slow_offset = 0;
+
+    LabelTable lt{};
+    size_t lt_alloc_rows = 0;
+    PairTable pt{};
+    size_t pt_alloc_cap = 0;
+    uint32_t* status = nullptr;       // [4]
+    unsigned int* counters = nullptr; // [4]: brick counter, compact count, max label, spare
+
+    u64* sort_keys[2] = {nullptr, nullptr};
+    uint32_t* sort_vals[2] = {nullptr, nullptr};
+    size_t sort_alloc = 0;
+    void* cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+    uint32_t* records = nullptr;
+    size_t records_alloc = 0;
+    uint64_t nrecords = 0;
+    bool have_tables = false;
+
+    cudaEvent_t ev[6] = {};
+    float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
+    uint64_t launches = 0;
+};
+
+static thread_local std::string g_err;
+
+#define TA_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                     cudaGetErrorString(e_));                                                 \
+            if (ctx) ctx->err = buf_; else g_err = buf_;                                      \
+            return TA_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+static int fail(ta_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg; else g_err = msg;
+    return code;
+}
+
+static size_t next_pow2(size_t v) { size_t p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename P> static int ensure(ta_ctx* ctx, P** ptr, size_t* have, size_t want_elems) {
+    if (*have >= want_elems && *ptr) return TA_OK;
+    if (*ptr) TA_CUDA(cudaFree(*ptr));
+    *ptr = nullptr; *have = 0;
+    TA_CUDA(cudaMalloc((void**)ptr, want_elems * sizeof(P)));
+    *have = want_elems;
+    return TA_OK;
+}
+
+extern "C" {
+
+const char* ta_version(void) { return "tissue_b200 0.1 (sm_100a)"; }
+
+const char* ta_last_error(ta_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int ta_ctx_create(ta_ctx** out, int device) {
+    ta_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, TA_ERR_BAD_ARG, "ta_ctx_create: out is null");
+    int ndev = 0;
+    TA_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(nullptr, TA_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device >= 0) TA_CUDA(cudaSetDevice(device));
+    else TA_CUDA(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    TA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, TA_ERR_CUDA, "device is not sm_100 class (Blackwell) hardware");
+    ctx = new ta_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    TA_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto& e : ctx->ev) TA_CUDA(cudaEventCreate(&e));
+    TA_CUDA(cudaMalloc((void**)&ctx->status, 4 * sizeof(uint32_t)));
+    TA_CUDA(cudaMalloc((void**)&ctx->counters, 4 * sizeof(unsigned int)));
+    TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ta::scan_smem_bytes()));
+    TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ta::scan_smem_bytes()));
+    *out = ctx;
+    return TA_OK;
+}
+
+int ta_ctx_destroy(ta_ctx* ctx) {
+    if (!ctx) return TA_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->vol_owned);
+    cudaFree(ctx->lt.count); cudaFree(ctx->lt.s1); cudaFree(ctx->lt.s2); cudaFree(ctx->lt.bmin); cudaFree(ctx->lt.bmax);
+    cudaFree(ctx->pt.keys); cudaFree(ctx->pt.vals);
+    cudaFree(ctx->status); cudaFree(ctx->counters);
+    for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
+    cudaFree(ctx->cub_temp); cudaFree(ctx->records);
+    for (auto& e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return TA_OK;
+}
+
+int ta_set_stream(ta_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return TA_OK;
+}
+
+int ta_bind_volume(ta_ctx* ctx, const void* data, int is_device, int elem_bytes, int64_t n_fast, int64_t n_mid,
+                   int64_t n_slow) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!data) return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: data is null");
+    if (elem_bytes != 2 && elem_bytes != 4) return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: elem_bytes must be 2 or 4");
+    if (n_fast <= 0 || n_mid <= 0 || n_slow <= 0 || n_fast > 0x7FFFFFF0LL || n_mid > 0x7FFFFFF0LL ||
+        n_slow > 0x7FFFFFF0LL)
+        return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: bad shape");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)n_fast * n_mid * n_slow * elem_bytes;
+    if (is_device) {
+        ctx->vol = data;
+    } else {
+        if (ctx->vol_owned_bytes < bytes) {
+            if (ctx->vol_owned) TA_CUDA(cudaFree(ctx->vol_owned));
+            ctx->vol_owned = nullptr; ctx->vol_owned_bytes = 0;
+            TA_CUDA(cudaMalloc(&ctx->vol_owned, bytes));
+            ctx->vol_owned_bytes = bytes;
+        }
+        TA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+        TA_CUDA(cudaMemcpyAsync(ctx->vol_owned, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        TA_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+        TA_CUDA(cudaStreamSynchronize(ctx->stream));
+        TA_CUDA(cudaEventElapsedTime(&ctx->h2d_ms, ctx->ev[4], ctx->ev[5]));
+        ctx->vol = ctx->vol_owned;
+    }
+    ctx->elem = elem_bytes;
+    ctx->nf = n_fast; ctx->nm = n_mid; ctx->ns = n_slow;
+    ctx->own_lo = 0; ctx->own_hi = n_slow; ctx->slow_offset = 0;
+    ctx->have_tables = false;
+    return TA_OK;
+}
+
+int ta_set_slab(ta_ctx* ctx, int64_t own_lo, int64_t own_hi, int64_t slow_offset) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "ta_set_slab: no volume bound");
+    if (own_lo < 0 || own_hi > ctx->ns || own_lo > own_hi || slow_offset < 0)
+        return fail(ctx, TA_ERR_BAD_ARG, "ta_set_slab: bad plane range");
+    ctx->own_lo = own_lo; ctx->own_hi = own_hi; ctx->slow_offset = slow_offset;
+    ctx->have_tables = false;
+    return TA_OK;
+}
+
+// compaction + sort + gather of the pair hash into ctx->records
+static int build_records(ta_ctx* ctx) {
+    cudaStream_t st = ctx->stream;
+    size_t cap = (size_t)ctx->pt.cap_mask + 1;
+    if (ctx->sort_alloc < cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->sort_keys[i]) TA_CUDA(cudaFree(ctx->sort_keys[i]));
+            if (ctx->sort_vals[i]) TA_CUDA(cudaFree(ctx->sort_vals[i]));
+            ctx->sort_keys[i] = nullptr; ctx->sort_vals[i] = nullptr;
+        }
+        ctx->sort_alloc = 0;
+        for (int i = 0; i < 2; ++i) {
+            TA_CUDA(cudaMalloc((void**)&ctx->sort_keys[i], cap * sizeof(u64)));
+            TA_CUDA(cudaMalloc((void**)&ctx->sort_vals[i], cap * sizeof(uint32_t)));
+        }
+        ctx->sort_alloc = cap;
+    }
+    TA_CUDA(cudaMemsetAsync(&ctx->counters[1], 0, sizeof(unsigned int), st));
+    int blocks = (int)std::min<size_t>((cap + 255) / 256, (size_t)ctx->num_sms * 8);
+    ta::compact_pairs_kernel<<<blocks, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], &ctx->counters[1]);
+    ctx->launches++;
+    unsigned int n = 0;
+    TA_CUDA(cudaMemcpyAsync(&n, &ctx->counters[1], sizeof n, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    ctx->nrecords = n;
+    if (n == 0) return TA_OK;
+    size_t need = 0;
+    TA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals[0],
+                                            ctx->sort_vals[1], (int)n, 0, 64, st));
+    if (need > ctx->cub_temp_bytes) {
+        if (ctx->cub_temp) TA_CUDA(cudaFree(ctx->cub_temp));
+        ctx->cub_temp = nullptr; ctx->cub_temp_bytes = 0;
+        TA_CUDA(cudaMalloc(&ctx->cub_temp, need));
+        ctx->cub_temp_bytes = need;
+    }
+    TA_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, need, ctx->sort_keys[0], ctx->sort_keys[1],
+                                            ctx->sort_vals[0], ctx->sort_vals[1], (int)n, 0, 64, st));
+    ctx->launches += 4;   // CUB radix passes (library kernels; not counted as ours in bench)
+    int rc = ensure(ctx, &ctx->records, &ctx->records_alloc, (size_t)n * ta::REC_WORDS);
+    if (rc) return rc;
+    ta::gather_records_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pt, ctx->sort_keys[1], ctx->sort_vals[1], n,
+                                                              ctx->records);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+static int ensure_pair_table(ta_ctx* ctx, size_t cap) {
+    if (ctx->pt_alloc_cap < cap) {
+        if (ctx->pt.keys) TA_CUDA(cudaFree(ctx->pt.keys));
+        if (ctx->pt.vals) TA_CUDA(cudaFree(ctx->pt.vals));
+        ctx->pt.keys = nullptr; ctx->pt.vals = nullptr; ctx->pt_alloc_cap = 0;
+        TA_CUDA(cudaMalloc((void**)&ctx->pt.keys, cap * sizeof(u64)));
+        TA_CUDA(cudaMalloc((void**)&ctx->pt.vals, cap * TA_PAIR_STRIDE * sizeof(uint32_t)));
+        ctx->pt_alloc_cap = cap;
+    }
+    ctx->pt.cap_mask = (uint32_t)(cap - 1);
+    ctx->pt.status = ctx->status;
+    TA_CUDA(cudaMemsetAsync(ctx->pt.keys, 0xFF, cap * sizeof(u64), ctx->stream));
+    TA_CUDA(cudaMemsetAsync(ctx->pt.vals, 0, cap * TA_PAIR_STRIDE * sizeof(uint32_t), ctx->stream));
+    return TA_OK;
+}
+
+int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "ta_run_pass: no volume bound");
+    if ((flags & TA_PASS_ALL) == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass: empty flags");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->have_tables = false;
+    const size_t nvox = (size_t)ctx->nf * ctx->nm * ctx->ns;
+    TA_CUDA(cudaEventRecord(ctx->ev[0], st));
+
+    // ---- label table rows ---------------------------------------------------------------------------------------
+    size_t nrows;
+    if (ctx->elem == 2) {
+        nrows = 65536;
+    } else if (max_label_hint) {
+        nrows = (size_t)max_label_hint + 1;
+    } else {
+        TA_CUDA(cudaMemsetAsync(&ctx->counters[2], 0, sizeof(unsigned int), st));
+        ta::max_label_kernel<<<ctx->num_sms * 8, 256, 0, st>>>((const uint32_t*)ctx->vol, nvox, &ctx->counters[2]);
+        ctx->launches++;
+        unsigned int mx = 0;
+        TA_CUDA(cudaMemcpyAsync(&mx, &ctx->counters[2], sizeof mx, cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        if (mx == 0xFFFFFFFFu) return fail(ctx, TA_ERR_LABEL_RANGE, "label 0xFFFFFFFF is reserved");
+        nrows = (size_t)mx + 1;
+    }
+    if (ctx->lt_alloc_rows < nrows) {
+        cudaFree(ctx->lt.count); cudaFree(ctx->lt.s1); cudaFree(ctx->lt.s2); cudaFree(ctx->lt.bmin); cudaFree(ctx->lt.bmax);
+        ctx->lt = LabelTable{}; ctx->lt_alloc_rows = 0;
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.count, nrows * sizeof(u64)));
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.s1, nrows * 3 * sizeof(u64)));
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.s2, nrows * 6 * sizeof(u64)));
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.bmin, nrows * 3 * sizeof(int)));
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.bmax, nrows * 3 * sizeof(int)));
+        ctx->lt_alloc_rows = nrows;
+    }
+    ctx->lt.nrows = (uint32_t)nrows;
+    ta::init_label_table_kernel<<<(unsigned)((nrows * 6 + 255) / 256), 256, 0, st>>>(ctx->lt);
+    ctx->launches++;
+
+    // ---- pair table -----------------------------------------------------------------------------------------------
+    size_t cap = pair_capacity_hint ? next_pow2((size_t)pair_capacity_hint * 3)
+                                    : next_pow2(std::min<size_t>(std::max<size_t>(nvox / 1024, 1u << 14), 1u << 24));
+    cap = std::max<size_t>(cap, 1024);
+    if (cap > (1ull << 31)) return fail(ctx, TA_ERR_BAD_ARG, "pair capacity too large");
+    int rc = ensure_pair_table(ctx, cap);
+    if (rc) return rc;
+    TA_CUDA(cudaMemsetAsync(ctx->status, 0, 4 * sizeof(uint32_t), st));
+    TA_CUDA(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned int), st));
+
+    // ---- the scan ---------------------------------------------------------------------------------------------------
+    ScanParams P{};
+    P.vol = ctx->vol;
+    P.nf = ctx->nf; P.nm = ctx->nm; P.ns = ctx->ns;
+    P.own_lo = ctx->own_lo; P.own_hi = ctx->own_hi; P.slow_offset = ctx->slow_offset;
+    const int seg = 16 / ctx->elem;
+    const long long BF = (long long)ta::NFS * seg;
+    P.nbf = (int)((ctx->nf + BF - 1) / BF);
+    P.nbm = (int)((ctx->nm + ta::BM - 1) / ta::BM);
+    P.nbs = (int)((ctx->own_hi - ctx->own_lo + ta::BS - 1) / ta::BS);
+    P.flags = flags;
+    P.vec_ok = ((ctx->nf % seg) == 0) && (((uintptr_t)ctx->vol & 15) == 0);
+    P.brick_counter = &ctx->counters[0];
+    const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
+    if (total > 0xFFFFFFF0ull) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass");
+    TA_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if (total > 0) {
+        int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 2);
+        if (ctx->elem == 2)
+            ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes(), st>>>(P, ctx->lt, ctx->pt);
+        else
+            ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes(), st>>>(P, ctx->lt, ctx->pt);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+    }
+    TA_CUDA(cudaEventRecord(ctx->ev[2], st));
+
+    rc = build_records(ctx);
+    if (rc) return rc;
+    TA_CUDA(cudaEventRecord(ctx->ev[3], st));
+    uint32_t status[4];
+    TA_CUDA(cudaMemcpyAsync(status, ctx->status, sizeof status, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    TA_CUDA(cudaEventElapsedTime(&ctx->scan_ms, ctx->ev[1], ctx->ev[2]));
+    TA_CUDA(cudaEventElapsedTime(&ctx->pass_ms, ctx->ev[0], ctx->ev[3]));
+    if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow: retry with a larger pair_capacity_hint");
+    if (status[1]) return fail(ctx, TA_ERR_LABEL_RANGE, "a label exceeds max_label_hint");
+    ctx->have_tables = true;
+    return TA_OK;
+}
+
+int ta_label_table_size(ta_ctx* ctx, uint64_t* n) {
+    if (!ctx || !n) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    *n = ctx->lt.nrows;
+    return TA_OK;
+}
+
+int ta_fetch_label_table(ta_ctx* ctx, uint64_t* count, uint64_t* s1, uint64_t* s2, int32_t* bbox) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    size_t n = ctx->lt.nrows;
+    cudaStream_t st = ctx->stream;
+    if (count) TA_CUDA(cudaMemcpyAsync(count, ctx->lt.count, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (s1) TA_CUDA(cudaMemcpyAsync(s1, ctx->lt.s1, n * 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (s2) TA_CUDA(cudaMemcpyAsync(s2, ctx->lt.s2, n * 6 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    if (bbox) {
+        std::vector<int> lo(n * 3), hi(n * 3);
+        TA_CUDA(cudaMemcpy(lo.data(), ctx->lt.bmin, n * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+        TA_CUDA(cudaMemcpy(hi.data(), ctx->lt.bmax, n * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a) { bbox[i * 6 + a] = lo[i * 3 + a]; bbox[i * 6 + 3 + a] = hi[i * 3 + a]; }
+    }
+    return TA_OK;
+}
+
+int ta_pair_table_size(ta_ctx* ctx, uint64_t* n) {
+    if (!ctx || !n) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    *n = ctx->nrecords;
+    return TA_OK;
+}
+
+int ta_fetch_pair_table(ta_ctx* ctx, uint32_t* lo, uint32_t* hi, uint32_t* faces, uint32_t* wall18) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    size_t n = ctx->nrecords;
+    if (n == 0) return TA_OK;
+    std::vector<uint32_t> rec(n * ta::REC_WORDS);
+    TA_CUDA(cudaMemcpyAsync(rec.data(), ctx->records, rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t* r = &rec[i * ta::REC_WORDS];
+        if (lo) lo[i] = r[0];
+        if (hi) hi[i] = r[1];
+        if (faces) for (int f = 0; f < 6; ++f) faces[i * 6 + f] = r[2 + f];
+        if (wall18) wall18[i] = r[8];
+    }
+    return TA_OK;
+}
+
+int ta_label_table_device(ta_ctx* ctx, void** count, void** s1, void** s2, void** bmin, void** bmax, uint64_t* n) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    if (count) *count = ctx->lt.count;
+    if (s1) *s1 = ctx->lt.s1;
+    if (s2) *s2 = ctx->lt.s2;
+    if (bmin) *bmin = ctx->lt.bmin;
+    if (bmax) *bmax = ctx->lt.bmax;
+    if (n) *n = ctx->lt.nrows;
+    return TA_OK;
+}
+
+int ta_pair_records_device(ta_ctx* ctx, void** records, uint64_t* n) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    if (records) *records = ctx->records;
+    if (n) *n = ctx->nrecords;
+    return TA_OK;
+}
+
+int ta_merge_pair_records(ta_ctx* ctx, const void* device_records, uint64_t n) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (n && !device_records) return fail(ctx, TA_ERR_BAD_ARG, "ta_merge_pair_records: null records");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t cap = std::max<size_t>(next_pow2((size_t)n * 2), 1024);
+    int rc = ensure_pair_table(ctx, cap);
+    if (rc) return rc;
+    TA_CUDA(cudaMemsetAsync(ctx->status, 0, 4 * sizeof(uint32_t), st));
+    if (n) {
+        ta::merge_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->pt, (const uint32_t*)device_records, n);
+        ctx->launches++;
+    }
+    rc = build_records(ctx);
+    if (rc) return rc;
+    uint32_t status[4];
+    TA_CUDA(cudaMemcpyAsync(status, ctx->status, sizeof status, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow in merge");
+    ctx->have_tables = true;
+    return TA_OK;
+}
+
+int ta_inertia_from_moments(ta_ctx* ctx, const uint32_t* labels, uint64_t n, double* evals, double* evecs) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    if (n == 0) return TA_OK;
+    if (!evals || !evecs) return fail(ctx, TA_ERR_BAD_ARG, "null output");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t* dl = nullptr; double *dv = nullptr, *dw = nullptr;
+    TA_CUDA(cudaMalloc((void**)&dw, n * 3 * sizeof(double)));
+    TA_CUDA(cudaMalloc((void**)&dv, n * 9 * sizeof(double)));
+    if (labels) {
+        TA_CUDA(cudaMalloc((void**)&dl, n * sizeof(uint32_t)));
+        TA_CUDA(cudaMemcpyAsync(dl, labels, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    ta::inertia_from_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->lt, dl, n, dw, dv);
+    ctx->launches++;
+    TA_CUDA(cudaMemcpyAsync(evals, dw, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaMemcpyAsync(evecs, dv, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dl); cudaFree(dv); cudaFree(dw);
+    return TA_OK;
+}
+
+int ta_inertia_eig(ta_ctx* ctx, const double* cov, uint64_t n, double* evals, double* evecs) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (n == 0) return TA_OK;
+    if (!cov || !evals || !evecs) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *dc = nullptr, *dv = nullptr, *dw = nullptr;
+    TA_CUDA(cudaMalloc((void**)&dc, n * 6 * sizeof(double)));
+    TA_CUDA(cudaMalloc((void**)&dw, n * 3 * sizeof(double)));
+    TA_CUDA(cudaMalloc((void**)&dv, n * 9 * sizeof(double)));
+    TA_CUDA(cudaMemcpyAsync(dc, cov, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    ta::inertia_eig_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dc, n, dw, dv);
+    ctx->launches++;
+    TA_CUDA(cudaMemcpyAsync(evals, dw, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaMemcpyAsync(evecs, dv, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dc); cudaFree(dv); cudaFree(dw);
+    return TA_OK;
+}
+
+int ta_wall_voxel_coords(ta_ctx* ctx, const uint32_t* lo, const uint32_t* hi, uint64_t npairs, uint64_t* counts,
+                         int64_t* xyz) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "no volume bound");
+    if (npairs == 0) return TA_OK;
+    if (!lo || !hi || !counts) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    return ta::wall_voxel_coords_impl(ctx->vol, ctx->elem, ctx->nf, ctx->nm, ctx->ns, ctx->own_lo, ctx->own_hi,
+                                      ctx->slow_offset, lo, hi, npairs, counts, xyz, ctx->stream, ctx->num_sms,
+                                      &ctx->launches, &ctx->err);
+}
+
+int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, void* out_host) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "no volume bound");
+    if (!out_host) return fail(ctx, TA_ERR_BAD_ARG, "null output");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    return ta::voxel_first_layer_impl(ctx->vol, ctx->elem, ctx->nf, ctx->nm, ctx->ns, background, keep_background,
+                                      out_host, ctx->stream, ctx->num_sms, &ctx->launches, &ctx->err);
+}
+
+int ta_last_timing(ta_ctx* ctx, float* scan_ms, float* pass_ms, float* h2d_ms) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (scan_ms) *scan_ms = ctx->scan_ms;
+    if (pass_ms) *pass_ms = ctx->pass_ms;
+    if (h2d_ms) *h2d_ms = ctx->h2d_ms;
+    return TA_OK;
+}
+
+int ta_launch_count(ta_ctx* ctx, uint64_t* n) {
+    if (!ctx || !n) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    *n = ctx->launches;
+    return TA_OK;
+}
+
+int ta_synth_voronoi(ta_ctx* ctx, void* device_out, int elem_bytes, int64_t n_fast, int64_t n_mid, int64_t n_slow,
+                     int64_t slow_offset, int64_t global_slow, const int32_t* seeds_host, uint32_t ncell,
+                     const int32_t* weight, int dome) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!device_out || !seeds_host || !weight || ncell == 0) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
+    if (elem_bytes != 2 && elem_bytes != 4) return fail(ctx, TA_ERR_BAD_ARG, "elem_bytes must be 2 or 4");
+    if (elem_bytes == 2 && ncell + 1 > 65535) return fail(ctx, TA_ERR_BAD_ARG, "too many cells for uint16");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ta::SynthParams P{};
+    P.nf = n_fast; P.nm = n_mid; P.ns = n_slow; P.slow_offset = slow_offset; P.global_slow = global_slow;
+    P.wf = weight[0]; P.wm = weight[1]; P.ws = weight[2];
+    P.dome = dome; P.ncell = ncell;
+    // weighted extents (fixed point 1/16 voxel) and a bin edge giving ~2 seeds per bin
+    double ext[3] = {16.0 * n_fast * P.wf, 16.0 * n_mid * P.wm, 16.0 * global_slow * P.ws};
+    double edge = cbrt(ext[0] * ext[1] * ext[2] * 2.0 / (double)ncell);
+    P.bin = (int)std::max(16.0, std::min(edge, 1.0e8));
+    P.gx = (int)(ext[0] / P.bin) + 1; P.gy = (int)(ext[1] / P.bin) + 1; P.gz = (int)(ext[2] / P.bin) + 1;
+    {
+        auto coef = [](long long dim) {
+            long long D = (long long)(0.94 * (double)dim + 0.5);
+            if (D < 1) D = 1;
+            return (1LL << 40) / (D * D);
+        };
+        P.kf = coef(n_fast); P.km = coef(n_mid); P.ks = coef(global_slow);
+    }
+    size_t nb = (size_t)P.gx * P.gy * P.gz;
+    std::vector<int> start(nb + 1, 0), order(ncell);
+    std::vector<size_t> binof(ncell);
+    for (uint32_t i = 0; i < ncell; ++i) {
+        long long x = (long long)seeds_host[i * 3 + 0] * P.wf / P.bin, y = (long long)seeds_host[i * 3 + 1] * P.wm / P.bin,
+                  z = (long long)seeds_host[i * 3 + 2] * P.ws / P.bin;
+        x = std::min<long long>(std::max<long long>(x, 0), P.gx - 1);
+        y = std::min<long long>(std::max<long long>(y, 0), P.gy - 1);
+        z = std::min<long long>(std::max<long long>(z, 0), P.gz - 1);
+        binof[i] = ((size_t)z * P.gy + y) * P.gx + x;
+        start[binof[i] + 1]++;
+    }
+    for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (uint32_t i = 0; i < ncell; ++i) order[fill[binof[i]]++] = (int)i;
+    int *d_start = nullptr, *d_order = nullptr, *d_seeds = nullptr;
+    TA_CUDA(cudaMalloc((void**)&d_start, (nb + 1) * sizeof(int)));
+    TA_CUDA(cudaMalloc((void**)&d_order, ncell * sizeof(int)));
+    TA_CUDA(cudaMalloc((void**)&d_seeds, (size_t)ncell * 3 * sizeof(int)));
+    TA_CUDA(cudaMemcpyAsync(d_start, start.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_order, order.data(), ncell * sizeof(int), cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_seeds, seeds_host, (size_t)ncell * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    int grid = ctx->num_sms * 16;
+    if (elem_bytes == 2)
+        ta::synth_voronoi_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)device_out, P, d_start, d_order, d_seeds);
+    else
+        ta::synth_voronoi_kernel<uint32_t><<<grid, 256, 0, st>>>((uint32_t*)device_out, P, d_start, d_order, d_seeds);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    TA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_start); cudaFree(d_order); cudaFree(d_seeds);
+    return TA_OK;
+}
+
+}  // extern "C"
