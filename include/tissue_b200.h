@@ -103,6 +103,9 @@ int ta_merge_pair_records(ta_ctx* ctx, const void* device_records, uint64_t n);
  * (128-bit), then a 3x3 Jacobi eigen-solve in fp64.  evals[n][3] descending; evecs[n][9] rows = eigenvectors,
  * in MEMORY axis order.  labels == NULL means rows 0..n-1 of the table. */
 int ta_inertia_from_moments(ta_ctx* ctx, const uint32_t* labels, uint64_t n, double* evals, double* evecs);
+/* The same for every row of the label table, results kept on the device (and copied out when the pointers are
+ * non-null: evals[nrows][3], evecs[nrows][9]); used after the multi-GPU merge and by the benchmark. */
+int ta_inertia_table(ta_ctx* ctx, double* evals, double* evecs);
 /* Same eigen-solve for caller-provided symmetric matrices cov[n][6] = (a00,a01,a02,a11,a12,a22). */
 int ta_inertia_eig(ta_ctx* ctx, const double* cov, uint64_t n, double* evals, double* evecs);
 

@@ -1,0 +1,158 @@
+"""`-m gpu` parity: the CUDA scan (through the C ABI and the Python mirror) against the CPU oracles.
+
+Integer outputs bit-exact; centre of mass and wall areas bit-exact floats; inertia eigen-data rtol 1e-6
+(eigenvectors up to sign, skipped inside degenerate eigenspaces) -- the tolerances north_star states.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import sia_onepass
+from oracle.sia_loops import LoopOracle
+from tests.helpers import TOY, compare_api, oracle_tables
+from tissue_analysis_b200 import SpatialImage, SpatialImageAnalysis3D
+from tissue_analysis_b200.synth import tissue_image
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore", category=UserWarning)
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+
+def assert_tables_equal(t, o):
+    n = min(t.nrows, o.nrows)
+    assert not t.count[n:].any() and not o.count[n:].any()
+    assert np.array_equal(t.count[:n], o.count[:n])
+    assert np.array_equal(t.s1[:n], o.s1[:n])
+    assert np.array_equal(t.s2[:n], o.s2[:n])
+    present = o.count[:n] > 0
+    assert np.array_equal(t.bmin[:n][present], o.bmin[:n][present])
+    assert np.array_equal(t.bmax[:n][present], o.bmax[:n][present])
+    assert np.array_equal(t.pair_lo, o.pair_lo) and np.array_equal(t.pair_hi, o.pair_hi)
+    assert np.array_equal(t.faces, o.faces)
+    assert np.array_equal(t.wall18, o.wall18)
+
+
+def both(img, **kw):
+    prod = SpatialImageAnalysis3D(img, **kw)
+    orc = LoopOracle(np.asarray(img), voxelsize=getattr(img, "voxelsize", None), **kw)
+    return prod, orc
+
+
+def test_docstring_image():
+    prod, orc = both(TOY.copy())
+    compare_api(prod, orc, eig=False)
+    assert prod.cell_wall_area(7, [2, 5]) == {(2, 7): 1.0, (5, 7): 2.0}
+
+
+def test_voronoi_dome_full_api():
+    img = tissue_image((40, 36, 30), 40, seed=11, dome=True)
+    prod, orc = both(img, background=1)
+    compare_api(prod, orc)
+
+
+def test_anisotropic_c_order_label_zero():
+    rng = np.random.default_rng(3)
+    arr = np.ascontiguousarray(np.asarray(tissue_image((36, 30, 24), 30, seed=5, weights=(2, 2, 5), dome=True)))
+    arr[rng.random(arr.shape) < 0.02] = 0
+    im = SpatialImage(arr, voxelsize=(0.2, 0.2, 0.5))
+    prod, orc = both(im, background=1, ignoredlabels=0)
+    compare_api(prod, orc)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 7, 3), (9, 1, 5), (17, 16, 8), (129, 17, 9), (8, 33, 19),
+                                   (131, 5, 3), (64, 16, 8), (256, 32, 16)])
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint32])
+def test_random_noise_tables(shape, dtype):
+    """Ragged shapes (not multiples of the brick / vector width) and many-label junctions."""
+    rng = np.random.default_rng(sum(shape))
+    arr = rng.integers(0, 23, size=shape[::-1]).astype(dtype)      # (z, y, x) C-order == x fastest
+    img = SpatialImage(arr.transpose(2, 1, 0))
+    prod = SpatialImageAnalysis3D(img, background=1)
+    assert_tables_equal(prod._tables(), oracle_tables(np.asarray(img)))
+
+
+def test_blocky_volume_tables_and_large_u32_labels():
+    rng = np.random.default_rng(7)
+    small = rng.integers(2, 400, size=(9, 11, 40))
+    arr = np.kron(small, np.ones((6, 5, 7), np.int64)).astype(np.uint32)
+    arr[arr == 17] = 3_000_000        # sparse huge label in a uint32 volume
+    prod = SpatialImageAnalysis3D(SpatialImage(arr), background=2)
+    assert_tables_equal(prod._tables(), oracle_tables(arr))
+
+
+def test_c1_config_tables_and_features():
+    """BASELINE config C1: 128^3 uint16, 500 cells (tables exact; API against the loop oracle)."""
+    img = tissue_image((128, 128, 128), 500, seed=0)
+    prod, orc = both(img)
+    assert_tables_equal(prod._tables(), oracle_tables(np.asarray(img)))
+    compare_api(prod, orc, check_wall_voxels=False, real_modes=(True,))
+
+
+def test_slab_split_equals_whole():
+    """Two z-slab 'ranks' on one GPU (ta_set_slab) + host merge == unsplit tables."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout, tables_from_memory_order
+    img = tissue_image((48, 40, 37), 60, seed=4, dome=True)
+    view, ax = memory_layout(img)
+    ns = view.shape[0]
+    cut = 19
+    parts = []
+    for lo, hi in ((0, cut), (cut, ns)):
+        b0, b1 = max(lo - 1, 0), min(hi + 1, ns)
+        ctx = _native.Context()
+        ctx.bind_host(np.ascontiguousarray(view[b0:b1]))
+        ctx.set_slab(lo - b0, hi - b0, b0)
+        ctx.run_pass()
+        parts.append((ctx.label_table(), ctx.pair_table()))
+        ctx.close()
+    (c0, s10, s20, bb0), (lo0, hi0, f0, w0) = parts[0]
+    (c1, s11, s21, bb1), (lo1, hi1, f1, w1) = parts[1]
+    bbox = np.concatenate([np.minimum(bb0[:, :3], bb1[:, :3]), np.maximum(bb0[:, 3:], bb1[:, 3:])], axis=1)
+    merged = sia_onepass.merge_pair_tables([dict(lo=lo0, hi=hi0, faces=f0.astype(np.int64), wall18=w0.astype(np.int64)),
+                                            dict(lo=lo1, hi=hi1, faces=f1.astype(np.int64), wall18=w1.astype(np.int64))])
+    t = tables_from_memory_order(img.shape, ax, c0 + c1, s10 + s11, s20 + s21, bbox, merged["lo"], merged["hi"],
+                                 merged["faces"], merged["wall18"])
+    assert_tables_equal(t, oracle_tables(np.asarray(img)))
+
+
+def test_native_inertia_eig_against_lapack():
+    from tissue_analysis_b200 import _native
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(500, 3, 3))
+    cov = a @ a.transpose(0, 2, 1)
+    cov[:20] = np.diag([3.0, 1.0, 0.0])            # already diagonal, zero eigenvalue
+    cov6 = np.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], axis=1)
+    ctx = _native.Context()
+    evals, evecs = ctx.inertia_eig(cov6)
+    ctx.close()
+    w = np.linalg.eigvalsh(cov)[:, ::-1]
+    np.testing.assert_allclose(evals, w, rtol=1e-10, atol=1e-12)
+    recon = np.einsum("nij,ni,nik->njk", evecs, evals, evecs)
+    np.testing.assert_allclose(recon, cov, rtol=1e-9, atol=1e-10)
+
+
+def test_errors_are_loud():
+    from tissue_analysis_b200 import _native
+    ctx = _native.Context()
+    with pytest.raises(_native.NativeError):
+        ctx.run_pass()                               # no volume bound
+    arr = np.zeros((4, 4, 4), np.uint16)
+    ctx.bind_host(arr)
+    with pytest.raises(_native.NativeError):
+        ctx.label_table()                            # no pass yet
+    ctx.close()
+
+
+def test_device_generator_equals_numpy_generator():
+    from tissue_analysis_b200.synth import voronoi_device, voronoi_numpy
+    for shape, ncell, w, dome, dt in (((40, 48, 56), 90, (1, 1, 1), True, "uint16"),
+                                      ((33, 20, 70), 300, (5, 2, 2), False, "uint32"),
+                                      ((16, 16, 16), 3, (1, 1, 1), True, "uint16")):
+        dev = voronoi_device(shape, ncell, 7, w, dome, dt).cpu().numpy()
+        ref = voronoi_numpy(shape, ncell, 7, w, dome, np.dtype(dt), k=16)
+        assert np.array_equal(dev, ref), (shape, ncell)
+    # slab generation == the same planes of the whole volume
+    whole = voronoi_device((40, 48, 56), 90, 7, (1, 1, 1), True, "uint16").cpu().numpy()
+    part = voronoi_device((40, 48, 56), 90, 7, (1, 1, 1), True, "uint16", zslice=(13, 29)).cpu().numpy()
+    assert np.array_equal(part, whole[13:29])

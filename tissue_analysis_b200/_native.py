@@ -26,7 +26,7 @@ EXPORTS = [
     "ta_version", "ta_ctx_create", "ta_ctx_destroy", "ta_last_error", "ta_set_stream", "ta_bind_volume",
     "ta_set_slab", "ta_run_pass", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
-    "ta_inertia_from_moments", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
+    "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
     "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
 ]
 
@@ -68,6 +68,7 @@ def load():
     lib.ta_pair_records_device.argtypes = [vp, P(vp), P(u64)]
     lib.ta_merge_pair_records.argtypes = [vp, vp, u64]
     lib.ta_inertia_from_moments.argtypes = [vp, vp, u64, vp, vp]
+    lib.ta_inertia_table.argtypes = [vp, vp, vp]
     lib.ta_inertia_eig.argtypes = [vp, vp, u64, vp, vp]
     lib.ta_wall_voxel_coords.argtypes = [vp, vp, vp, u64, vp, vp]
     lib.ta_voxel_first_layer.argtypes = [vp, u32, ci, vp]
@@ -186,6 +187,16 @@ class Context(object):
         evals = np.empty((n, 3), np.float64)
         evecs = np.empty((n, 3, 3), np.float64)
         self._check(self.lib.ta_inertia_from_moments(self.h, _ptr(labels), n, _ptr(evals), _ptr(evecs)))
+        return evals, evecs
+
+    def inertia_table(self, fetch=True, nrows=None):
+        """Eigen-solve every table row on the device; ``fetch=False`` leaves the result resident."""
+        if not fetch:
+            self._check(self.lib.ta_inertia_table(self.h, None, None))
+            return None
+        evals = np.empty((nrows, 3), np.float64)
+        evecs = np.empty((nrows, 3, 3), np.float64)
+        self._check(self.lib.ta_inertia_table(self.h, _ptr(evals), _ptr(evecs)))
         return evals, evecs
 
     def inertia_eig(self, cov6):

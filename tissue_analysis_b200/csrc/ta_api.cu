@@ -42,6 +42,9 @@ struct ta_ctx {
     size_t records_alloc = 0;
     uint64_t nrecords = 0;
     bool have_tables = false;
+    double* d_evals = nullptr;
+    double* d_evecs = nullptr;
+    size_t eig_alloc_rows = 0;
 
     cudaEvent_t ev[6] = {};
     float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
@@ -121,6 +124,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->status); cudaFree(ctx->counters);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
+    cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -213,7 +217,6 @@ static int build_records(ta_ctx* ctx) {
     }
     TA_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, need, ctx->sort_keys[0], ctx->sort_keys[1],
                                             ctx->sort_vals[0], ctx->sort_vals[1], (int)n, 0, 64, st));
-    ctx->launches += 4;   // CUB radix passes (library kernels; not counted as ours in bench)
     int rc = ensure(ctx, &ctx->records, &ctx->records_alloc, (size_t)n * ta::REC_WORDS);
     if (rc) return rc;
     ta::gather_records_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pt, ctx->sort_keys[1], ctx->sort_vals[1], n,
@@ -446,6 +449,29 @@ int ta_inertia_from_moments(ta_ctx* ctx, const uint32_t* labels, uint64_t n, dou
     TA_CUDA(cudaMemcpyAsync(evecs, dv, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
     cudaFree(dl); cudaFree(dv); cudaFree(dw);
+    return TA_OK;
+}
+
+int ta_inertia_table(ta_ctx* ctx, double* evals, double* evecs) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t n = ctx->lt.nrows;
+    if (ctx->eig_alloc_rows < n) {
+        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
+        ctx->d_evals = ctx->d_evecs = nullptr; ctx->eig_alloc_rows = 0;
+        TA_CUDA(cudaMalloc((void**)&ctx->d_evals, n * 3 * sizeof(double)));
+        TA_CUDA(cudaMalloc((void**)&ctx->d_evecs, n * 9 * sizeof(double)));
+        ctx->eig_alloc_rows = n;
+    }
+    ta::inertia_from_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->lt, nullptr, n, ctx->d_evals,
+                                                                               ctx->d_evecs);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    if (evals) TA_CUDA(cudaMemcpyAsync(evals, ctx->d_evals, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (evecs) TA_CUDA(cudaMemcpyAsync(evecs, ctx->d_evecs, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (evals || evecs) TA_CUDA(cudaStreamSynchronize(st));
     return TA_OK;
 }
 

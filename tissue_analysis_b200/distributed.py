@@ -1,0 +1,141 @@
+"""z-slab sharding of one label volume over the GPUs of a node (one process per GPU, torch.distributed).
+
+The reference is a single Python process (no parallelism of any kind: SURVEY.md section 2); this is the multi-GPU
+form of the same pass.  Every output of the scan is a commutative reduction, so a rank needs only its planes
+plus one halo plane on each side:
+
+  1. halo exchange     boundary planes to both neighbours (NCCL send/recv over NVLink; 2 MiB per face at C3)
+  2. local pass        ownership rules of ``ta_set_slab``: a face belongs to the rank owning its lower voxel, an
+                       18-connected wall voxel to the rank owning the voxel
+  3. label table       all_reduce SUM of the exact u64 sums, MIN / MAX of the bounding boxes
+  4. pair table        all_gather of the packed records (variable length -> sizes first) and a device hash
+                       sum-merge (``ta_merge_pair_records``) on every rank
+
+The collective helpers below act on plain tensors, so the world_size-2 ``gloo`` tests drive them on the CPU with
+oracle tables; on GPUs they act directly on the library's device buffers (zero copy).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REC_WORDS = 9
+
+
+def partition_planes(n_slow, world):
+    """Contiguous, balanced plane ranges: rank r owns [b[r], b[r+1])."""
+    return [(n_slow * r) // world for r in range(world + 1)]
+
+
+def exchange_halo_planes(buf, own_lo, own_hi, rank, world):
+    """``buf`` holds [halo?][owned planes][halo?] along dim 0.  Sends the first / last owned plane to the lower /
+    upper neighbour and receives their boundary planes into the halo slots."""
+    if world == 1:
+        return
+    ops, keep = [], []
+    raw = buf.view(torch.uint8)
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, raw[own_lo], rank - 1))
+        ops.append(dist.P2POp(dist.irecv, raw[own_lo - 1], rank - 1))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, raw[own_hi - 1], rank + 1))
+        ops.append(dist.P2POp(dist.irecv, raw[own_hi], rank + 1))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    del keep
+
+
+def allreduce_label_tables(count, s1, s2, bmin, bmax):
+    """In place: sums are exact integers (two's complement SUM is u64 addition), boxes are MIN / MAX."""
+    dist.all_reduce(count, op=dist.ReduceOp.SUM)
+    dist.all_reduce(s1, op=dist.ReduceOp.SUM)
+    dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+    dist.all_reduce(bmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+
+
+def allgather_pair_records(records, world):
+    """records: int32[n, 9] (this rank's packed pair rows) -> int32[sum n_r, 9] on every rank."""
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    padded = torch.zeros((cap, REC_WORDS), dtype=records.dtype, device=records.device)
+    padded[:records.shape[0]] = records
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded)
+    return torch.cat([g[:s] for g, s in zip(gathered, sizes)], dim=0)
+
+
+class _DeviceView(object):
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3)
+
+
+def device_tensor(ptr, shape, typestr):
+    """Zero-copy torch view of a library-owned device buffer."""
+    return torch.as_tensor(_DeviceView(ptr, shape, typestr), device="cuda")
+
+
+class SlabScan(object):
+    """One rank of the z-slab sharded scan.  ``global_shape`` is (slow, mid, fast)."""
+
+    def __init__(self, global_shape, dtype=torch.uint16, rank=None, world=None, device=None):
+        from . import _native
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.global_shape = tuple(int(v) for v in global_shape)
+        ns, nm, nf = self.global_shape
+        b = partition_planes(ns, self.world)
+        self.g_lo, self.g_hi = b[self.rank], b[self.rank + 1]
+        self.has_lo, self.has_hi = self.rank > 0, self.rank < self.world - 1
+        self.own_lo = 1 if self.has_lo else 0
+        self.own_hi = self.own_lo + (self.g_hi - self.g_lo)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.buf = torch.zeros((self.own_hi + (1 if self.has_hi else 0), nm, nf), dtype=dtype, device=self.device)
+        self.elem = self.buf.element_size()
+        self.ctx = _native.Context(self.device.index)
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._native = _native
+
+    def owned(self):
+        """View of the owned planes (fill it by upload or by the device generator)."""
+        return self.buf[self.own_lo:self.own_hi]
+
+    def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False):
+        ns, nm, nf = self.buf.shape
+        exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.bind_device(self.buf.data_ptr(), self.elem, nf, nm, ns, keepalive=self.buf)
+        self.ctx.set_slab(self.own_lo, self.own_hi, self.g_lo - self.own_lo)
+        self.ctx.run_pass(flags, max_label_hint, pair_capacity_hint)
+        if self.world > 1:
+            self.merge()
+        if inertia:
+            self.ctx.inertia_table(fetch=False)
+
+    def merge(self):
+        (p_count, p_s1, p_s2, p_bmin, p_bmax), n = self.ctx.label_table_device()
+        allreduce_label_tables(device_tensor(p_count, (n,), "<i8"), device_tensor(p_s1, (n * 3,), "<i8"),
+                               device_tensor(p_s2, (n * 6,), "<i8"), device_tensor(p_bmin, (n * 3,), "<i4"),
+                               device_tensor(p_bmax, (n * 3,), "<i4"))
+        p_rec, n_rec = self.ctx.pair_records_device()
+        if n_rec:
+            mine = device_tensor(p_rec, (n_rec, REC_WORDS), "<i4")
+        else:
+            mine = torch.zeros((0, REC_WORDS), dtype=torch.int32, device=self.device)
+        allrec = allgather_pair_records(mine, self.world).contiguous()
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.merge_pair_records(allrec.data_ptr(), allrec.shape[0])
+
+    def tables(self, ax_of_mem=(2, 1, 0)):
+        """Merged tables as ScanTables (API shape = global (slow, mid, fast) unless ``ax_of_mem`` says otherwise)."""
+        from .engine import tables_from_memory_order
+        count, s1, s2, bbox = self.ctx.label_table()
+        lo, hi, faces, wall = self.ctx.pair_table()
+        ns, nm, nf = self.global_shape
+        mem_dims = (nf, nm, ns)
+        shape_api = [0, 0, 0]
+        for k in range(3):
+            shape_api[ax_of_mem[k]] = mem_dims[k]
+        return tables_from_memory_order(tuple(shape_api), ax_of_mem, count, s1, s2, bbox, lo, hi, faces, wall)
