@@ -1,17 +1,22 @@
 // The single streaming pass over the label volume (sm_100a).
 //
 // Work unit: a brick of BF x BM x BS voxels (BF = 16 segments of 16 bytes) staged in shared memory with a
-// one-voxel halo (clamped at the buffer edges, which reproduces the reference's "image border contributes
-// nothing" rule: a clamped neighbour equals an in-bounds 6/18-neighbour or the voxel itself).
-// Thread (fseg, m) owns one 16-byte segment column and marches along s.
+// one-voxel halo, clamped at the buffer edges (a clamped neighbour equals an in-bounds 6/18-neighbour or the
+// voxel itself, which reproduces the reference's "the image border contributes nothing" rule).
 //
-// Hierarchy of paths, cheapest first:
-//   1. interior segment (the 3x3 rows x (SEG+2) voxels around it hold one label): run-length accumulation of
-//      (count, sum s, sum s^2) in registers, closed-form f/m moments on flush; no pair work at all.
-//   2. boundary segment: per-lane moments by runs, per-lane 6-face compares and 18-neighbour distinct-label
-//      dedup into a per-brick shared-memory pair hash.
-// Per-brick shared tables (labels: u32 sums in brick-local coordinates; pairs: 7 u32 counters) are flushed to
-// the global dense label table (u64 REDs) and the global open-addressing pair table once per brick.
+// Phases per brick (every phase keeps whole warps busy; irregular work is compacted into worklists first):
+//   A  stage brick + halo: 128-bit streaming loads -> shared tile.
+//   B  per row-segment uniformity code: the label if the SEG+2 voxels (segment + f-halo) are equal.
+//   C1 march: thread (fseg, m) walks s.  Uniform segments extend a register run (count, sum s, sum s^2; f/m
+//      moments are closed forms on flush); mixed segments add per-lane runs.  Segments whose 3x3 rows are not one
+//      label go to the SEGMENT worklist.
+//   C2 per listed segment, SIMD on the packed lanes: OR of XORs of the segment with its 18 neighbour vectors
+//      (f-shifted ones built with funnel shifts) -> exact "has a different 18-neighbour" flag per voxel; flagged
+//      voxels go to the VOXEL worklist.
+//   D  per listed voxel: 18 neighbour labels -> first other label + "only one other label" test; the common case
+//      is ONE shared-memory hash lookup and <= 4 packed 16-bit counter adds (wall18 + the +f/+m/+s faces);
+//      junction voxels take the exact dedup path.
+//   F  flush the per-brick label table (u32 brick-local sums -> u64 global REDs) and pair table.
 #pragma once
 #include "ta_common.cuh"
 
@@ -24,16 +29,19 @@ constexpr int NTHREADS = NFS * BM;      // one thread per segment column
 constexpr int LT_SLOTS = 64;            // per-brick label slots
 constexpr int LT_FIELDS = 16;           // n, sf, sm, ss, sff, sfm, sfs, smm, sms, sss, min f/m/s, max f/m/s
 constexpr int PT_SLOTS = 256;           // per-brick pair slots
+constexpr int PT_WORDS = 4;             // packed 16-bit counters: [w18|f0] [f1|f2] [f3|f4] [f5|-]
 constexpr int TILE_ROWS = (BS + 2) * (BM + 2);
 constexpr int TILE_SEGS = TILE_ROWS * (NFS + 2);
+constexpr int SEGLIST_CAP = NFS * BM * BS;
+constexpr int VOXLIST_CAP = NTHREADS * 8;
 
 template <typename T> struct Vox;
-template <> struct Vox<uint16_t> { static constexpr int SEG = 8; };
-template <> struct Vox<uint32_t> { static constexpr int SEG = 4; };
+template <> struct Vox<uint16_t> { static constexpr int SEG = 8; static constexpr int LOG_SEG = 3; };
+template <> struct Vox<uint32_t> { static constexpr int SEG = 4; static constexpr int LOG_SEG = 2; };
 
 constexpr size_t scan_smem_bytes() {
     return (size_t)TILE_SEGS * 16 + (size_t)TILE_ROWS * NFS * 4 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 +
-           PT_SLOTS * 8 + PT_SLOTS * TA_PAIR_STRIDE * 4 + 16;
+           PT_SLOTS * 8 + PT_SLOTS * PT_WORDS * 4 + SEGLIST_CAP * 2 + VOXLIST_CAP * 2 + 32;
 }
 
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
@@ -44,13 +52,15 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
 }
 
 struct BrickShared {
-    uint4* tile;          // [TILE_SEGS]
-    uint32_t* codes;      // [TILE_ROWS * NFS]
-    uint32_t* lt_key;     // [LT_SLOTS]
-    uint32_t* lt_val;     // [LT_SLOTS * LT_FIELDS]
-    u64* pt_key;          // [PT_SLOTS]
-    uint32_t* pt_val;     // [PT_SLOTS * TA_PAIR_STRIDE]
-    unsigned int* next;   // [1] brick index broadcast
+    uint4* tile;            // [TILE_SEGS]
+    uint32_t* codes;        // [TILE_ROWS * NFS]
+    uint32_t* lt_key;       // [LT_SLOTS]
+    uint32_t* lt_val;       // [LT_SLOTS * LT_FIELDS]
+    u64* pt_key;            // [PT_SLOTS]
+    uint32_t* pt_val;       // [PT_SLOTS * PT_WORDS]
+    unsigned short* seglist;   // [SEGLIST_CAP]
+    unsigned short* voxlist;   // [VOXLIST_CAP]
+    unsigned int* ctr;      // [0] next brick, [1] nseg, [2..3] nvox ping-pong
 };
 
 // ---- global flush of one label's brick-local sums -----------------------------------------------------------
@@ -101,34 +111,127 @@ __device__ __forceinline__ void label_add(const BrickShared& sh, const LabelTabl
     for (int i = 13; i < 16; ++i) atomicMax(&d[i], v[i]);
 }
 
-// ---- per-brick pair accumulation -----------------------------------------------------------------------------
-__device__ __forceinline__ void pair_add(const BrickShared& sh, const PairTable& pt, uint32_t a, uint32_t b,
-                                         int field, uint32_t n) {
-    u64 key = ta_pair_key(a, b);
-    uint32_t slot = ta_hash64(key) & (PT_SLOTS - 1);
+// ---- per-brick pair accumulation (packed 16-bit counters; a brick has < 65536 voxels) ------------------------
+// field 6 = wall18, fields 0..5 = directional faces.  idx = field+1 (wall18 -> 0): word idx>>1, half idx&1.
+__device__ __forceinline__ int pair_slot_shared(const BrickShared& sh, u64 key) {
+    uint32_t h = ((uint32_t)(key >> 32) * 0x9E3779B1u) ^ ((uint32_t)key * 0x85EBCA77u);
+    uint32_t slot = h >> 24;
     for (int probe = 0; probe < PT_SLOTS; ++probe) {
         u64 k = *((volatile u64*)&sh.pt_key[slot]);
-        if (k == key) { atomicAdd(&sh.pt_val[slot * TA_PAIR_STRIDE + field], n); return; }
+        if (k == key) return (int)slot;
         if (k == TA_EMPTY64) {
             u64 old = atomicCAS(&sh.pt_key[slot], TA_EMPTY64, key);
-            if (old == TA_EMPTY64 || old == key) {
-                atomicAdd(&sh.pt_val[slot * TA_PAIR_STRIDE + field], n);
-                return;
-            }
+            if (old == TA_EMPTY64 || old == key) return (int)slot;
         }
         slot = (slot + 1) & (PT_SLOTS - 1);
     }
-    ta_pair_add(pt, key, field, n);   // brick table full: straight to the global table
+    return -1;
+}
+
+__device__ __forceinline__ void pair_add_packed(const BrickShared& sh, const PairTable& pt, u64 key,
+                                                const uint32_t inc[PT_WORDS]) {
+    int slot = pair_slot_shared(sh, key);
+    if (slot >= 0) {
+#pragma unroll
+        for (int w = 0; w < PT_WORDS; ++w) if (inc[w]) atomicAdd(&sh.pt_val[slot * PT_WORDS + w], inc[w]);
+        return;
+    }
+    int g = ta_pair_slot(pt, key);          // brick table full: straight to the global table
+    if (g < 0) return;
+    uint32_t* v = &pt.vals[(size_t)g * TA_PAIR_STRIDE];
+#pragma unroll
+    for (int idx = 0; idx < 7; ++idx) {
+        uint32_t n = (inc[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+        if (n) atomicAdd(&v[idx == 0 ? 6 : idx - 1], n);
+    }
+}
+
+__device__ __forceinline__ void pair_add(const BrickShared& sh, const PairTable& pt, uint32_t a, uint32_t b,
+                                         int field, uint32_t n) {
+    uint32_t inc[PT_WORDS] = {0, 0, 0, 0};
+    int idx = field == 6 ? 0 : field + 1;
+    inc[idx >> 1] = n << ((idx & 1) * 16);
+    pair_add_packed(sh, pt, ta_pair_key(a, b), inc);
 }
 
 __device__ __forceinline__ uint32_t sumsq_upto(uint32_t k) { return k * (k + 1) * (2 * k + 1) / 6; }  // 0..k
+
+// ---- phase C2: exact "has a different 18-neighbour" bit per voxel of one segment ---------------------------
+// t = tile vector index of the centre segment; returns a SEG-bit mask.
+template <typename T> struct Boundary;
+
+template <> struct Boundary<uint16_t> {
+    static __device__ __forceinline__ void cross(uint32_t acc[4], const uint4& C, const uint4* tile, int t,
+                                                 bool unshifted) {
+        const uint4 R = tile[t];
+        const uint32_t e0 = (uint32_t)(reinterpret_cast<const unsigned short*>(tile + t)[-1]) << 16;
+        const uint32_t e5 = reinterpret_cast<const unsigned short*>(tile + t + 1)[0];
+        const uint32_t s0 = __funnelshift_r(e0, R.x, 16), s1 = __funnelshift_r(R.x, R.y, 16),
+                       s2 = __funnelshift_r(R.y, R.z, 16), s3 = __funnelshift_r(R.z, R.w, 16),
+                       s4 = __funnelshift_r(R.w, e5, 16);
+        acc[0] |= (C.x ^ s0) | (C.x ^ s1);
+        acc[1] |= (C.y ^ s1) | (C.y ^ s2);
+        acc[2] |= (C.z ^ s2) | (C.z ^ s3);
+        acc[3] |= (C.w ^ s3) | (C.w ^ s4);
+        if (unshifted) { acc[0] |= C.x ^ R.x; acc[1] |= C.y ^ R.y; acc[2] |= C.z ^ R.z; acc[3] |= C.w ^ R.w; }
+    }
+    static __device__ __forceinline__ void diag(uint32_t acc[4], const uint4& C, const uint4* tile, int t) {
+        const uint4 R = tile[t];
+        acc[0] |= C.x ^ R.x; acc[1] |= C.y ^ R.y; acc[2] |= C.z ^ R.z; acc[3] |= C.w ^ R.w;
+    }
+    static __device__ __forceinline__ uint32_t mask(const uint32_t acc[4]) {
+        const uint32_t one = 0x00010001u;
+        uint32_t tt = __vminu2(acc[0], one) | (__vminu2(acc[1], one) << 2) | (__vminu2(acc[2], one) << 4) |
+                      (__vminu2(acc[3], one) << 6);
+        return (tt & 0x55u) | ((tt >> 15) & 0xAAu);
+    }
+};
+
+template <> struct Boundary<uint32_t> {
+    static __device__ __forceinline__ void cross(uint32_t acc[4], const uint4& C, const uint4* tile, int t,
+                                                 bool unshifted) {
+        const uint4 R = tile[t];
+        const uint32_t e0 = reinterpret_cast<const uint32_t*>(tile + t)[-1];
+        const uint32_t e5 = reinterpret_cast<const uint32_t*>(tile + t + 1)[0];
+        acc[0] |= (C.x ^ e0) | (C.x ^ R.y);
+        acc[1] |= (C.y ^ R.x) | (C.y ^ R.z);
+        acc[2] |= (C.z ^ R.y) | (C.z ^ R.w);
+        acc[3] |= (C.w ^ R.z) | (C.w ^ e5);
+        if (unshifted) { acc[0] |= C.x ^ R.x; acc[1] |= C.y ^ R.y; acc[2] |= C.z ^ R.z; acc[3] |= C.w ^ R.w; }
+    }
+    static __device__ __forceinline__ void diag(uint32_t acc[4], const uint4& C, const uint4* tile, int t) {
+        const uint4 R = tile[t];
+        acc[0] |= C.x ^ R.x; acc[1] |= C.y ^ R.y; acc[2] |= C.z ^ R.z; acc[3] |= C.w ^ R.w;
+    }
+    static __device__ __forceinline__ uint32_t mask(const uint32_t acc[4]) {
+        return (acc[0] ? 1u : 0u) | (acc[1] ? 2u : 0u) | (acc[2] ? 4u : 0u) | (acc[3] ? 8u : 0u);
+    }
+};
+
+// k-th offset of the 18-neighbourhood (1 <= |df|+|dm|+|ds| <= 2) in tile elements; rare-path helper
+template <int ROWE, int PLANEE>
+__device__ __noinline__ int neighbour_offset(int k) {
+    int c = 0;
+    for (int i = 0; i < 27; ++i) {
+        int df = i % 3 - 1, dm = (i / 3) % 3 - 1, ds = i / 9 - 1;
+        int l1 = abs(df) + abs(dm) + abs(ds);
+        if (l1 >= 1 && l1 <= 2) {
+            if (c == k) return ds * PLANEE + dm * ROWE + df;
+            ++c;
+        }
+    }
+    return 0;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2)
 scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     constexpr int SEG = Vox<T>::SEG;
+    constexpr int LOG_SEG = Vox<T>::LOG_SEG;
     constexpr int ROWE = (NFS + 2) * SEG;          // elements per tile row
     constexpr int PLANEE = (BM + 2) * ROWE;        // elements per tile plane
+    constexpr int ROWV = NFS + 2;                  // vectors per tile row
+    constexpr int PLANEV = (BM + 2) * ROWV;        // vectors per tile plane
     constexpr int BF = NFS * SEG;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -139,13 +242,17 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     sh.lt_val = sh.lt_key + LT_SLOTS;
     sh.pt_key = reinterpret_cast<u64*>(sh.lt_val + LT_SLOTS * LT_FIELDS);
     sh.pt_val = reinterpret_cast<uint32_t*>(sh.pt_key + PT_SLOTS);
-    sh.next = reinterpret_cast<unsigned int*>(sh.pt_val + PT_SLOTS * TA_PAIR_STRIDE);
+    sh.seglist = reinterpret_cast<unsigned short*>(sh.pt_val + PT_SLOTS * PT_WORDS);
+    sh.voxlist = sh.seglist + SEGLIST_CAP;
+    sh.ctr = reinterpret_cast<unsigned int*>(sh.voxlist + VOXLIST_CAP);
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const T* vol = reinterpret_cast<const T*>(P.vol);
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
+    const bool do_pairs = do_p6 || do_w18;
 
     // reset the per-brick tables once; the flush at the end of each brick re-arms them
     for (int i = tid; i < LT_SLOTS; i += NTHREADS) sh.lt_key[i] = TA_EMPTY32;
@@ -154,20 +261,21 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         sh.lt_val[i] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
     }
     for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = TA_EMPTY64;
-    for (int i = tid; i < PT_SLOTS * TA_PAIR_STRIDE; i += NTHREADS) sh.pt_val[i] = 0u;
+    for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
 
     for (;;) {
-        if (tid == 0) *sh.next = atomicAdd(P.brick_counter, 1u);
+        if (tid == 0) { sh.ctr[0] = atomicAdd(P.brick_counter, 1u); sh.ctr[1] = 0u; sh.ctr[2] = 0u; sh.ctr[3] = 0u; }
         __syncthreads();
-        const unsigned int brick = *sh.next;
+        const unsigned int brick = sh.ctr[0];
         if (brick >= total) break;
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const long long F0 = (long long)bf * BF, M0 = (long long)bm * BM, S0 = P.own_lo + (long long)bs * BS;
+        const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)(S0 + P.slow_offset);
 
         // ---- phase A: stage brick + halo (clamped) ------------------------------------------------------------
         for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-            int fs = i % (NFS + 2) - 1;
-            int r = i / (NFS + 2);
+            int fs = i % ROWV - 1;
+            int r = i / ROWV;
             int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
             long long gs = min(max(S0 + s, 0LL), P.ns - 1);
             long long gm = min(max(M0 + m, 0LL), P.nm - 1);
@@ -197,7 +305,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         for (int i = tid; i < TILE_ROWS * NFS; i += NTHREADS) {
             int fs = i % NFS, r = i / NFS;
             const T* rp = tileT + r * ROWE + (fs + 1) * SEG;
-            uint4 v = sh.tile[r * (NFS + 2) + fs + 1];
+            uint4 v = sh.tile[r * ROWV + fs + 1];
             uint32_t l = rp[0];
             uint32_t pat = (SEG == 8) ? (l | (l << 16)) : l;
             bool uni = (v.x == pat) & (v.y == pat) & (v.z == pat) & (v.w == pat) &
@@ -206,7 +314,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         }
         __syncthreads();
 
-        // ---- phase C: march ---------------------------------------------------------------------------------------
+        // ---- phase C1: march (moments, interior test, segment worklist) -------------------------------------------
         {
             const int fs = tid % NFS, m = tid / NFS;
             const long long gf0 = F0 + (long long)fs * SEG, gm = M0 + m;
@@ -214,7 +322,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             const int nvalid = col_valid ? (int)min((long long)SEG, P.nf - gf0) : 0;
             const int smax = (int)min((long long)BS, P.own_hi - S0);
             const uint32_t lf0 = fs * SEG;
-            const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)(S0 + P.slow_offset);
 
             uint32_t run_label = TA_EMPTY32, run_cnt = 0, run_s = 0, run_ss = 0, run_first = 0;
             auto flush_run = [&](int s_end) {
@@ -231,105 +338,203 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 label_add(sh, lt, pt.status, run_label, v, gF0, gM0, gS0);
                 run_cnt = 0; run_s = 0; run_ss = 0;
             };
-
             auto tcode = [&](int s) {
                 int base = ((s + 1) * (BM + 2) + (m + 1)) * NFS + fs;
                 uint32_t e0 = sh.codes[base - NFS], e1 = sh.codes[base], e2 = sh.codes[base + NFS];
                 return (e0 == e1 && e1 == e2) ? e1 : TA_EMPTY32;
             };
 
-            if (col_valid && smax > 0) {
-                uint32_t t_prev = tcode(-1), t_cur = tcode(0);
-                for (int s = 0; s < smax; ++s) {
-                    const uint32_t t_next = tcode(s + 1);
-                    const uint32_t e_c = sh.codes[((s + 1) * (BM + 2) + (m + 1)) * NFS + fs];
-                    const bool interior = (t_cur != TA_EMPTY32) && (t_prev == t_cur) && (t_next == t_cur);
-                    const T* cp = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG;
+            uint32_t t_prev = tcode(-1), t_cur = tcode(0);
+            for (int s = 0; s < BS; ++s) {
+                const bool active = col_valid && (s < smax);
+                const uint32_t t_next = tcode(s + 1);
+                const uint32_t e_c = sh.codes[((s + 1) * (BM + 2) + (m + 1)) * NFS + fs];
+                const bool interior = (t_cur != TA_EMPTY32) && (t_prev == t_cur) && (t_next == t_cur);
 
-                    if (do_mom) {
-                        if (e_c != TA_EMPTY32 && nvalid == SEG) {
-                            if (e_c != run_label) { flush_run(s); run_label = e_c; run_first = s; }
-                            run_cnt += 1; run_s += s; run_ss += s * s;
-                        } else {
-                            flush_run(s);
-                            run_label = TA_EMPTY32;
-                            int j0 = 0;
-                            while (j0 < nvalid) {
-                                uint32_t L = cp[j0];
-                                int j1 = j0 + 1;
-                                while (j1 < nvalid && (uint32_t)cp[j1] == L) ++j1;
-                                uint32_t len = j1 - j0;
-                                uint32_t sj = (uint32_t)(j0 + j1 - 1) * len / 2;
-                                uint32_t sjj = sumsq_upto(j1 - 1) - (j0 > 0 ? sumsq_upto(j0 - 1) : 0u);
-                                uint32_t v[LT_FIELDS];
-                                v[0] = len; v[1] = len * lf0 + sj; v[2] = len * m; v[3] = len * s;
-                                v[4] = len * lf0 * lf0 + 2 * lf0 * sj + sjj; v[5] = m * v[1]; v[6] = s * v[1];
-                                v[7] = len * m * m; v[8] = len * m * s; v[9] = len * s * s;
-                                v[10] = lf0 + j0; v[11] = m; v[12] = s;
-                                v[13] = lf0 + j1 - 1; v[14] = m; v[15] = s;
-                                label_add(sh, lt, pt.status, L, v, gF0, gM0, gS0);
-                                j0 = j1;
-                            }
+                if (do_mom && active) {
+                    if (e_c != TA_EMPTY32 && nvalid == SEG) {
+                        if (e_c != run_label) { flush_run(s); run_label = e_c; run_first = s; }
+                        run_cnt += 1; run_s += s; run_ss += s * s;
+                    } else {
+                        flush_run(s);
+                        run_label = TA_EMPTY32;
+                        const T* cp = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG;
+                        int j0 = 0;
+                        while (j0 < nvalid) {
+                            uint32_t L = cp[j0];
+                            int j1 = j0 + 1;
+                            while (j1 < nvalid && (uint32_t)cp[j1] == L) ++j1;
+                            uint32_t len = j1 - j0;
+                            uint32_t sj = (uint32_t)(j0 + j1 - 1) * len / 2;
+                            uint32_t sjj = sumsq_upto(j1 - 1) - (j0 > 0 ? sumsq_upto(j0 - 1) : 0u);
+                            uint32_t v[LT_FIELDS];
+                            v[0] = len; v[1] = len * lf0 + sj; v[2] = len * m; v[3] = len * s;
+                            v[4] = len * lf0 * lf0 + 2 * lf0 * sj + sjj; v[5] = m * v[1]; v[6] = s * v[1];
+                            v[7] = len * m * m; v[8] = len * m * s; v[9] = len * s * s;
+                            v[10] = lf0 + j0; v[11] = m; v[12] = s;
+                            v[13] = lf0 + j1 - 1; v[14] = m; v[15] = s;
+                            label_add(sh, lt, pt.status, L, v, gF0, gM0, gS0);
+                            j0 = j1;
                         }
                     }
-
-                    if (!interior && (do_p6 || do_w18)) {
-                        for (int j = 0; j < nvalid; ++j) {
-                            const T* p = cp + j;
-                            const uint32_t a = p[0];
-                            if (do_p6) {
-                                uint32_t w = p[1];
-                                if (w != a) pair_add(sh, pt, a, w, a < w ? 0 : 1, 1u);
-                                w = p[ROWE];
-                                if (w != a) pair_add(sh, pt, a, w, a < w ? 2 : 3, 1u);
-                                w = p[PLANEE];
-                                if (w != a) pair_add(sh, pt, a, w, a < w ? 4 : 5, 1u);
-                            }
-                            if (do_w18) {
-                                const int offs[18] = {
-                                    -1, 1, -ROWE, ROWE, -PLANEE, PLANEE,
-                                    -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
-                                    -PLANEE - 1, -PLANEE + 1, PLANEE - 1, PLANEE + 1,
-                                    -PLANEE - ROWE, -PLANEE + ROWE, PLANEE - ROWE, PLANEE + ROWE};
-                                uint32_t d0 = a, d1 = a, d2 = a, d3 = a;
-                                int nd = 0;
-#pragma unroll
-                                for (int k = 0; k < 18; ++k) {
-                                    uint32_t b = p[offs[k]];
-                                    if (b != a && b != d0 && b != d1 && b != d2 && b != d3) {
-                                        if (nd == 0) d0 = b; else if (nd == 1) d1 = b;
-                                        else if (nd == 2) d2 = b; else if (nd == 3) d3 = b;
-                                        ++nd;
-                                    }
-                                }
-                                if (nd <= 4) {
-                                    if (nd > 0) pair_add(sh, pt, a, d0, 6, 1u);
-                                    if (nd > 1) pair_add(sh, pt, a, d1, 6, 1u);
-                                    if (nd > 2) pair_add(sh, pt, a, d2, 6, 1u);
-                                    if (nd > 3) pair_add(sh, pt, a, d3, 6, 1u);
-                                } else {
-                                    // more than four distinct neighbour labels: exact first-occurrence rescan
-                                    for (int k = 0; k < 18; ++k) {
-                                        uint32_t b = p[offs[k]];
-                                        if (b == a) continue;
-                                        bool seen = false;
-                                        for (int q = 0; q < k; ++q) seen |= ((uint32_t)p[offs[q]] == b);
-                                        if (!seen) pair_add(sh, pt, a, b, 6, 1u);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    t_prev = t_cur; t_cur = t_next;
                 }
-                if (do_mom) flush_run(smax);
+                // warp-aggregated append of non-interior segments
+                const bool want = do_pairs && active && !interior;
+                const unsigned ball = __ballot_sync(0xffffffffu, want);
+                if (ball) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.ctr[1], (unsigned)__popc(ball));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (want) sh.seglist[base + __popc(ball & ((1u << lane) - 1u))] =
+                        (unsigned short)((s * BM + m) * NFS + fs);
+                }
+                t_prev = t_cur; t_cur = t_next;
             }
+            if (do_mom) flush_run(smax);
         }
         __syncthreads();
 
-        // ---- flush the per-brick tables -----------------------------------------------------------------------------
+        // ---- phases C2 + D in rounds of NTHREADS listed segments ------------------------------------------------------
+        if (do_pairs) {
+            const int nseg = (int)sh.ctr[1];
+            for (int base = 0, round = 0; base < nseg; base += NTHREADS, ++round) {
+                unsigned int* nvox = &sh.ctr[2 + (round & 1)];
+                if (tid == 0) sh.ctr[2 + ((round + 1) & 1)] = 0u;
+                // C2: boundary bits of one listed segment per thread
+                const int idx = base + tid;
+                uint32_t bits = 0, id = 0;
+                if (idx < nseg) {
+                    id = sh.seglist[idx];
+                    const int fs = id % NFS, m = (id / NFS) % BM, s = id / (NFS * BM);
+                    const int t = (s + 1) * PLANEV + (m + 1) * ROWV + (fs + 1);
+                    const uint4 C = sh.tile[t];
+                    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+                    Boundary<T>::cross(acc, C, sh.tile, t, false);
+                    Boundary<T>::cross(acc, C, sh.tile, t - ROWV, true);
+                    Boundary<T>::cross(acc, C, sh.tile, t + ROWV, true);
+                    Boundary<T>::cross(acc, C, sh.tile, t - PLANEV, true);
+                    Boundary<T>::cross(acc, C, sh.tile, t + PLANEV, true);
+                    Boundary<T>::diag(acc, C, sh.tile, t - PLANEV - ROWV);
+                    Boundary<T>::diag(acc, C, sh.tile, t - PLANEV + ROWV);
+                    Boundary<T>::diag(acc, C, sh.tile, t + PLANEV - ROWV);
+                    Boundary<T>::diag(acc, C, sh.tile, t + PLANEV + ROWV);
+                    bits = Boundary<T>::mask(acc);
+                    const long long left = P.nf - (F0 + (long long)fs * SEG);
+                    if (left < SEG) bits &= (1u << (int)left) - 1u;
+                }
+                {
+                    // warp exclusive scan of popcounts, one shared atomic per warp
+                    const unsigned cnt = __popc(bits);
+                    unsigned inc = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += y;
+                    }
+                    unsigned wtot = __shfl_sync(0xffffffffu, inc, 31);
+                    unsigned wbase = 0;
+                    if (lane == 31 && wtot) wbase = atomicAdd(nvox, wtot);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                    unsigned pos = wbase + inc - cnt;
+                    while (bits) {
+                        int j = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        sh.voxlist[pos++] = (unsigned short)((id << LOG_SEG) | j);
+                    }
+                }
+                __syncthreads();
+
+                // D: one listed voxel per thread
+                const int nv = (int)*nvox;
+                for (int i = tid; i < nv; i += NTHREADS) {
+                    const uint32_t e = sh.voxlist[i];
+                    const uint32_t sid = e >> LOG_SEG;
+                    const int j = e & (SEG - 1);
+                    const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
+                    const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
+                    const uint32_t a = p[0];
+                    constexpr int offs[18] = {
+                        1, ROWE, PLANEE, -1, -ROWE, -PLANEE,
+                        -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
+                        -PLANEE - 1, -PLANEE + 1, PLANEE - 1, PLANEE + 1,
+                        -PLANEE - ROWE, -PLANEE + ROWE, PLANEE - ROWE, PLANEE + ROWE};
+                    uint32_t nb[18];
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) nb[k] = p[offs[k]];
+                    uint32_t d0 = a;
+                    bool simple = true;
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) {
+                        const uint32_t b = nb[k];
+                        const bool ne = b != a;
+                        const bool first = ne && (d0 == a);
+                        simple = simple && (!ne || first || b == d0);
+                        d0 = first ? b : d0;
+                    }
+                    if (d0 == a) continue;
+                    if (simple) {
+                        const bool lo = a < d0;
+                        uint32_t inc[PT_WORDS] = {do_w18 ? 1u : 0u, 0u, 0u, 0u};
+                        if (do_p6) {
+                            if (nb[0] != a) { if (lo) inc[0] += 1u << 16; else inc[1] += 1u; }
+                            if (nb[1] != a) { if (lo) inc[1] += 1u << 16; else inc[2] += 1u; }
+                            if (nb[2] != a) { if (lo) inc[2] += 1u << 16; else inc[3] += 1u; }
+                        }
+                        pair_add_packed(sh, pt, ta_pair_key(a, d0), inc);
+                    } else {
+                        // junction voxel: distinct other labels in registers (up to 4), one packed add per label
+                        uint32_t d1 = a, d2 = a, d3 = a;
+                        int nd = 1;
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) {
+                            const uint32_t b = nb[k];
+                            const bool isnew = (b != a) & (b != d0) & (b != d1) & (b != d2) & (b != d3);
+                            d1 = (isnew && nd == 1) ? b : d1;
+                            d2 = (isnew && nd == 2) ? b : d2;
+                            d3 = (isnew && nd == 3) ? b : d3;
+                            nd += isnew ? 1 : 0;
+                        }
+                        if (nd <= 4) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t d = q == 0 ? d0 : q == 1 ? d1 : q == 2 ? d2 : d3;
+                                if (q >= nd) break;
+                                const bool lo = a < d;
+                                uint32_t inc[PT_WORDS] = {do_w18 ? 1u : 0u, 0u, 0u, 0u};
+                                if (do_p6) {
+                                    if (nb[0] == d) { if (lo) inc[0] += 1u << 16; else inc[1] += 1u; }
+                                    if (nb[1] == d) { if (lo) inc[1] += 1u << 16; else inc[2] += 1u; }
+                                    if (nb[2] == d) { if (lo) inc[2] += 1u << 16; else inc[3] += 1u; }
+                                }
+                                pair_add_packed(sh, pt, ta_pair_key(a, d), inc);
+                            }
+                        } else {
+                            // more than four distinct other labels (noise-like data): exact first-occurrence rescan
+                            if (do_p6) {
+                                if (nb[0] != a) pair_add(sh, pt, a, nb[0], a < nb[0] ? 0 : 1, 1u);
+                                if (nb[1] != a) pair_add(sh, pt, a, nb[1], a < nb[1] ? 2 : 3, 1u);
+                                if (nb[2] != a) pair_add(sh, pt, a, nb[2], a < nb[2] ? 4 : 5, 1u);
+                            }
+                            if (do_w18) {
+#pragma unroll 1
+                                for (int k = 0; k < 18; ++k) {
+                                    const uint32_t b = p[neighbour_offset<ROWE, PLANEE>(k)];
+                                    if (b == a) continue;
+                                    bool seen = false;
+                                    for (int q = 0; q < k; ++q)
+                                        seen |= ((uint32_t)p[neighbour_offset<ROWE, PLANEE>(q)] == b);
+                                    if (!seen) pair_add(sh, pt, a, b, 6, 1u);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- phase F: flush the per-brick tables ---------------------------------------------------------------------
         {
-            const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)(S0 + P.slow_offset);
             for (int i = tid; i < LT_SLOTS; i += NTHREADS) {
                 uint32_t L = sh.lt_key[i];
                 if (L == TA_EMPTY32) continue;
@@ -342,13 +547,15 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
                 u64 key = sh.pt_key[i];
                 if (key == TA_EMPTY64) continue;
-                uint32_t* d = &sh.pt_val[i * TA_PAIR_STRIDE];
+                uint32_t* d = &sh.pt_val[i * PT_WORDS];
                 int slot = ta_pair_slot(pt, key);
 #pragma unroll
-                for (int f = 0; f < 7; ++f) {
-                    if (d[f] && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + f], d[f]);
-                    d[f] = 0u;
+                for (int idx = 0; idx < 7; ++idx) {
+                    uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+                    if (n && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + (idx == 0 ? 6 : idx - 1)], n);
                 }
+#pragma unroll
+                for (int w = 0; w < PT_WORDS; ++w) d[w] = 0u;
                 sh.pt_key[i] = TA_EMPTY64;
             }
         }
