@@ -107,9 +107,9 @@ int ta_ctx_create(ta_ctx** out, int device) {
     TA_CUDA(cudaMalloc((void**)&ctx->status, 4 * sizeof(uint32_t)));
     TA_CUDA(cudaMalloc((void**)&ctx->counters, 4 * sizeof(unsigned int)));
     TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::scan_smem_bytes()));
+                                 (int)ta::scan_smem_bytes<uint16_t>()));
     TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::scan_smem_bytes()));
+                                 (int)ta::scan_smem_bytes<uint32_t>()));
     *out = ctx;
     return TA_OK;
 }
@@ -245,7 +245,7 @@ static int ensure_pair_table(ta_ctx* ctx, size_t cap) {
 int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "ta_run_pass: no volume bound");
-    if ((flags & TA_PASS_ALL) == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass: empty flags");
+    if ((flags & (TA_PASS_ALL | 0x300u)) == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass: empty flags");
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->have_tables = false;
@@ -311,9 +311,9 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     if (total > 0) {
         int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 2);
         if (ctx->elem == 2)
-            ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes(), st>>>(P, ctx->lt, ctx->pt);
+            ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt);
         else
-            ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes(), st>>>(P, ctx->lt, ctx->pt);
+            ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt);
         ctx->launches++;
         TA_CUDA(cudaGetLastError());
     }

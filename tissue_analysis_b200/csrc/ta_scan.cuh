@@ -4,18 +4,22 @@
 // one-voxel halo, clamped at the buffer edges (a clamped neighbour equals an in-bounds 6/18-neighbour or the
 // voxel itself, which reproduces the reference's "the image border contributes nothing" rule).
 //
-// Phases per brick (every phase keeps whole warps busy; irregular work is compacted into worklists first):
+// Phases per brick (irregular work is compacted into worklists first so whole warps stay busy):
 //   A  stage brick + halo: 128-bit streaming loads -> shared tile.
 //   B  per row-segment uniformity code: the label if the SEG+2 voxels (segment + f-halo) are equal.
-//   C1 march: thread (fseg, m) walks s.  Uniform segments extend a register run (count, sum s, sum s^2; f/m
-//      moments are closed forms on flush); mixed segments add per-lane runs.  Segments whose 3x3 rows are not one
-//      label go to the SEGMENT worklist.
+//   C1 march: thread (fseg, m) walks s.  Moments go to two register slots per thread (the column of a thread
+//      rarely sees more than two labels): n, sum f, sum s, sum ff, sum fs, sum ss, f/s bounds; the m terms are
+//      closed forms.  Uniform segments cost a handful of adds, mixed segments are split into runs with SIMD
+//      compares.  At the end of the column the slots are merged across the warp (match.any + redux) and one lane
+//      per label updates the per-brick shared label table.  Segments whose 3x3 rows are not one label go to the
+//      SEGMENT worklist.
 //   C2 per listed segment, SIMD on the packed lanes: OR of XORs of the segment with its 18 neighbour vectors
 //      (f-shifted ones built with funnel shifts) -> exact "has a different 18-neighbour" flag per voxel; flagged
 //      voxels go to the VOXEL worklist.
-//   D  per listed voxel: 18 neighbour labels -> first other label + "only one other label" test; the common case
-//      is ONE shared-memory hash lookup and <= 4 packed 16-bit counter adds (wall18 + the +f/+m/+s faces);
-//      junction voxels take the exact dedup path.
+//   D  per listed voxel: 18 neighbour labels -> first other label + "only one other label" test.  The common case
+//      is merged across the warp (match.any on the pair key, redux of the packed 16-bit counters: wall18 and the
+//      +f/+m/+s faces) and one lane per pair updates the per-brick shared pair table.  Junction voxels (>= 2 other
+//      labels) go to a third worklist and are handled with a register dedup of up to 4 labels.
 //   F  flush the per-brick label table (u32 brick-local sums -> u64 global REDs) and pair table.
 #pragma once
 #include "ta_common.cuh"
@@ -31,17 +35,40 @@ constexpr int LT_FIELDS = 16;           // n, sf, sm, ss, sff, sfm, sfs, smm, sm
 constexpr int PT_SLOTS = 256;           // per-brick pair slots
 constexpr int PT_WORDS = 4;             // packed 16-bit counters: [w18|f0] [f1|f2] [f3|f4] [f5|-]
 constexpr int TILE_ROWS = (BS + 2) * (BM + 2);
-constexpr int TILE_SEGS = TILE_ROWS * (NFS + 2);
+constexpr int ROWV = NFS + 2;           // vectors per tile row
+constexpr int PLANEV = (BM + 2) * ROWV; // vectors per tile plane
+constexpr int TILE_SEGS = TILE_ROWS * ROWV;
 constexpr int SEGLIST_CAP = NFS * BM * BS;
 constexpr int VOXLIST_CAP = NTHREADS * 8;
 
 template <typename T> struct Vox;
-template <> struct Vox<uint16_t> { static constexpr int SEG = 8; static constexpr int LOG_SEG = 3; };
-template <> struct Vox<uint32_t> { static constexpr int SEG = 4; static constexpr int LOG_SEG = 2; };
+template <> struct Vox<uint16_t> {
+    static constexpr int SEG = 8, LOG_SEG = 3;
+    typedef unsigned short Code;                    // label 0xFFFF reads as "mixed": slower exact paths, same result
+    static constexpr uint32_t MIXED = 0xFFFFu;
+    typedef uint32_t PKey;                          // (lo << 16) | hi
+    static constexpr PKey PEMPTY = 0xFFFFFFFFu;
+    static __device__ __forceinline__ PKey key(uint32_t a, uint32_t b) { return a < b ? (a << 16) | b : (b << 16) | a; }
+    static __device__ __forceinline__ u64 key64(PKey k) { return ((u64)(k >> 16) << 32) | (k & 0xFFFFu); }
+    static __device__ __forceinline__ uint32_t hash(PKey k) { return (k * 0x9E3779B1u) >> 24; }
+};
+template <> struct Vox<uint32_t> {
+    static constexpr int SEG = 4, LOG_SEG = 2;
+    typedef uint32_t Code;
+    static constexpr uint32_t MIXED = 0xFFFFFFFFu;
+    typedef u64 PKey;
+    static constexpr PKey PEMPTY = TA_EMPTY64;
+    static __device__ __forceinline__ PKey key(uint32_t a, uint32_t b) { return ta_pair_key(a, b); }
+    static __device__ __forceinline__ u64 key64(PKey k) { return k; }
+    static __device__ __forceinline__ uint32_t hash(PKey k) {
+        return (((uint32_t)(k >> 32) * 0x9E3779B1u) ^ ((uint32_t)k * 0x85EBCA77u)) >> 24;
+    }
+};
 
-constexpr size_t scan_smem_bytes() {
-    return (size_t)TILE_SEGS * 16 + (size_t)TILE_ROWS * NFS * 4 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 +
-           PT_SLOTS * 8 + PT_SLOTS * PT_WORDS * 4 + SEGLIST_CAP * 2 + VOXLIST_CAP * 2 + 32;
+template <typename T> constexpr size_t scan_smem_bytes() {
+    return (size_t)TILE_SEGS * 16 + (size_t)TILE_ROWS * NFS * sizeof(typename Vox<T>::Code) + LT_SLOTS * 4 +
+           LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + PT_SLOTS * PT_WORDS * 4 +
+           SEGLIST_CAP * 2 + 2 * VOXLIST_CAP * 2 + 32;
 }
 
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
@@ -51,16 +78,17 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
     return r;
 }
 
-struct BrickShared {
-    uint4* tile;            // [TILE_SEGS]
-    uint32_t* codes;        // [TILE_ROWS * NFS]
-    uint32_t* lt_key;       // [LT_SLOTS]
-    uint32_t* lt_val;       // [LT_SLOTS * LT_FIELDS]
-    u64* pt_key;            // [PT_SLOTS]
-    uint32_t* pt_val;       // [PT_SLOTS * PT_WORDS]
-    unsigned short* seglist;   // [SEGLIST_CAP]
-    unsigned short* voxlist;   // [VOXLIST_CAP]
-    unsigned int* ctr;      // [0] next brick, [1] nseg, [2..3] nvox ping-pong
+template <typename T> struct BrickShared {
+    uint4* tile;                       // [TILE_SEGS]
+    typename Vox<T>::Code* codes;      // [TILE_ROWS * NFS]
+    uint32_t* lt_key;                  // [LT_SLOTS]
+    uint32_t* lt_val;                  // [LT_SLOTS * LT_FIELDS]
+    typename Vox<T>::PKey* pt_key;     // [PT_SLOTS]
+    uint32_t* pt_val;                  // [PT_SLOTS * PT_WORDS]
+    unsigned short* seglist;           // [SEGLIST_CAP]
+    unsigned short* voxlist;           // [VOXLIST_CAP]
+    unsigned short* junclist;          // [VOXLIST_CAP]
+    unsigned int* ctr;                 // [0] next brick, [1] nseg, [2..3] nvox ping-pong, [4..5] njunc ping-pong
 };
 
 // ---- global flush of one label's brick-local sums -----------------------------------------------------------
@@ -88,7 +116,8 @@ __device__ __forceinline__ void label_to_global(const LabelTable& lt, uint32_t* 
 }
 
 // ---- per-brick label accumulation (brick-local coordinates, u32) -----------------------------------------
-__device__ __forceinline__ void label_add(const BrickShared& sh, const LabelTable& lt, uint32_t* status,
+template <typename T>
+__device__ __forceinline__ void label_add(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
                                           uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0) {
     uint32_t slot = (L * 0x9E3779B1u) >> 26;   // 6 bits
     int found = -1;
@@ -111,32 +140,61 @@ __device__ __forceinline__ void label_add(const BrickShared& sh, const LabelTabl
     for (int i = 13; i < 16; ++i) atomicMax(&d[i], v[i]);
 }
 
+// all 32 lanes call; lanes with L == TA_EMPTY32 contribute nothing.  One shared-table update per distinct label.
+template <typename T>
+__device__ __forceinline__ void label_add_warp(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
+                                               uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0, int lane) {
+    const unsigned grp = __match_any_sync(0xffffffffu, L);
+    uint32_t r[LT_FIELDS];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = __reduce_add_sync(grp, v[i]);
+#pragma unroll
+    for (int i = 10; i < 13; ++i) r[i] = __reduce_min_sync(grp, v[i]);
+#pragma unroll
+    for (int i = 13; i < 16; ++i) r[i] = __reduce_max_sync(grp, v[i]);
+    if (L != TA_EMPTY32 && lane == __ffs(grp) - 1) label_add(sh, lt, status, L, r, F0, M0, S0);
+}
+
+// thread-private moment accumulator for one label over the thread's (fseg, m) column
+struct MomSlot {
+    uint32_t label, n, sf, ss, sff, sfs, sss, fmin, fmax, smin, smax;
+    __device__ __forceinline__ void reset(uint32_t L) {
+        label = L; n = sf = ss = sff = sfs = sss = 0u; fmin = 0xFFFFFFFFu; fmax = 0u; smin = 0xFFFFFFFFu; smax = 0u;
+    }
+    __device__ __forceinline__ void add(uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t s, uint32_t f_first,
+                                        uint32_t f_last) {
+        n += len; sf += sfr; ss += len * s; sff += sffr; sfs += s * sfr; sss += len * s * s;
+        fmin = min(fmin, f_first); fmax = max(fmax, f_last); smin = min(smin, s); smax = max(smax, s);
+    }
+    __device__ __forceinline__ void fields(uint32_t v[LT_FIELDS], uint32_t m) const {
+        v[0] = n; v[1] = sf; v[2] = n * m; v[3] = ss; v[4] = sff; v[5] = m * sf; v[6] = sfs;
+        v[7] = n * m * m; v[8] = m * ss; v[9] = sss;
+        v[10] = fmin; v[11] = m; v[12] = smin; v[13] = fmax; v[14] = m; v[15] = smax;
+    }
+};
+
 // ---- per-brick pair accumulation (packed 16-bit counters; a brick has < 65536 voxels) ------------------------
 // field 6 = wall18, fields 0..5 = directional faces.  idx = field+1 (wall18 -> 0): word idx>>1, half idx&1.
-__device__ __forceinline__ int pair_slot_shared(const BrickShared& sh, u64 key) {
-    uint32_t h = ((uint32_t)(key >> 32) * 0x9E3779B1u) ^ ((uint32_t)key * 0x85EBCA77u);
-    uint32_t slot = h >> 24;
+template <typename T>
+__device__ __forceinline__ void pair_add_packed(const BrickShared<T>& sh, const PairTable& pt,
+                                                typename Vox<T>::PKey key, const uint32_t inc[PT_WORDS]) {
+    typedef typename Vox<T>::PKey PKey;
+    uint32_t slot = Vox<T>::hash(key);
     for (int probe = 0; probe < PT_SLOTS; ++probe) {
-        u64 k = *((volatile u64*)&sh.pt_key[slot]);
-        if (k == key) return (int)slot;
-        if (k == TA_EMPTY64) {
-            u64 old = atomicCAS(&sh.pt_key[slot], TA_EMPTY64, key);
-            if (old == TA_EMPTY64 || old == key) return (int)slot;
+        PKey k = *((volatile PKey*)&sh.pt_key[slot]);
+        bool hit = (k == key);
+        if (!hit && k == Vox<T>::PEMPTY) {
+            PKey old = atomicCAS(&sh.pt_key[slot], Vox<T>::PEMPTY, key);
+            hit = (old == Vox<T>::PEMPTY || old == key);
+        }
+        if (hit) {
+#pragma unroll
+            for (int w = 0; w < PT_WORDS; ++w) if (inc[w]) atomicAdd(&sh.pt_val[slot * PT_WORDS + w], inc[w]);
+            return;
         }
         slot = (slot + 1) & (PT_SLOTS - 1);
     }
-    return -1;
-}
-
-__device__ __forceinline__ void pair_add_packed(const BrickShared& sh, const PairTable& pt, u64 key,
-                                                const uint32_t inc[PT_WORDS]) {
-    int slot = pair_slot_shared(sh, key);
-    if (slot >= 0) {
-#pragma unroll
-        for (int w = 0; w < PT_WORDS; ++w) if (inc[w]) atomicAdd(&sh.pt_val[slot * PT_WORDS + w], inc[w]);
-        return;
-    }
-    int g = ta_pair_slot(pt, key);          // brick table full: straight to the global table
+    int g = ta_pair_slot(pt, Vox<T>::key64(key));          // brick table full: straight to the global table
     if (g < 0) return;
     uint32_t* v = &pt.vals[(size_t)g * TA_PAIR_STRIDE];
 #pragma unroll
@@ -146,18 +204,26 @@ __device__ __forceinline__ void pair_add_packed(const BrickShared& sh, const Pai
     }
 }
 
-__device__ __forceinline__ void pair_add(const BrickShared& sh, const PairTable& pt, uint32_t a, uint32_t b,
+template <typename T>
+__device__ __forceinline__ void pair_add(const BrickShared<T>& sh, const PairTable& pt, uint32_t a, uint32_t b,
                                          int field, uint32_t n) {
     uint32_t inc[PT_WORDS] = {0, 0, 0, 0};
     int idx = field == 6 ? 0 : field + 1;
     inc[idx >> 1] = n << ((idx & 1) * 16);
-    pair_add_packed(sh, pt, ta_pair_key(a, b), inc);
+    pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
+}
+
+// packed increments of one voxel (label a) towards other label d: wall18 + the faces to its +f/+m/+s neighbours
+__device__ __forceinline__ void voxel_increments(uint32_t inc[PT_WORDS], bool lo, bool w18, bool ff, bool fm, bool fsl) {
+    inc[0] = (w18 ? 1u : 0u) + ((ff && lo) ? (1u << 16) : 0u);
+    inc[1] = ((ff && !lo) ? 1u : 0u) + ((fm && lo) ? (1u << 16) : 0u);
+    inc[2] = ((fm && !lo) ? 1u : 0u) + ((fsl && lo) ? (1u << 16) : 0u);
+    inc[3] = ((fsl && !lo) ? 1u : 0u);
 }
 
 __device__ __forceinline__ uint32_t sumsq_upto(uint32_t k) { return k * (k + 1) * (2 * k + 1) / 6; }  // 0..k
 
-// ---- phase C2: exact "has a different 18-neighbour" bit per voxel of one segment ---------------------------
-// t = tile vector index of the centre segment; returns a SEG-bit mask.
+// ---- SIMD helpers on one 16-byte segment ------------------------------------------------------------------------
 template <typename T> struct Boundary;
 
 template <> struct Boundary<uint16_t> {
@@ -185,6 +251,12 @@ template <> struct Boundary<uint16_t> {
                       (__vminu2(acc[3], one) << 6);
         return (tt & 0x55u) | ((tt >> 15) & 0xAAu);
     }
+    // bit j set iff lane j differs from lane j+1 (j = 0..6)
+    static __device__ __forceinline__ uint32_t run_breaks(const uint4& C) {
+        uint32_t d[4] = {C.x ^ __funnelshift_r(C.x, C.y, 16), C.y ^ __funnelshift_r(C.y, C.z, 16),
+                         C.z ^ __funnelshift_r(C.z, C.w, 16), (C.w ^ (C.w >> 16)) & 0xFFFFu};
+        return mask(d) & 0x7Fu;
+    }
 };
 
 template <> struct Boundary<uint32_t> {
@@ -206,6 +278,9 @@ template <> struct Boundary<uint32_t> {
     static __device__ __forceinline__ uint32_t mask(const uint32_t acc[4]) {
         return (acc[0] ? 1u : 0u) | (acc[1] ? 2u : 0u) | (acc[2] ? 4u : 0u) | (acc[3] ? 8u : 0u);
     }
+    static __device__ __forceinline__ uint32_t run_breaks(const uint4& C) {
+        return (C.x != C.y ? 1u : 0u) | (C.y != C.z ? 2u : 0u) | (C.z != C.w ? 4u : 0u);
+    }
 };
 
 // k-th offset of the 18-neighbourhood (1 <= |df|+|dm|+|ds| <= 2) in tile elements; rare-path helper
@@ -226,25 +301,27 @@ __device__ __noinline__ int neighbour_offset(int k) {
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2)
 scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
+    typedef typename Vox<T>::Code Code;
+    typedef typename Vox<T>::PKey PKey;
     constexpr int SEG = Vox<T>::SEG;
     constexpr int LOG_SEG = Vox<T>::LOG_SEG;
-    constexpr int ROWE = (NFS + 2) * SEG;          // elements per tile row
+    constexpr uint32_t MIXED = Vox<T>::MIXED;
+    constexpr int ROWE = ROWV * SEG;               // elements per tile row
     constexpr int PLANEE = (BM + 2) * ROWE;        // elements per tile plane
-    constexpr int ROWV = NFS + 2;                  // vectors per tile row
-    constexpr int PLANEV = (BM + 2) * ROWV;        // vectors per tile plane
     constexpr int BF = NFS * SEG;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BrickShared sh;
+    BrickShared<T> sh;
     sh.tile = reinterpret_cast<uint4*>(smem_raw);
-    sh.codes = reinterpret_cast<uint32_t*>(sh.tile + TILE_SEGS);
-    sh.lt_key = sh.codes + TILE_ROWS * NFS;
+    sh.lt_key = reinterpret_cast<uint32_t*>(sh.tile + TILE_SEGS);
     sh.lt_val = sh.lt_key + LT_SLOTS;
-    sh.pt_key = reinterpret_cast<u64*>(sh.lt_val + LT_SLOTS * LT_FIELDS);
-    sh.pt_val = reinterpret_cast<uint32_t*>(sh.pt_key + PT_SLOTS);
-    sh.seglist = reinterpret_cast<unsigned short*>(sh.pt_val + PT_SLOTS * PT_WORDS);
+    sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
+    sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
+    sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
+    sh.codes = reinterpret_cast<Code*>(sh.ctr + 8);
+    sh.seglist = reinterpret_cast<unsigned short*>(sh.codes + TILE_ROWS * NFS);
     sh.voxlist = sh.seglist + SEGLIST_CAP;
-    sh.ctr = reinterpret_cast<unsigned int*>(sh.voxlist + VOXLIST_CAP);
+    sh.junclist = sh.voxlist + VOXLIST_CAP;
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
@@ -253,6 +330,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
     const bool do_pairs = do_p6 || do_w18;
+    const int nf = (int)P.nf, nm = (int)P.nm, ns = (int)P.ns;
 
     // reset the per-brick tables once; the flush at the end of each brick re-arms them
     for (int i = tid; i < LT_SLOTS; i += NTHREADS) sh.lt_key[i] = TA_EMPTY32;
@@ -260,34 +338,44 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         int f = i % LT_FIELDS;
         sh.lt_val[i] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
     }
-    for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = TA_EMPTY64;
+    for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
     for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
 
     for (;;) {
-        if (tid == 0) { sh.ctr[0] = atomicAdd(P.brick_counter, 1u); sh.ctr[1] = 0u; sh.ctr[2] = 0u; sh.ctr[3] = 0u; }
+        if (tid == 0) {
+            sh.ctr[0] = atomicAdd(P.brick_counter, 1u);
+            sh.ctr[1] = 0u; sh.ctr[2] = 0u; sh.ctr[3] = 0u; sh.ctr[4] = 0u; sh.ctr[5] = 0u;
+        }
         __syncthreads();
         const unsigned int brick = sh.ctr[0];
         if (brick >= total) break;
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
-        const long long F0 = (long long)bf * BF, M0 = (long long)bm * BM, S0 = P.own_lo + (long long)bs * BS;
-        const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)(S0 + P.slow_offset);
+        const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
+        const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
 
         // ---- phase A: stage brick + halo (clamped) ------------------------------------------------------------
         for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-            int fs = i % ROWV - 1;
-            int r = i / ROWV;
-            int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
-            long long gs = min(max(S0 + s, 0LL), P.ns - 1);
-            long long gm = min(max(M0 + m, 0LL), P.nm - 1);
-            long long gf = F0 + (long long)fs * SEG;
-            const T* row = vol + (gs * P.nm + gm) * P.nf;
+            const int fs = i % ROWV - 1;
+            const int r = i / ROWV;
+            const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
+            const int gs = min(max(S0 + s, 0), ns - 1);
+            const int gm = min(max(M0 + m, 0), nm - 1);
+            const int gf = F0 + fs * SEG;
+            const T* row = vol + ((size_t)gs * nm + gm) * (size_t)nf;
             uint4 v;
-            if (P.vec_ok && gf >= 0 && gf + SEG <= P.nf) {
-                v = ld_stream_128(row + gf);
+            if (P.vec_ok) {
+                // rows are whole segments: out-of-range halo segments replicate the edge voxel
+                const int gfc = min(max(gf, 0), nf - SEG);
+                v = ld_stream_128(row + gfc);
+                if (gf != gfc) {
+                    uint32_t e = (gf < 0) ? ((SEG == 8) ? (v.x & 0xFFFFu) : v.x) : ((SEG == 8) ? (v.w >> 16) : v.w);
+                    if (SEG == 8) e |= e << 16;
+                    v.x = v.y = v.z = v.w = e;
+                }
             } else {
                 T tmp[SEG];
 #pragma unroll
-                for (int j = 0; j < SEG; ++j) tmp[j] = row[min(max(gf + j, 0LL), P.nf - 1)];
+                for (int j = 0; j < SEG; ++j) tmp[j] = row[min(max(gf + j, 0), nf - 1)];
                 if (SEG == 8) {
                     v.x = (uint32_t)tmp[0] | ((uint32_t)tmp[1] << 16);
                     v.y = (uint32_t)tmp[2] | ((uint32_t)tmp[3] << 16);
@@ -301,47 +389,53 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         }
         __syncthreads();
 
+        if (P.flags & 0x100u) continue;   // debug: staging only
         // ---- phase B: per row-segment uniformity code (label if the SEG+2 voxels are equal) -------------------
         for (int i = tid; i < TILE_ROWS * NFS; i += NTHREADS) {
-            int fs = i % NFS, r = i / NFS;
+            const int fs = i % NFS, r = i / NFS;
             const T* rp = tileT + r * ROWE + (fs + 1) * SEG;
-            uint4 v = sh.tile[r * ROWV + fs + 1];
-            uint32_t l = rp[0];
-            uint32_t pat = (SEG == 8) ? (l | (l << 16)) : l;
-            bool uni = (v.x == pat) & (v.y == pat) & (v.z == pat) & (v.w == pat) &
-                       ((uint32_t)rp[-1] == l) & ((uint32_t)rp[SEG] == l);
-            sh.codes[i] = uni ? l : TA_EMPTY32;
+            const uint4 v = sh.tile[r * ROWV + fs + 1];
+            const uint32_t l = rp[0];
+            const uint32_t pat = (SEG == 8) ? (l | (l << 16)) : l;
+            const bool uni = (v.x == pat) & (v.y == pat) & (v.z == pat) & (v.w == pat) &
+                             ((uint32_t)rp[-1] == l) & ((uint32_t)rp[SEG] == l);
+            sh.codes[i] = (Code)(uni ? l : MIXED);
         }
         __syncthreads();
 
+        if (P.flags & 0x200u) continue;   // debug: staging + codes only
         // ---- phase C1: march (moments, interior test, segment worklist) -------------------------------------------
         {
             const int fs = tid % NFS, m = tid / NFS;
-            const long long gf0 = F0 + (long long)fs * SEG, gm = M0 + m;
-            const bool col_valid = (gf0 < P.nf) && (gm < P.nm);
-            const int nvalid = col_valid ? (int)min((long long)SEG, P.nf - gf0) : 0;
-            const int smax = (int)min((long long)BS, P.own_hi - S0);
+            const int gf0 = F0 + fs * SEG, gm = M0 + m;
+            const bool col_valid = (gf0 < nf) && (gm < nm);
+            const int nvalid = col_valid ? min(SEG, nf - gf0) : 0;
+            const int smax = min(BS, (int)P.own_hi - S0);
             const uint32_t lf0 = fs * SEG;
+            const uint32_t rowsum = SEG * lf0 + SEG * (SEG - 1) / 2;
+            const uint32_t rowsq = SEG * lf0 * lf0 + lf0 * SEG * (SEG - 1) + (SEG - 1) * SEG * (2 * SEG - 1) / 6;
 
-            uint32_t run_label = TA_EMPTY32, run_cnt = 0, run_s = 0, run_ss = 0, run_first = 0;
-            auto flush_run = [&](int s_end) {
-                if (run_cnt == 0) return;
-                uint32_t v[LT_FIELDS];
-                const uint32_t n = run_cnt * SEG;
-                const uint32_t rowsum = SEG * lf0 + SEG * (SEG - 1) / 2;
-                const uint32_t rowsq = SEG * lf0 * lf0 + lf0 * SEG * (SEG - 1) + (SEG - 1) * SEG * (2 * SEG - 1) / 6;
-                v[0] = n; v[1] = run_cnt * rowsum; v[2] = n * m; v[3] = SEG * run_s;
-                v[4] = run_cnt * rowsq; v[5] = m * v[1]; v[6] = rowsum * run_s;
-                v[7] = n * m * m; v[8] = SEG * m * run_s; v[9] = SEG * run_ss;
-                v[10] = lf0; v[11] = m; v[12] = run_first;
-                v[13] = lf0 + SEG - 1; v[14] = m; v[15] = s_end - 1;
-                label_add(sh, lt, pt.status, run_label, v, gF0, gM0, gS0);
-                run_cnt = 0; run_s = 0; run_ss = 0;
+            MomSlot A, B;
+            A.reset(TA_EMPTY32); B.reset(TA_EMPTY32);
+            bool mruA = true;
+            auto evict = [&](MomSlot& sl) {
+                if (sl.n) {
+                    uint32_t v[LT_FIELDS];
+                    sl.fields(v, (uint32_t)m);
+                    label_add<T>(sh, lt, pt.status, sl.label, v, gF0, gM0, gS0);
+                }
             };
-            auto tcode = [&](int s) {
-                int base = ((s + 1) * (BM + 2) + (m + 1)) * NFS + fs;
-                uint32_t e0 = sh.codes[base - NFS], e1 = sh.codes[base], e2 = sh.codes[base + NFS];
-                return (e0 == e1 && e1 == e2) ? e1 : TA_EMPTY32;
+            auto account = [&](uint32_t L, uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t s, uint32_t f0,
+                               uint32_t f1) {
+                if (L == A.label) { A.add(len, sfr, sffr, s, f0, f1); mruA = true; }
+                else if (L == B.label) { B.add(len, sfr, sffr, s, f0, f1); mruA = false; }
+                else if (mruA) { evict(B); B.reset(L); B.add(len, sfr, sffr, s, f0, f1); mruA = false; }
+                else { evict(A); A.reset(L); A.add(len, sfr, sffr, s, f0, f1); mruA = true; }
+            };
+            auto tcode = [&](int s) -> uint32_t {
+                const int base = ((s + 1) * (BM + 2) + (m + 1)) * NFS + fs;
+                const uint32_t e0 = sh.codes[base - NFS], e1 = sh.codes[base], e2 = sh.codes[base + NFS];
+                return (e0 == e1 && e1 == e2) ? e1 : MIXED;
             };
 
             uint32_t t_prev = tcode(-1), t_cur = tcode(0);
@@ -349,31 +443,27 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 const bool active = col_valid && (s < smax);
                 const uint32_t t_next = tcode(s + 1);
                 const uint32_t e_c = sh.codes[((s + 1) * (BM + 2) + (m + 1)) * NFS + fs];
-                const bool interior = (t_cur != TA_EMPTY32) && (t_prev == t_cur) && (t_next == t_cur);
+                const bool interior = (t_cur != MIXED) && (t_prev == t_cur) && (t_next == t_cur);
 
                 if (do_mom && active) {
-                    if (e_c != TA_EMPTY32 && nvalid == SEG) {
-                        if (e_c != run_label) { flush_run(s); run_label = e_c; run_first = s; }
-                        run_cnt += 1; run_s += s; run_ss += s * s;
+                    if (e_c != MIXED && nvalid == SEG) {
+                        account(e_c, SEG, rowsum, rowsq, (uint32_t)s, lf0, lf0 + SEG - 1);
                     } else {
-                        flush_run(s);
-                        run_label = TA_EMPTY32;
-                        const T* cp = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG;
+                        const int tv = (s + 1) * PLANEV + (m + 1) * ROWV + (fs + 1);
+                        const uint4 C = sh.tile[tv];
+                        const T* cp = reinterpret_cast<const T*>(sh.tile + tv);
+                        uint32_t brk = Boundary<T>::run_breaks(C);
                         int j0 = 0;
                         while (j0 < nvalid) {
-                            uint32_t L = cp[j0];
-                            int j1 = j0 + 1;
-                            while (j1 < nvalid && (uint32_t)cp[j1] == L) ++j1;
-                            uint32_t len = j1 - j0;
-                            uint32_t sj = (uint32_t)(j0 + j1 - 1) * len / 2;
-                            uint32_t sjj = sumsq_upto(j1 - 1) - (j0 > 0 ? sumsq_upto(j0 - 1) : 0u);
-                            uint32_t v[LT_FIELDS];
-                            v[0] = len; v[1] = len * lf0 + sj; v[2] = len * m; v[3] = len * s;
-                            v[4] = len * lf0 * lf0 + 2 * lf0 * sj + sjj; v[5] = m * v[1]; v[6] = s * v[1];
-                            v[7] = len * m * m; v[8] = len * m * s; v[9] = len * s * s;
-                            v[10] = lf0 + j0; v[11] = m; v[12] = s;
-                            v[13] = lf0 + j1 - 1; v[14] = m; v[15] = s;
-                            label_add(sh, lt, pt.status, L, v, gF0, gM0, gS0);
+                            const uint32_t rest = brk >> j0;
+                            int j1 = rest ? j0 + __ffs(rest) : SEG;
+                            j1 = min(j1, nvalid);
+                            const uint32_t L = cp[j0];
+                            const uint32_t len = j1 - j0;
+                            const uint32_t sj = (uint32_t)(j0 + j1 - 1) * len / 2;
+                            const uint32_t sjj = sumsq_upto(j1 - 1) - (j0 > 0 ? sumsq_upto(j0 - 1) : 0u);
+                            account(L, len, len * lf0 + sj, len * lf0 * lf0 + 2 * lf0 * sj + sjj, (uint32_t)s,
+                                    lf0 + j0, lf0 + j1 - 1);
                             j0 = j1;
                         }
                     }
@@ -390,7 +480,13 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 }
                 t_prev = t_cur; t_cur = t_next;
             }
-            if (do_mom) flush_run(smax);
+            if (do_mom) {
+                uint32_t v[LT_FIELDS];
+                A.fields(v, (uint32_t)m);
+                label_add_warp<T>(sh, lt, pt.status, A.n ? A.label : TA_EMPTY32, v, gF0, gM0, gS0, lane);
+                B.fields(v, (uint32_t)m);
+                label_add_warp<T>(sh, lt, pt.status, B.n ? B.label : TA_EMPTY32, v, gF0, gM0, gS0, lane);
+            }
         }
         __syncthreads();
 
@@ -399,7 +495,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             const int nseg = (int)sh.ctr[1];
             for (int base = 0, round = 0; base < nseg; base += NTHREADS, ++round) {
                 unsigned int* nvox = &sh.ctr[2 + (round & 1)];
-                if (tid == 0) sh.ctr[2 + ((round + 1) & 1)] = 0u;
+                unsigned int* njunc = &sh.ctr[4 + (round & 1)];
+                if (tid == 0) { sh.ctr[2 + ((round + 1) & 1)] = 0u; sh.ctr[4 + ((round + 1) & 1)] = 0u; }
                 // C2: boundary bits of one listed segment per thread
                 const int idx = base + tid;
                 uint32_t bits = 0, id = 0;
@@ -419,8 +516,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     Boundary<T>::diag(acc, C, sh.tile, t + PLANEV - ROWV);
                     Boundary<T>::diag(acc, C, sh.tile, t + PLANEV + ROWV);
                     bits = Boundary<T>::mask(acc);
-                    const long long left = P.nf - (F0 + (long long)fs * SEG);
-                    if (left < SEG) bits &= (1u << (int)left) - 1u;
+                    const int left = nf - (F0 + fs * SEG);
+                    if (left < SEG) bits &= (1u << left) - 1u;
                 }
                 {
                     // warp exclusive scan of popcounts, one shared atomic per warp
@@ -444,10 +541,74 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 }
                 __syncthreads();
 
-                // D: one listed voxel per thread
+                // D: listed voxels, one per thread per iteration; simple voxels are merged across the warp
                 const int nv = (int)*nvox;
-                for (int i = tid; i < nv; i += NTHREADS) {
-                    const uint32_t e = sh.voxlist[i];
+                for (int ib = 0; ib < nv; ib += NTHREADS) {
+                    const int i = ib + tid;
+                    PKey key = Vox<T>::PEMPTY;
+                    uint32_t inc[PT_WORDS] = {0u, 0u, 0u, 0u};
+                    bool junction = false;
+                    uint32_t e = 0;
+                    if (i < nv) {
+                        e = sh.voxlist[i];
+                        const uint32_t sid = e >> LOG_SEG;
+                        const int j = e & (SEG - 1);
+                        const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
+                        const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
+                        const uint32_t a = p[0];
+                        constexpr int offs[18] = {
+                            1, ROWE, PLANEE, -1, -ROWE, -PLANEE,
+                            -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
+                            -PLANEE - 1, -PLANEE + 1, PLANEE - 1, PLANEE + 1,
+                            -PLANEE - ROWE, -PLANEE + ROWE, PLANEE - ROWE, PLANEE + ROWE};
+                        uint32_t nb[18];
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) nb[k] = p[offs[k]];
+                        uint32_t d0 = a;
+                        bool simple = true;
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) {
+                            const uint32_t b = nb[k];
+                            const bool ne = b != a;
+                            const bool first = ne && (d0 == a);
+                            simple = simple && (!ne || first || b == d0);
+                            d0 = first ? b : d0;
+                        }
+                        if (d0 != a) {
+                            if (simple) {
+                                key = Vox<T>::key(a, d0);
+                                voxel_increments(inc, a < d0, do_w18, do_p6 && nb[0] != a, do_p6 && nb[1] != a,
+                                                 do_p6 && nb[2] != a);
+                            } else {
+                                junction = true;
+                            }
+                        }
+                    }
+                    // one shared-table update per distinct pair in the warp
+                    {
+                        const unsigned grp = __match_any_sync(0xffffffffu, key);
+                        uint32_t tot[PT_WORDS];
+#pragma unroll
+                        for (int w = 0; w < PT_WORDS; ++w) tot[w] = __reduce_add_sync(grp, inc[w]);
+                        if (key != Vox<T>::PEMPTY && lane == __ffs(grp) - 1) pair_add_packed<T>(sh, pt, key, tot);
+                    }
+                    // junction voxels -> third worklist
+                    {
+                        const unsigned ball = __ballot_sync(0xffffffffu, junction);
+                        if (ball) {
+                            unsigned jb = 0;
+                            if (lane == 0) jb = atomicAdd(njunc, (unsigned)__popc(ball));
+                            jb = __shfl_sync(0xffffffffu, jb, 0);
+                            if (junction) sh.junclist[jb + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)e;
+                        }
+                    }
+                }
+                __syncthreads();
+
+                // D2: junction voxels: distinct other labels in registers (up to 4), one packed add per label
+                const int nj = (int)*njunc;
+                for (int i = tid; i < nj; i += NTHREADS) {
+                    const uint32_t e = sh.junclist[i];
                     const uint32_t sid = e >> LOG_SEG;
                     const int j = e & (SEG - 1);
                     const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
@@ -461,70 +622,45 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     uint32_t nb[18];
 #pragma unroll
                     for (int k = 0; k < 18; ++k) nb[k] = p[offs[k]];
-                    uint32_t d0 = a;
-                    bool simple = true;
+                    uint32_t d0 = a, d1 = a, d2 = a, d3 = a;
+                    int nd = 0;
 #pragma unroll
                     for (int k = 0; k < 18; ++k) {
                         const uint32_t b = nb[k];
-                        const bool ne = b != a;
-                        const bool first = ne && (d0 == a);
-                        simple = simple && (!ne || first || b == d0);
-                        d0 = first ? b : d0;
+                        const bool isnew = (b != a) & (b != d0) & (b != d1) & (b != d2) & (b != d3);
+                        d0 = (isnew && nd == 0) ? b : d0;
+                        d1 = (isnew && nd == 1) ? b : d1;
+                        d2 = (isnew && nd == 2) ? b : d2;
+                        d3 = (isnew && nd == 3) ? b : d3;
+                        nd += isnew ? 1 : 0;
                     }
-                    if (d0 == a) continue;
-                    if (simple) {
-                        const bool lo = a < d0;
-                        uint32_t inc[PT_WORDS] = {do_w18 ? 1u : 0u, 0u, 0u, 0u};
-                        if (do_p6) {
-                            if (nb[0] != a) { if (lo) inc[0] += 1u << 16; else inc[1] += 1u; }
-                            if (nb[1] != a) { if (lo) inc[1] += 1u << 16; else inc[2] += 1u; }
-                            if (nb[2] != a) { if (lo) inc[2] += 1u << 16; else inc[3] += 1u; }
+                    if (nd <= 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t d = q == 0 ? d0 : q == 1 ? d1 : q == 2 ? d2 : d3;
+                            if (q < nd) {
+                                uint32_t inc[PT_WORDS];
+                                voxel_increments(inc, a < d, do_w18, do_p6 && nb[0] == d, do_p6 && nb[1] == d,
+                                                 do_p6 && nb[2] == d);
+                                pair_add_packed<T>(sh, pt, Vox<T>::key(a, d), inc);
+                            }
                         }
-                        pair_add_packed(sh, pt, ta_pair_key(a, d0), inc);
                     } else {
-                        // junction voxel: distinct other labels in registers (up to 4), one packed add per label
-                        uint32_t d1 = a, d2 = a, d3 = a;
-                        int nd = 1;
-#pragma unroll
-                        for (int k = 0; k < 18; ++k) {
-                            const uint32_t b = nb[k];
-                            const bool isnew = (b != a) & (b != d0) & (b != d1) & (b != d2) & (b != d3);
-                            d1 = (isnew && nd == 1) ? b : d1;
-                            d2 = (isnew && nd == 2) ? b : d2;
-                            d3 = (isnew && nd == 3) ? b : d3;
-                            nd += isnew ? 1 : 0;
+                        // more than four distinct other labels (noise-like data): exact first-occurrence rescan
+                        if (do_p6) {
+                            if (nb[0] != a) pair_add<T>(sh, pt, a, nb[0], a < nb[0] ? 0 : 1, 1u);
+                            if (nb[1] != a) pair_add<T>(sh, pt, a, nb[1], a < nb[1] ? 2 : 3, 1u);
+                            if (nb[2] != a) pair_add<T>(sh, pt, a, nb[2], a < nb[2] ? 4 : 5, 1u);
                         }
-                        if (nd <= 4) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t d = q == 0 ? d0 : q == 1 ? d1 : q == 2 ? d2 : d3;
-                                if (q >= nd) break;
-                                const bool lo = a < d;
-                                uint32_t inc[PT_WORDS] = {do_w18 ? 1u : 0u, 0u, 0u, 0u};
-                                if (do_p6) {
-                                    if (nb[0] == d) { if (lo) inc[0] += 1u << 16; else inc[1] += 1u; }
-                                    if (nb[1] == d) { if (lo) inc[1] += 1u << 16; else inc[2] += 1u; }
-                                    if (nb[2] == d) { if (lo) inc[2] += 1u << 16; else inc[3] += 1u; }
-                                }
-                                pair_add_packed(sh, pt, ta_pair_key(a, d), inc);
-                            }
-                        } else {
-                            // more than four distinct other labels (noise-like data): exact first-occurrence rescan
-                            if (do_p6) {
-                                if (nb[0] != a) pair_add(sh, pt, a, nb[0], a < nb[0] ? 0 : 1, 1u);
-                                if (nb[1] != a) pair_add(sh, pt, a, nb[1], a < nb[1] ? 2 : 3, 1u);
-                                if (nb[2] != a) pair_add(sh, pt, a, nb[2], a < nb[2] ? 4 : 5, 1u);
-                            }
-                            if (do_w18) {
+                        if (do_w18) {
 #pragma unroll 1
-                                for (int k = 0; k < 18; ++k) {
-                                    const uint32_t b = p[neighbour_offset<ROWE, PLANEE>(k)];
-                                    if (b == a) continue;
-                                    bool seen = false;
-                                    for (int q = 0; q < k; ++q)
-                                        seen |= ((uint32_t)p[neighbour_offset<ROWE, PLANEE>(q)] == b);
-                                    if (!seen) pair_add(sh, pt, a, b, 6, 1u);
-                                }
+                            for (int k = 0; k < 18; ++k) {
+                                const uint32_t b = p[neighbour_offset<ROWE, PLANEE>(k)];
+                                if (b == a) continue;
+                                bool seen = false;
+                                for (int q = 0; q < k; ++q)
+                                    seen |= ((uint32_t)p[neighbour_offset<ROWE, PLANEE>(q)] == b);
+                                if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
                             }
                         }
                     }
@@ -534,7 +670,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         }
 
         // ---- phase F: flush the per-brick tables ---------------------------------------------------------------------
-        {
+        if (!(P.flags & 0x400u)) {
             for (int i = tid; i < LT_SLOTS; i += NTHREADS) {
                 uint32_t L = sh.lt_key[i];
                 if (L == TA_EMPTY32) continue;
@@ -545,10 +681,10 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 sh.lt_key[i] = TA_EMPTY32;
             }
             for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
-                u64 key = sh.pt_key[i];
-                if (key == TA_EMPTY64) continue;
+                PKey key = sh.pt_key[i];
+                if (key == Vox<T>::PEMPTY) continue;
                 uint32_t* d = &sh.pt_val[i * PT_WORDS];
-                int slot = ta_pair_slot(pt, key);
+                int slot = ta_pair_slot(pt, Vox<T>::key64(key));
 #pragma unroll
                 for (int idx = 0; idx < 7; ++idx) {
                     uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
@@ -556,7 +692,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 }
 #pragma unroll
                 for (int w = 0; w < PT_WORDS; ++w) d[w] = 0u;
-                sh.pt_key[i] = TA_EMPTY64;
+                sh.pt_key[i] = Vox<T>::PEMPTY;
             }
         }
         __syncthreads();
