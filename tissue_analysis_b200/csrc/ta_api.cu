@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,7 @@ struct ta_ctx {
     double* d_evals = nullptr;
     double* d_evecs = nullptr;
     size_t eig_alloc_rows = 0;
+    u64* phase_cycles = nullptr;
 
     cudaEvent_t ev[6] = {};
     float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
@@ -124,7 +126,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->status); cudaFree(ctx->counters);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
-    cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
+    cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -305,11 +307,18 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     P.flags = flags;
     P.vec_ok = ((ctx->nf % seg) == 0) && (((uintptr_t)ctx->vol & 15) == 0);
     P.brick_counter = &ctx->counters[0];
+    P.phase_cycles = nullptr;
+    const bool phase_timing = getenv("TA_PHASE_TIMING") != nullptr;
+    if (phase_timing) {
+        if (!ctx->phase_cycles) TA_CUDA(cudaMalloc((void**)&ctx->phase_cycles, 8 * sizeof(u64)));
+        TA_CUDA(cudaMemsetAsync(ctx->phase_cycles, 0, 8 * sizeof(u64), st));
+        P.phase_cycles = ctx->phase_cycles;
+    }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
     if (total > 0xFFFFFFF0ull) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass");
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (total > 0) {
-        int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 2);
+        int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
         if (ctx->elem == 2)
             ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt);
         else
@@ -318,6 +327,17 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
         TA_CUDA(cudaGetLastError());
     }
     TA_CUDA(cudaEventRecord(ctx->ev[2], st));
+    if (phase_timing) {
+        u64 cyc[8];
+        TA_CUDA(cudaMemcpyAsync(cyc, ctx->phase_cycles, sizeof cyc, cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        double tot = 0;
+        for (int k = 0; k < 8; ++k) tot += (double)cyc[k];
+        const char* nm[8] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush"};
+        fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
+        fprintf(stderr, "\n");
+    }
 
     rc = build_records(ctx);
     if (rc) return rc;
@@ -327,6 +347,8 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     TA_CUDA(cudaStreamSynchronize(st));
     TA_CUDA(cudaEventElapsedTime(&ctx->scan_ms, ctx->ev[1], ctx->ev[2]));
     TA_CUDA(cudaEventElapsedTime(&ctx->pass_ms, ctx->ev[0], ctx->ev[3]));
+    if (phase_timing) fprintf(stderr, "[ta] moment-slot evictions: %u (%.3f per segment column)\n", status[2],
+                              (double)status[2] / ((double)total * ta::NTHREADS));
     if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow: retry with a larger pair_capacity_hint");
     if (status[1]) return fail(ctx, TA_ERR_LABEL_RANGE, "a label exceeds max_label_hint");
     ctx->have_tables = true;
@@ -459,7 +481,7 @@ int ta_inertia_table(ta_ctx* ctx, double* evals, double* evecs) {
     cudaStream_t st = ctx->stream;
     size_t n = ctx->lt.nrows;
     if (ctx->eig_alloc_rows < n) {
-        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
+        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
         ctx->d_evals = ctx->d_evecs = nullptr; ctx->eig_alloc_rows = 0;
         TA_CUDA(cudaMalloc((void**)&ctx->d_evals, n * 3 * sizeof(double)));
         TA_CUDA(cudaMalloc((void**)&ctx->d_evecs, n * 9 * sizeof(double)));

@@ -30,9 +30,11 @@ constexpr int NFS = 16;                 // 16-byte segments per brick row
 constexpr int BM = 16;                  // brick rows (mid axis)
 constexpr int BS = 8;                   // brick planes (slow axis)
 constexpr int NTHREADS = NFS * BM;      // one thread per segment column
-constexpr int LT_SLOTS = 64;            // per-brick label slots
+constexpr int LT_SLOTS = 32;            // per-brick label slots (power of two)
+constexpr int LT_BITS = 5;
 constexpr int LT_FIELDS = 16;           // n, sf, sm, ss, sff, sfm, sfs, smm, sms, sss, min f/m/s, max f/m/s
-constexpr int PT_SLOTS = 256;           // per-brick pair slots
+constexpr int PT_SLOTS = 128;           // per-brick pair slots (power of two)
+constexpr int PT_BITS = 7;
 constexpr int PT_WORDS = 4;             // packed 16-bit counters: [w18|f0] [f1|f2] [f3|f4] [f5|-]
 constexpr int TILE_ROWS = (BS + 2) * (BM + 2);
 constexpr int ROWV = NFS + 2;           // vectors per tile row
@@ -50,7 +52,7 @@ template <> struct Vox<uint16_t> {
     static constexpr PKey PEMPTY = 0xFFFFFFFFu;
     static __device__ __forceinline__ PKey key(uint32_t a, uint32_t b) { return a < b ? (a << 16) | b : (b << 16) | a; }
     static __device__ __forceinline__ u64 key64(PKey k) { return ((u64)(k >> 16) << 32) | (k & 0xFFFFu); }
-    static __device__ __forceinline__ uint32_t hash(PKey k) { return (k * 0x9E3779B1u) >> 24; }
+    static __device__ __forceinline__ uint32_t hash(PKey k) { return (k * 0x9E3779B1u) >> (32 - PT_BITS); }
 };
 template <> struct Vox<uint32_t> {
     static constexpr int SEG = 4, LOG_SEG = 2;
@@ -61,14 +63,14 @@ template <> struct Vox<uint32_t> {
     static __device__ __forceinline__ PKey key(uint32_t a, uint32_t b) { return ta_pair_key(a, b); }
     static __device__ __forceinline__ u64 key64(PKey k) { return k; }
     static __device__ __forceinline__ uint32_t hash(PKey k) {
-        return (((uint32_t)(k >> 32) * 0x9E3779B1u) ^ ((uint32_t)k * 0x85EBCA77u)) >> 24;
+        return (((uint32_t)(k >> 32) * 0x9E3779B1u) ^ ((uint32_t)k * 0x85EBCA77u)) >> (32 - PT_BITS);
     }
 };
 
 template <typename T> constexpr size_t scan_smem_bytes() {
     return (size_t)TILE_SEGS * 16 + (size_t)TILE_ROWS * NFS * sizeof(typename Vox<T>::Code) + LT_SLOTS * 4 +
            LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + PT_SLOTS * PT_WORDS * 4 +
-           SEGLIST_CAP * 2 + 2 * VOXLIST_CAP * 2 + 32;
+           SEGLIST_CAP * 2 + 2 * VOXLIST_CAP * 2 + 64;
 }
 
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
@@ -76,6 +78,14 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 template <typename T> struct BrickShared {
@@ -119,7 +129,7 @@ __device__ __forceinline__ void label_to_global(const LabelTable& lt, uint32_t* 
 template <typename T>
 __device__ __forceinline__ void label_add(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
                                           uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0) {
-    uint32_t slot = (L * 0x9E3779B1u) >> 26;   // 6 bits
+    uint32_t slot = (L * 0x9E3779B1u) >> (32 - LT_BITS);
     int found = -1;
     for (int probe = 0; probe < LT_SLOTS; ++probe) {
         uint32_t k = *((volatile uint32_t*)&sh.lt_key[slot]);
@@ -133,45 +143,94 @@ __device__ __forceinline__ void label_add(const BrickShared<T>& sh, const LabelT
     if (found < 0) { label_to_global(lt, status, L, v, F0, M0, S0); return; }
     uint32_t* d = &sh.lt_val[found * LT_FIELDS];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) if (v[i]) atomicAdd(&d[i], v[i]);
+    for (int i = 0; i < 10; ++i) atomicAdd(&d[i], v[i]);   // branch-free: zero adds are harmless
 #pragma unroll
     for (int i = 10; i < 13; ++i) atomicMin(&d[i], v[i]);
 #pragma unroll
     for (int i = 13; i < 16; ++i) atomicMax(&d[i], v[i]);
 }
 
-// all 32 lanes call; lanes with L == TA_EMPTY32 contribute nothing.  One shared-table update per distinct label.
-template <typename T>
-__device__ __forceinline__ void label_add_warp(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
-                                               uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0, int lane) {
-    const unsigned grp = __match_any_sync(0xffffffffu, L);
-    uint32_t r[LT_FIELDS];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) r[i] = __reduce_add_sync(grp, v[i]);
-#pragma unroll
-    for (int i = 10; i < 13; ++i) r[i] = __reduce_min_sync(grp, v[i]);
-#pragma unroll
-    for (int i = 13; i < 16; ++i) r[i] = __reduce_max_sync(grp, v[i]);
-    if (L != TA_EMPTY32 && lane == __ffs(grp) - 1) label_add(sh, lt, status, L, r, F0, M0, S0);
-}
-
 // thread-private moment accumulator for one label over the thread's (fseg, m) column
+// Six registers, bit-packed (a column is at most 8 lanes x 8 planes, f < 128, s < 8):
+//   pS  n [0..6]  | sum s [7..15]   | sum s^2 [16..27]     one IMAD per run: len * (1 | s<<7 | s^2<<16)
+//   pF  sum f [0..12] | sum f*s [13..27]                   one IMAD per run: runsum_f * (1 | s<<13)
+//   sff sum f^2
+//   g   f_min | (255 - f_max) << 16   h   s_min | (255 - s_max) << 16     both updated with one vmin.u16x2
 struct MomSlot {
-    uint32_t label, n, sf, ss, sff, sfs, sss, fmin, fmax, smin, smax;
+    uint32_t label, pS, pF, sff, g, h;
     __device__ __forceinline__ void reset(uint32_t L) {
-        label = L; n = sf = ss = sff = sfs = sss = 0u; fmin = 0xFFFFFFFFu; fmax = 0u; smin = 0xFFFFFFFFu; smax = 0u;
+        label = L; pS = pF = sff = 0u; g = h = 0xFFFFFFFFu;
     }
-    __device__ __forceinline__ void add(uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t s, uint32_t f_first,
-                                        uint32_t f_last) {
-        n += len; sf += sfr; ss += len * s; sff += sffr; sfs += s * sfr; sss += len * s * s;
-        fmin = min(fmin, f_first); fmax = max(fmax, f_last); smin = min(smin, s); smax = max(smax, s);
+    __device__ __forceinline__ void add(uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t kS, uint32_t kF,
+                                        uint32_t gf, uint32_t hs) {
+        pS += len * kS; pF += sfr * kF; sff += sffr;
+        g = __vminu2(g, gf); h = __vminu2(h, hs);
     }
+    __device__ __forceinline__ uint32_t n() const { return pS & 0x7Fu; }
+    __device__ __forceinline__ uint32_t ss() const { return (pS >> 7) & 0x1FFu; }
+    __device__ __forceinline__ uint32_t sss() const { return pS >> 16; }
+    __device__ __forceinline__ uint32_t sf() const { return pF & 0x1FFFu; }
+    __device__ __forceinline__ uint32_t sfs() const { return pF >> 13; }
+    __device__ __forceinline__ uint32_t fmin() const { return g & 0xFFFFu; }
+    __device__ __forceinline__ uint32_t fmax() const { return 255u - (g >> 16); }
+    __device__ __forceinline__ uint32_t smin() const { return h & 0xFFFFu; }
+    __device__ __forceinline__ uint32_t smax() const { return 255u - (h >> 16); }
     __device__ __forceinline__ void fields(uint32_t v[LT_FIELDS], uint32_t m) const {
-        v[0] = n; v[1] = sf; v[2] = n * m; v[3] = ss; v[4] = sff; v[5] = m * sf; v[6] = sfs;
-        v[7] = n * m * m; v[8] = m * ss; v[9] = sss;
-        v[10] = fmin; v[11] = m; v[12] = smin; v[13] = fmax; v[14] = m; v[15] = smax;
+        const uint32_t n_ = n(), sf_ = sf(), ss_ = ss();
+        v[0] = n_; v[1] = sf_; v[2] = n_ * m; v[3] = ss_; v[4] = sff; v[5] = m * sf_; v[6] = sfs();
+        v[7] = n_ * m * m; v[8] = m * ss_; v[9] = sss();
+        v[10] = fmin(); v[11] = m; v[12] = smin(); v[13] = fmax(); v[14] = m; v[15] = smax();
     }
 };
+
+// Column-end merge of one slot across the warp (all 32 lanes call; lanes whose slot is empty pass
+// L == TA_EMPTY32).  A warp covers two m rows (lanes 0-15: m0, lanes 16-31: m0 + 1), so the m terms follow from
+// the totals and the totals of the upper half: 9 full-mask redux per distinct label instead of 16.
+template <typename T>
+__device__ __forceinline__ void slot_flush_warp(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
+                                                const MomSlot& sl, uint32_t m0, u64 F0, u64 M0, u64 S0, int lane) {
+    const uint32_t L = sl.pS ? sl.label : TA_EMPTY32;
+    const bool upper = lane >= 16;
+    const uint32_t n = sl.n(), sf = sl.sf(), ss = sl.ss();
+    const uint32_t w1 = n | (ss << 12);
+    const uint32_t w2 = sl.sss() | ((upper ? n : 0u) << 17);
+    const uint32_t w3 = sf | ((upper ? ss : 0u) << 18);
+    const uint32_t w4 = sl.sfs(), w5 = sl.sff, w6 = upper ? sf : 0u;
+    const uint32_t w7 = sl.fmin(), w8 = sl.fmax();
+    const uint32_t w9 = sl.pS ? ((1u << sl.smin()) | (1u << sl.smax())) : 0u;
+    unsigned pending = __ballot_sync(0xffffffffu, L != TA_EMPTY32);
+    uint32_t r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0, r8 = 0, r9 = 0, rb = 0;
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t Lk = __shfl_sync(0xffffffffu, L, leader);
+        const bool mine = (L == Lk);
+        const bool lead = (lane == leader);
+        const unsigned mb = __ballot_sync(0xffffffffu, mine);
+        uint32_t t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w1 : 0u); if (lead) r1 = t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w2 : 0u); if (lead) r2 = t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w3 : 0u); if (lead) r3 = t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w4 : 0u); if (lead) r4 = t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w5 : 0u); if (lead) r5 = t;
+        t = __reduce_add_sync(0xffffffffu, mine ? w6 : 0u); if (lead) r6 = t;
+        t = __reduce_min_sync(0xffffffffu, mine ? w7 : 0xFFFFFFFFu); if (lead) r7 = t;
+        t = __reduce_max_sync(0xffffffffu, mine ? w8 : 0u); if (lead) r8 = t;
+        t = __reduce_or_sync(0xffffffffu, mine ? w9 : 0u); if (lead) r9 = t;
+        if (lead) { rb = mb; am_leader = true; }
+        pending &= ~mb;
+    }
+    if (am_leader) {       // every group leader updates the shared table in the same SIMT pass
+        const uint32_t nt = r1 & 0xFFFu, sst = r1 >> 12, ssst = r2 & 0x1FFFFu, n1 = r2 >> 17;
+        const uint32_t sft = r3 & 0x3FFFFu, ss1 = r3 >> 18, sf1 = r6;
+        uint32_t v[LT_FIELDS];
+        v[0] = nt; v[1] = sft; v[2] = m0 * nt + n1; v[3] = sst; v[4] = r5; v[5] = m0 * sft + sf1; v[6] = r4;
+        v[7] = m0 * m0 * nt + (2 * m0 + 1) * n1; v[8] = m0 * sst + ss1; v[9] = ssst;
+        v[10] = r7; v[11] = (rb & 0xFFFFu) ? m0 : m0 + 1; v[12] = __ffs(r9) - 1;
+        v[13] = r8; v[14] = (rb >> 16) ? m0 + 1 : m0; v[15] = 31 - __clz(r9);
+        label_add(sh, lt, status, L, v, F0, M0, S0);
+    }
+}
 
 // ---- per-brick pair accumulation (packed 16-bit counters; a brick has < 65536 voxels) ------------------------
 // field 6 = wall18, fields 0..5 = directional faces.  idx = field+1 (wall18 -> 0): word idx>>1, half idx&1.
@@ -189,7 +248,7 @@ __device__ __forceinline__ void pair_add_packed(const BrickShared<T>& sh, const 
         }
         if (hit) {
 #pragma unroll
-            for (int w = 0; w < PT_WORDS; ++w) if (inc[w]) atomicAdd(&sh.pt_val[slot * PT_WORDS + w], inc[w]);
+            for (int w = 0; w < PT_WORDS; ++w) atomicAdd(&sh.pt_val[slot * PT_WORDS + w], inc[w]);
             return;
         }
         slot = (slot + 1) & (PT_SLOTS - 1);
@@ -221,7 +280,11 @@ __device__ __forceinline__ void voxel_increments(uint32_t inc[PT_WORDS], bool lo
     inc[3] = ((fsl && !lo) ? 1u : 0u);
 }
 
-__device__ __forceinline__ uint32_t sumsq_upto(uint32_t k) { return k * (k + 1) * (2 * k + 1) / 6; }  // 0..k
+// sum of j^2 for j < k, k = 0..8, from two packed byte tables (no cubic, no division)
+__device__ __forceinline__ uint32_t sumsq_below(uint32_t k) {
+    const uint32_t lo = 0x05010000u, hi = 0x5B371E0Eu;   // 0,0,1,5 | 14,30,55,91
+    return k >= 8 ? 140u : (((k & 4u) ? hi : lo) >> ((k & 3u) * 8)) & 0xFFu;
+}
 
 // ---- SIMD helpers on one 16-byte segment ------------------------------------------------------------------------
 template <typename T> struct Boundary;
@@ -283,6 +346,70 @@ template <> struct Boundary<uint32_t> {
     }
 };
 
+// ---- phase D: the 18 neighbours of one voxel -> first other label d0 (== a if none) and "only one other
+// label" flag; also returns the +f / +m / +s neighbour labels for the face counters.
+template <typename T> struct NeighbourTest;
+
+template <> struct NeighbourTest<uint32_t> {
+    template <int ROWE, int PLANEE>
+    static __device__ __forceinline__ void run(const uint32_t* p, int, uint32_t& a, uint32_t& d0, bool& simple,
+                                               uint32_t& nbf, uint32_t& nbm, uint32_t& nbs) {
+        constexpr int offs[18] = {1, ROWE, PLANEE, -1, -ROWE, -PLANEE, -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
+                                  -PLANEE - 1, -PLANEE + 1, PLANEE - 1, PLANEE + 1,
+                                  -PLANEE - ROWE, -PLANEE + ROWE, PLANEE - ROWE, PLANEE + ROWE};
+        a = p[0];
+        uint32_t nb[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) nb[k] = p[offs[k]];
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) x |= nb[k] ^ a;       // == a ^ d0 when there is a single other label
+        d0 = a ^ x;
+        uint32_t bad = 0;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) bad |= min(nb[k] ^ a, nb[k] ^ d0);
+        simple = (bad == 0);
+        nbf = nb[0]; nbm = nb[1]; nbs = nb[2];
+    }
+};
+
+// uint16: neighbours are fetched as aligned 32-bit pairs where possible and tested two at a time
+// (min(v ^ a, v ^ d0) == 0 per 16-bit lane <=> v is a or d0).
+template <> struct NeighbourTest<uint16_t> {
+    template <int ROWE, int PLANEE>
+    static __device__ __forceinline__ void run(const uint16_t* p, int j, uint32_t& a, uint32_t& d0, bool& simple,
+                                               uint32_t& nbf, uint32_t& nbm, uint32_t& nbs) {
+        const int odd = j & 1;
+        const int far = odd ? 1 : -1;            // the lane next to the aligned pair, on its other side
+        const uint16_t* pw = p - odd;            // 4-byte aligned: lanes (j & ~1, (j & ~1) + 1)
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pw);
+        const uint32_t wmm = *reinterpret_cast<const uint32_t*>(pw - ROWE);
+        const uint32_t wmp = *reinterpret_cast<const uint32_t*>(pw + ROWE);
+        const uint32_t wsm = *reinterpret_cast<const uint32_t*>(pw - PLANEE);
+        const uint32_t wsp = *reinterpret_cast<const uint32_t*>(pw + PLANEE);
+        const uint32_t e0 = p[far], emm = p[far - ROWE], emp = p[far + ROWE], esm = p[far - PLANEE],
+                       esp = p[far + PLANEE];
+        const uint32_t g0 = p[-PLANEE - ROWE], g1 = p[-PLANEE + ROWE], g2 = p[PLANEE - ROWE], g3 = p[PLANEE + ROWE];
+        a = odd ? (w0 >> 16) : (w0 & 0xFFFFu);
+        const uint32_t AA = a * 0x00010001u;
+        const uint32_t r5 = e0 | (emm << 16), r6 = emp | (esm << 16), r7 = esp | (g0 << 16), r8 = g1 | (g2 << 16),
+                       r9 = g3 | (a << 16);
+        uint32_t acc = (w0 ^ AA) | (wmm ^ AA) | (wmp ^ AA) | (wsm ^ AA) | (wsp ^ AA) | (r5 ^ AA) | (r6 ^ AA) |
+                       (r7 ^ AA) | (r8 ^ AA) | (r9 ^ AA);
+        const uint32_t x = (acc | (acc >> 16)) & 0xFFFFu;
+        d0 = a ^ x;
+        const uint32_t DD = d0 * 0x00010001u;
+        uint32_t bad = __vminu2(w0 ^ AA, w0 ^ DD) | __vminu2(wmm ^ AA, wmm ^ DD) | __vminu2(wmp ^ AA, wmp ^ DD) |
+                       __vminu2(wsm ^ AA, wsm ^ DD) | __vminu2(wsp ^ AA, wsp ^ DD) | __vminu2(r5 ^ AA, r5 ^ DD) |
+                       __vminu2(r6 ^ AA, r6 ^ DD) | __vminu2(r7 ^ AA, r7 ^ DD) | __vminu2(r8 ^ AA, r8 ^ DD) |
+                       __vminu2(r9 ^ AA, r9 ^ DD);
+        simple = (bad == 0);
+        nbf = odd ? e0 : (w0 >> 16);
+        nbm = odd ? (wmp >> 16) : (wmp & 0xFFFFu);
+        nbs = odd ? (wsp >> 16) : (wsp & 0xFFFFu);
+    }
+};
+
 // k-th offset of the 18-neighbourhood (1 <= |df|+|dm|+|ds| <= 2) in tile elements; rare-path helper
 template <int ROWE, int PLANEE>
 __device__ __noinline__ int neighbour_offset(int k) {
@@ -299,7 +426,7 @@ __device__ __noinline__ int neighbour_offset(int k) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, 3)
 scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     typedef typename Vox<T>::Code Code;
     typedef typename Vox<T>::PKey PKey;
@@ -318,7 +445,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
     sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
     sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
-    sh.codes = reinterpret_cast<Code*>(sh.ctr + 8);
+    sh.codes = reinterpret_cast<Code*>(sh.ctr + 16);
     sh.seglist = reinterpret_cast<unsigned short*>(sh.codes + TILE_ROWS * NFS);
     sh.voxlist = sh.seglist + SEGLIST_CAP;
     sh.junclist = sh.voxlist + VOXLIST_CAP;
@@ -341,14 +468,21 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
     for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
 
-    for (;;) {
+    long long tp = 0;
+    if (P.phase_cycles && tid == 0) tp = clock64();
+#define TA_TICK(k) if (P.phase_cycles && tid == 0) { long long now_ = clock64(); atomicAdd(&P.phase_cycles[k], (u64)(now_ - tp)); tp = now_; }
+
+    if (tid == 0) sh.ctr[6] = atomicAdd(P.brick_counter, 1u);
+    __syncthreads();
+    for (unsigned iter = 0;; ++iter) {
+        const unsigned int brick = sh.ctr[6 + (iter & 1u)];
+        if (brick >= total) break;
         if (tid == 0) {
-            sh.ctr[0] = atomicAdd(P.brick_counter, 1u);
+            // fetch the next brick index now; it is consumed after the last barrier of this iteration
+            sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
             sh.ctr[1] = 0u; sh.ctr[2] = 0u; sh.ctr[3] = 0u; sh.ctr[4] = 0u; sh.ctr[5] = 0u;
         }
-        __syncthreads();
-        const unsigned int brick = sh.ctr[0];
-        if (brick >= total) break;
+        TA_TICK(0);
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
@@ -364,14 +498,14 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             const T* row = vol + ((size_t)gs * nm + gm) * (size_t)nf;
             uint4 v;
             if (P.vec_ok) {
-                // rows are whole segments: out-of-range halo segments replicate the edge voxel
+                // rows are whole segments: in-range segments are asynchronous 16-byte copies (all in flight at
+                // once); out-of-range halo segments replicate the edge voxel
                 const int gfc = min(max(gf, 0), nf - SEG);
+                if (gf == gfc) { cp_async_16(&sh.tile[i], row + gf); continue; }
                 v = ld_stream_128(row + gfc);
-                if (gf != gfc) {
-                    uint32_t e = (gf < 0) ? ((SEG == 8) ? (v.x & 0xFFFFu) : v.x) : ((SEG == 8) ? (v.w >> 16) : v.w);
-                    if (SEG == 8) e |= e << 16;
-                    v.x = v.y = v.z = v.w = e;
-                }
+                uint32_t e = (gf < 0) ? ((SEG == 8) ? (v.x & 0xFFFFu) : v.x) : ((SEG == 8) ? (v.w >> 16) : v.w);
+                if (SEG == 8) e |= e << 16;
+                v.x = v.y = v.z = v.w = e;
             } else {
                 T tmp[SEG];
 #pragma unroll
@@ -387,7 +521,9 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             }
             sh.tile[i] = v;
         }
+        cp_async_wait_all();
         __syncthreads();
+        TA_TICK(1);
 
         if (P.flags & 0x100u) continue;   // debug: staging only
         // ---- phase B: per row-segment uniformity code (label if the SEG+2 voxels are equal) -------------------
@@ -403,6 +539,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
         }
         __syncthreads();
 
+        TA_TICK(2);
         if (P.flags & 0x200u) continue;   // debug: staging + codes only
         // ---- phase C1: march (moments, interior test, segment worklist) -------------------------------------------
         {
@@ -415,22 +552,34 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             const uint32_t rowsum = SEG * lf0 + SEG * (SEG - 1) / 2;
             const uint32_t rowsq = SEG * lf0 * lf0 + lf0 * SEG * (SEG - 1) + (SEG - 1) * SEG * (2 * SEG - 1) / 6;
 
-            MomSlot A, B;
-            A.reset(TA_EMPTY32); B.reset(TA_EMPTY32);
-            bool mruA = true;
-            auto evict = [&](MomSlot& sl) {
-                if (sl.n) {
-                    uint32_t v[LT_FIELDS];
-                    sl.fields(v, (uint32_t)m);
-                    label_add<T>(sh, lt, pt.status, sl.label, v, gF0, gM0, gS0);
+            // three slots, most recently used first; a fourth label in one column evicts the oldest (rare)
+            MomSlot S0_, S1_, S2_;
+            S0_.reset(TA_EMPTY32); S1_.reset(TA_EMPTY32); S2_.reset(TA_EMPTY32);
+            // Hits add in place (no slot moves).  `last` / `prev` are the two most recently used slot indices; the
+            // victim of a miss is the remaining slot, moved into S2_ first so the eviction code exists once.
+            int last = 0, prev = 1;
+            auto account = [&](uint32_t L, uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t kS, uint32_t kF,
+                               uint32_t gf, uint32_t hs) {
+                int k;
+                if (L == S0_.label) { S0_.add(len, sfr, sffr, kS, kF, gf, hs); k = 0; }
+                else if (L == S1_.label) { S1_.add(len, sfr, sffr, kS, kF, gf, hs); k = 1; }
+                else if (L == S2_.label) { S2_.add(len, sfr, sffr, kS, kF, gf, hs); k = 2; }
+                else {
+                    const int victim = 3 - last - prev;
+                    if (victim == 0) { const MomSlot t = S0_; S0_ = S2_; S2_ = t; }
+                    else if (victim == 1) { const MomSlot t = S1_; S1_ = S2_; S2_ = t; }
+                    if (last == 2) last = victim; else if (prev == 2) prev = victim;   // the old S2_ moved there
+                    if (S2_.pS) {
+                        if (P.phase_cycles) atomicAdd(&pt.status[2], 1u);   // profiling aid: eviction count
+                        uint32_t v[LT_FIELDS];
+                        S2_.fields(v, (uint32_t)m);
+                        label_add<T>(sh, lt, pt.status, S2_.label, v, gF0, gM0, gS0);
+                    }
+                    S2_.reset(L);
+                    S2_.add(len, sfr, sffr, kS, kF, gf, hs);
+                    k = 2;
                 }
-            };
-            auto account = [&](uint32_t L, uint32_t len, uint32_t sfr, uint32_t sffr, uint32_t s, uint32_t f0,
-                               uint32_t f1) {
-                if (L == A.label) { A.add(len, sfr, sffr, s, f0, f1); mruA = true; }
-                else if (L == B.label) { B.add(len, sfr, sffr, s, f0, f1); mruA = false; }
-                else if (mruA) { evict(B); B.reset(L); B.add(len, sfr, sffr, s, f0, f1); mruA = false; }
-                else { evict(A); A.reset(L); A.add(len, sfr, sffr, s, f0, f1); mruA = true; }
+                if (k != last) { prev = last; last = k; }
             };
             auto tcode = [&](int s) -> uint32_t {
                 const int base = ((s + 1) * (BM + 2) + (m + 1)) * NFS + fs;
@@ -446,26 +595,30 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 const bool interior = (t_cur != MIXED) && (t_prev == t_cur) && (t_next == t_cur);
 
                 if (do_mom && active) {
-                    if (e_c != MIXED && nvalid == SEG) {
-                        account(e_c, SEG, rowsum, rowsq, (uint32_t)s, lf0, lf0 + SEG - 1);
-                    } else {
-                        const int tv = (s + 1) * PLANEV + (m + 1) * ROWV + (fs + 1);
-                        const uint4 C = sh.tile[tv];
-                        const T* cp = reinterpret_cast<const T*>(sh.tile + tv);
-                        uint32_t brk = Boundary<T>::run_breaks(C);
-                        int j0 = 0;
-                        while (j0 < nvalid) {
-                            const uint32_t rest = brk >> j0;
-                            int j1 = rest ? j0 + __ffs(rest) : SEG;
-                            j1 = min(j1, nvalid);
-                            const uint32_t L = cp[j0];
-                            const uint32_t len = j1 - j0;
+                    // runs of equal labels inside the segment (one run when the code says "uniform")
+                    const bool uni = (e_c != MIXED);
+                    const int tv = (s + 1) * PLANEV + (m + 1) * ROWV + (fs + 1);
+                    const T* cp = reinterpret_cast<const T*>(sh.tile + tv);
+                    uint32_t brk = 0u;
+                    if (!uni) brk = Boundary<T>::run_breaks(sh.tile[tv]);
+                    const uint32_t us = (uint32_t)s;
+                    const uint32_t kS = 1u | (us << 7) | ((us * us) << 16), kF = 1u | (us << 13);
+                    const uint32_t hs = us | ((255u - us) << 16);
+                    int j0 = 0;
+                    while (j0 < nvalid) {
+                        const uint32_t rest = brk >> j0;
+                        const int j1 = min(rest ? j0 + __ffs(rest) : SEG, nvalid);
+                        const uint32_t L = uni ? e_c : (uint32_t)cp[j0];
+                        const uint32_t len = j1 - j0;
+                        uint32_t sfr = rowsum, sffr = rowsq;
+                        if (len != SEG) {
                             const uint32_t sj = (uint32_t)(j0 + j1 - 1) * len / 2;
-                            const uint32_t sjj = sumsq_upto(j1 - 1) - (j0 > 0 ? sumsq_upto(j0 - 1) : 0u);
-                            account(L, len, len * lf0 + sj, len * lf0 * lf0 + 2 * lf0 * sj + sjj, (uint32_t)s,
-                                    lf0 + j0, lf0 + j1 - 1);
-                            j0 = j1;
+                            const uint32_t sjj = sumsq_below((uint32_t)j1) - sumsq_below((uint32_t)j0);
+                            sfr = len * lf0 + sj;
+                            sffr = len * lf0 * lf0 + 2 * lf0 * sj + sjj;
                         }
+                        account(L, len, sfr, sffr, kS, kF, (lf0 + j0) | ((255u - (lf0 + j1 - 1)) << 16), hs);
+                        j0 = j1;
                     }
                 }
                 // warp-aggregated append of non-interior segments
@@ -481,14 +634,14 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 t_prev = t_cur; t_cur = t_next;
             }
             if (do_mom) {
-                uint32_t v[LT_FIELDS];
-                A.fields(v, (uint32_t)m);
-                label_add_warp<T>(sh, lt, pt.status, A.n ? A.label : TA_EMPTY32, v, gF0, gM0, gS0, lane);
-                B.fields(v, (uint32_t)m);
-                label_add_warp<T>(sh, lt, pt.status, B.n ? B.label : TA_EMPTY32, v, gF0, gM0, gS0, lane);
+                const uint32_t m0 = (uint32_t)(m & ~1);
+                slot_flush_warp<T>(sh, lt, pt.status, S0_, m0, gF0, gM0, gS0, lane);
+                slot_flush_warp<T>(sh, lt, pt.status, S1_, m0, gF0, gM0, gS0, lane);
+                slot_flush_warp<T>(sh, lt, pt.status, S2_, m0, gF0, gM0, gS0, lane);
             }
         }
         __syncthreads();
+        TA_TICK(3);
 
         // ---- phases C2 + D in rounds of NTHREADS listed segments ------------------------------------------------------
         if (do_pairs) {
@@ -540,6 +693,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     }
                 }
                 __syncthreads();
+                TA_TICK(4);
 
                 // D: listed voxels, one per thread per iteration; simple voxels are merged across the warp
                 const int nv = (int)*nvox;
@@ -555,42 +709,38 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                         const int j = e & (SEG - 1);
                         const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
                         const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
-                        const uint32_t a = p[0];
-                        constexpr int offs[18] = {
-                            1, ROWE, PLANEE, -1, -ROWE, -PLANEE,
-                            -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
-                            -PLANEE - 1, -PLANEE + 1, PLANEE - 1, PLANEE + 1,
-                            -PLANEE - ROWE, -PLANEE + ROWE, PLANEE - ROWE, PLANEE + ROWE};
-                        uint32_t nb[18];
-#pragma unroll
-                        for (int k = 0; k < 18; ++k) nb[k] = p[offs[k]];
-                        uint32_t d0 = a;
-                        bool simple = true;
-#pragma unroll
-                        for (int k = 0; k < 18; ++k) {
-                            const uint32_t b = nb[k];
-                            const bool ne = b != a;
-                            const bool first = ne && (d0 == a);
-                            simple = simple && (!ne || first || b == d0);
-                            d0 = first ? b : d0;
-                        }
+                        uint32_t a, d0, nbf, nbm, nbs;
+                        bool simple;
+                        NeighbourTest<T>::template run<ROWE, PLANEE>(p, j, a, d0, simple, nbf, nbm, nbs);
                         if (d0 != a) {
                             if (simple) {
                                 key = Vox<T>::key(a, d0);
-                                voxel_increments(inc, a < d0, do_w18, do_p6 && nb[0] != a, do_p6 && nb[1] != a,
-                                                 do_p6 && nb[2] != a);
+                                voxel_increments(inc, a < d0, do_w18, do_p6 && nbf != a, do_p6 && nbm != a,
+                                                 do_p6 && nbs != a);
                             } else {
                                 junction = true;
                             }
                         }
                     }
-                    // one shared-table update per distinct pair in the warp
+                    // one shared-table update per distinct pair in the warp (warp-uniform loop, full-mask redux)
                     {
-                        const unsigned grp = __match_any_sync(0xffffffffu, key);
-                        uint32_t tot[PT_WORDS];
+                        unsigned pending = __ballot_sync(0xffffffffu, key != Vox<T>::PEMPTY);
+                        uint32_t tot[PT_WORDS] = {0u, 0u, 0u, 0u};
+                        bool am_leader = false;
+                        while (pending) {
+                            const int leader = __ffs(pending) - 1;
+                            const PKey kk = __shfl_sync(0xffffffffu, key, leader);
+                            const bool mine = (key == kk);
 #pragma unroll
-                        for (int w = 0; w < PT_WORDS; ++w) tot[w] = __reduce_add_sync(grp, inc[w]);
-                        if (key != Vox<T>::PEMPTY && lane == __ffs(grp) - 1) pair_add_packed<T>(sh, pt, key, tot);
+                            for (int w = 0; w < PT_WORDS; ++w) {
+                                const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? inc[w] : 0u);
+                                if (lane == leader) tot[w] = r;
+                            }
+                            am_leader = am_leader || (lane == leader);
+                            pending &= ~__ballot_sync(0xffffffffu, mine);
+                        }
+                        // all group leaders update the shared pair table in one SIMT pass
+                        if (am_leader) pair_add_packed<T>(sh, pt, key, tot);
                     }
                     // junction voxels -> third worklist
                     {
@@ -604,6 +754,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     }
                 }
                 __syncthreads();
+                TA_TICK(5);
 
                 // D2: junction voxels: distinct other labels in registers (up to 4), one packed add per label
                 const int nj = (int)*njunc;
@@ -666,6 +817,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     }
                 }
                 __syncthreads();
+                TA_TICK(6);
             }
         }
 
@@ -696,7 +848,9 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             }
         }
         __syncthreads();
+        TA_TICK(7);
     }
+#undef TA_TICK
 }
 
 }  // namespace ta

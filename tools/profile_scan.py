@@ -21,3 +21,5 @@ for i in range(a.passes):
     ctx.run_pass(a.flags, cfg["ncell"] + 1 if vol.element_size() == 4 else 0)
     t = ctx.last_timing()
     print("pass %d: scan %.3f ms, pass %.3f ms -> %.1f Gvoxel/s" % (i, t["scan_ms"], t["pass_ms"], X * Y * Z / t["scan_ms"] / 1e6))
+lo, hi, faces, wall = ctx.pair_table()
+print("pairs %d, sum wall18 / voxels = %.3f, sum faces / voxels = %.3f" % (lo.size, wall.sum() / (X * Y * Z), faces.sum() / (X * Y * Z)))
