@@ -695,31 +695,52 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 __syncthreads();
                 TA_TICK(4);
 
-                // D: listed voxels, one per thread per iteration; simple voxels are merged across the warp
+                // D: listed voxels.  Each thread takes DCH consecutive list entries (they come from one segment, so
+                // they mostly share the label pair) and sums their packed counters in registers; one warp merge per
+                // chunk then updates the shared pair table.
+                constexpr int DCH = 4;
                 const int nv = (int)*nvox;
-                for (int ib = 0; ib < nv; ib += NTHREADS) {
-                    const int i = ib + tid;
+                for (int ib = 0; ib < nv; ib += NTHREADS * DCH) {
                     PKey key = Vox<T>::PEMPTY;
                     uint32_t inc[PT_WORDS] = {0u, 0u, 0u, 0u};
-                    bool junction = false;
-                    uint32_t e = 0;
-                    if (i < nv) {
-                        e = sh.voxlist[i];
-                        const uint32_t sid = e >> LOG_SEG;
-                        const int j = e & (SEG - 1);
-                        const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
-                        const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
-                        uint32_t a, d0, nbf, nbm, nbs;
-                        bool simple;
-                        NeighbourTest<T>::template run<ROWE, PLANEE>(p, j, a, d0, simple, nbf, nbm, nbs);
-                        if (d0 != a) {
-                            if (simple) {
-                                key = Vox<T>::key(a, d0);
-                                voxel_increments(inc, a < d0, do_w18, do_p6 && nbf != a, do_p6 && nbm != a,
-                                                 do_p6 && nbs != a);
-                            } else {
-                                junction = true;
+#pragma unroll 1
+                    for (int c = 0; c < DCH; ++c) {
+                        const int i = ib + tid * DCH + c;
+                        bool junction = false;
+                        uint32_t e = 0;
+                        if (i < nv) {
+                            e = sh.voxlist[i];
+                            const uint32_t sid = e >> LOG_SEG;
+                            const int j = e & (SEG - 1);
+                            const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
+                            const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
+                            uint32_t a, d0, nbf, nbm, nbs;
+                            bool simple;
+                            NeighbourTest<T>::template run<ROWE, PLANEE>(p, j, a, d0, simple, nbf, nbm, nbs);
+                            if (d0 != a) {
+                                if (simple) {
+                                    const PKey k2 = Vox<T>::key(a, d0);
+                                    uint32_t v[PT_WORDS];
+                                    voxel_increments(v, a < d0, do_w18, do_p6 && nbf != a, do_p6 && nbm != a,
+                                                     do_p6 && nbs != a);
+                                    if (k2 != key && key != Vox<T>::PEMPTY) {   // pair changed inside the chunk (rare)
+                                        pair_add_packed<T>(sh, pt, key, inc);
+                                        inc[0] = inc[1] = inc[2] = inc[3] = 0u;
+                                    }
+                                    key = k2;
+                                    inc[0] += v[0]; inc[1] += v[1]; inc[2] += v[2]; inc[3] += v[3];
+                                } else {
+                                    junction = true;
+                                }
                             }
+                        }
+                        // junction voxels -> third worklist
+                        const unsigned ball = __ballot_sync(0xffffffffu, junction);
+                        if (ball) {
+                            unsigned jb = 0;
+                            if (lane == 0) jb = atomicAdd(njunc, (unsigned)__popc(ball));
+                            jb = __shfl_sync(0xffffffffu, jb, 0);
+                            if (junction) sh.junclist[jb + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)e;
                         }
                     }
                     // one shared-table update per distinct pair in the warp (warp-uniform loop, full-mask redux)
@@ -741,16 +762,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                         }
                         // all group leaders update the shared pair table in one SIMT pass
                         if (am_leader) pair_add_packed<T>(sh, pt, key, tot);
-                    }
-                    // junction voxels -> third worklist
-                    {
-                        const unsigned ball = __ballot_sync(0xffffffffu, junction);
-                        if (ball) {
-                            unsigned jb = 0;
-                            if (lane == 0) jb = atomicAdd(njunc, (unsigned)__popc(ball));
-                            jb = __shfl_sync(0xffffffffu, jb, 0);
-                            if (junction) sh.junclist[jb + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)e;
-                        }
                     }
                 }
                 __syncthreads();
