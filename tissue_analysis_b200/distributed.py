@@ -104,6 +104,13 @@ class SlabScan(object):
 
     def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False):
         ns, nm, nf = self.buf.shape
+        if self.elem == 4 and not max_label_hint and self.world > 1:
+            # every rank must size its dense label table identically before the all_reduce
+            mx = self.owned().view(torch.int32).max().to(torch.int64).reshape(1)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            max_label_hint = int(mx.item())
+            if max_label_hint < 0:
+                raise ValueError("labels >= 2**31 are not supported in the sharded path")
         exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.bind_device(self.buf.data_ptr(), self.elem, nf, nm, ns, keepalive=self.buf)
