@@ -209,8 +209,9 @@ static int build_records(ta_ctx* ctx) {
     ctx->nrecords = n;
     if (n == 0) return TA_OK;
     size_t need = 0;
+    const int end_bit = (ctx->elem == 2) ? 48 : 64;   // uint16 labels: key bits 16..31 and 48..63 are zero
     TA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals[0],
-                                            ctx->sort_vals[1], (int)n, 0, 64, st));
+                                            ctx->sort_vals[1], (int)n, 0, end_bit, st));
     if (need > ctx->cub_temp_bytes) {
         if (ctx->cub_temp) TA_CUDA(cudaFree(ctx->cub_temp));
         ctx->cub_temp = nullptr; ctx->cub_temp_bytes = 0;
@@ -218,7 +219,7 @@ static int build_records(ta_ctx* ctx) {
         ctx->cub_temp_bytes = need;
     }
     TA_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, need, ctx->sort_keys[0], ctx->sort_keys[1],
-                                            ctx->sort_vals[0], ctx->sort_vals[1], (int)n, 0, 64, st));
+                                            ctx->sort_vals[0], ctx->sort_vals[1], (int)n, 0, end_bit, st));
     int rc = ensure(ctx, &ctx->records, &ctx->records_alloc, (size_t)n * ta::REC_WORDS);
     if (rc) return rc;
     ta::gather_records_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pt, ctx->sort_keys[1], ctx->sort_vals[1], n,

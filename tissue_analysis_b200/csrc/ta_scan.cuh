@@ -652,11 +652,12 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 if (tid == 0) { sh.ctr[2 + ((round + 1) & 1)] = 0u; sh.ctr[4 + ((round + 1) & 1)] = 0u; }
                 // C2: boundary bits of one listed segment per thread
                 const int idx = base + tid;
-                uint32_t bits = 0, id = 0;
+                uint32_t bits = 0, id = 0, ebase = 0;      // ebase: tile element offset of the segment
                 if (idx < nseg) {
                     id = sh.seglist[idx];
                     const int fs = id % NFS, m = (id / NFS) % BM, s = id / (NFS * BM);
                     const int t = (s + 1) * PLANEV + (m + 1) * ROWV + (fs + 1);
+                    ebase = (uint32_t)t * SEG;
                     const uint4 C = sh.tile[t];
                     uint32_t acc[4] = {0u, 0u, 0u, 0u};
                     Boundary<T>::cross(acc, C, sh.tile, t, false);
@@ -689,7 +690,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                     while (bits) {
                         int j = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        sh.voxlist[pos++] = (unsigned short)((id << LOG_SEG) | j);
+                        sh.voxlist[pos++] = (unsigned short)(ebase + j);   // tile element offset (< 65536)
                     }
                 }
                 __syncthreads();
@@ -710,10 +711,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                         uint32_t e = 0;
                         if (i < nv) {
                             e = sh.voxlist[i];
-                            const uint32_t sid = e >> LOG_SEG;
                             const int j = e & (SEG - 1);
-                            const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
-                            const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
+                            const T* p = tileT + e;
                             uint32_t a, d0, nbf, nbm, nbs;
                             bool simple;
                             NeighbourTest<T>::template run<ROWE, PLANEE>(p, j, a, d0, simple, nbf, nbm, nbs);
@@ -771,10 +770,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
                 const int nj = (int)*njunc;
                 for (int i = tid; i < nj; i += NTHREADS) {
                     const uint32_t e = sh.junclist[i];
-                    const uint32_t sid = e >> LOG_SEG;
-                    const int j = e & (SEG - 1);
-                    const int fs = sid % NFS, m = (sid / NFS) % BM, s = sid / (NFS * BM);
-                    const T* p = tileT + (s + 1) * PLANEE + (m + 1) * ROWE + (fs + 1) * SEG + j;
+                    const T* p = tileT + e;
                     const uint32_t a = p[0];
                     constexpr int offs[18] = {
                         1, ROWE, PLANEE, -1, -ROWE, -PLANEE,
