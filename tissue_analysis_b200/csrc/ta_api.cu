@@ -121,7 +121,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->vol_owned);
-    cudaFree(ctx->lt.count); cudaFree(ctx->lt.s1); cudaFree(ctx->lt.s2); cudaFree(ctx->lt.bmin); cudaFree(ctx->lt.bmax);
+    cudaFree(ctx->lt.count); cudaFree(ctx->lt.bmin);   // two blocks: sums (count|s1|s2) and boxes (bmin|bmax)
     cudaFree(ctx->pt.keys); cudaFree(ctx->pt.vals);
     cudaFree(ctx->status); cudaFree(ctx->counters);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
@@ -272,13 +272,15 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
         nrows = (size_t)mx + 1;
     }
     if (ctx->lt_alloc_rows < nrows) {
-        cudaFree(ctx->lt.count); cudaFree(ctx->lt.s1); cudaFree(ctx->lt.s2); cudaFree(ctx->lt.bmin); cudaFree(ctx->lt.bmax);
+        cudaFree(ctx->lt.count); cudaFree(ctx->lt.bmin);
         ctx->lt = LabelTable{}; ctx->lt_alloc_rows = 0;
-        TA_CUDA(cudaMalloc((void**)&ctx->lt.count, nrows * sizeof(u64)));
-        TA_CUDA(cudaMalloc((void**)&ctx->lt.s1, nrows * 3 * sizeof(u64)));
-        TA_CUDA(cudaMalloc((void**)&ctx->lt.s2, nrows * 6 * sizeof(u64)));
-        TA_CUDA(cudaMalloc((void**)&ctx->lt.bmin, nrows * 3 * sizeof(int)));
-        TA_CUDA(cudaMalloc((void**)&ctx->lt.bmax, nrows * 3 * sizeof(int)));
+        // one block for the sums (count | s1 | s2 = 10 u64 per row) and one for the boxes (bmin | bmax): the sharded
+        // driver all_reduces each block with a single collective
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.count, nrows * 10 * sizeof(u64)));
+        ctx->lt.s1 = ctx->lt.count + nrows;
+        ctx->lt.s2 = ctx->lt.s1 + nrows * 3;
+        TA_CUDA(cudaMalloc((void**)&ctx->lt.bmin, nrows * 6 * sizeof(int)));
+        ctx->lt.bmax = ctx->lt.bmin + nrows * 3;
         ctx->lt_alloc_rows = nrows;
     }
     ctx->lt.nrows = (uint32_t)nrows;

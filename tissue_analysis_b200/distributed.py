@@ -56,15 +56,15 @@ def allreduce_label_tables(count, s1, s2, bmin, bmax):
 def allgather_pair_records(records, world):
     """records: int32[n, 9] (this rank's packed pair rows) -> int32[sum n_r, 9] on every rank."""
     n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = torch.zeros(world, dtype=torch.int64, device=records.device)
+    dist.all_gather_into_tensor(sizes, n)
+    sizes = sizes.tolist()                       # one host synchronisation for all ranks' sizes
     cap = max(max(sizes), 1)
     padded = torch.zeros((cap, REC_WORDS), dtype=records.dtype, device=records.device)
     padded[:records.shape[0]] = records
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded)
-    return torch.cat([g[:s] for g, s in zip(gathered, sizes)], dim=0)
+    gathered = torch.empty((world * cap, REC_WORDS), dtype=records.dtype, device=records.device)
+    dist.all_gather_into_tensor(gathered, padded)             # rank r's rows land at [r * cap, (r + 1) * cap)
+    return torch.cat([gathered[r * cap:r * cap + s] for r, s in enumerate(sizes)], dim=0)
 
 
 class _DeviceView(object):
@@ -123,9 +123,15 @@ class SlabScan(object):
 
     def merge(self):
         (p_count, p_s1, p_s2, p_bmin, p_bmax), n = self.ctx.label_table_device()
-        allreduce_label_tables(device_tensor(p_count, (n,), "<i8"), device_tensor(p_s1, (n * 3,), "<i8"),
-                               device_tensor(p_s2, (n * 6,), "<i8"), device_tensor(p_bmin, (n * 3,), "<i4"),
-                               device_tensor(p_bmax, (n * 3,), "<i4"))
+        if p_s1 == p_count + 8 * n and p_s2 == p_s1 + 24 * n:
+            # the library keeps count | s1 | s2 in one block: one SUM collective for all ten u64 columns
+            dist.all_reduce(device_tensor(p_count, (n * 10,), "<i8"), op=dist.ReduceOp.SUM)
+            dist.all_reduce(device_tensor(p_bmin, (n * 3,), "<i4"), op=dist.ReduceOp.MIN)
+            dist.all_reduce(device_tensor(p_bmax, (n * 3,), "<i4"), op=dist.ReduceOp.MAX)
+        else:
+            allreduce_label_tables(device_tensor(p_count, (n,), "<i8"), device_tensor(p_s1, (n * 3,), "<i8"),
+                                   device_tensor(p_s2, (n * 6,), "<i8"), device_tensor(p_bmin, (n * 3,), "<i4"),
+                                   device_tensor(p_bmax, (n * 3,), "<i4"))
         p_rec, n_rec = self.ctx.pair_records_device()
         if n_rec:
             mine = device_tensor(p_rec, (n_rec, REC_WORDS), "<i4")
