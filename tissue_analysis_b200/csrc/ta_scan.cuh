@@ -527,6 +527,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
 
         if (P.flags & 0x100u) continue;   // debug: staging only
         // ---- phase B: per row-segment uniformity code (label if the SEG+2 voxels are equal) -------------------
+        const uint32_t ref_label = tileT[SEG];            // first in-brick-row element of the tile
+        bool all_ref = true;
         for (int i = tid; i < TILE_ROWS * NFS; i += NTHREADS) {
             const int fs = i % NFS, r = i / NFS;
             const T* rp = tileT + r * ROWE + (fs + 1) * SEG;
@@ -536,8 +538,27 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
             const bool uni = (v.x == pat) & (v.y == pat) & (v.z == pat) & (v.w == pat) &
                              ((uint32_t)rp[-1] == l) & ((uint32_t)rp[SEG] == l);
             sh.codes[i] = (Code)(uni ? l : MIXED);
+            all_ref = all_ref && uni && (l == ref_label);
         }
-        __syncthreads();
+        // Whole tile (brick + halo) is one label (background, or the inside of a large cell): closed-form moments,
+        // no pairs.  MIXED-coded labels (0xFFFF in uint16 volumes) never take this path.
+        if (__syncthreads_and(all_ref && ref_label != MIXED) && !(P.flags & 0x300u)) {
+            if (tid == 0 && do_mom) {
+                const uint32_t a = (uint32_t)min(BF, nf - F0), b = (uint32_t)min(BM, nm - M0),
+                               c = (uint32_t)min(BS, (int)P.own_hi - S0);
+                const uint32_t ta = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
+                const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6,
+                               qc = (c - 1) * c * (2 * c - 1) / 6;
+                uint32_t v[LT_FIELDS];
+                v[0] = a * b * c; v[1] = b * c * ta; v[2] = a * c * tb; v[3] = a * b * tc;
+                v[4] = b * c * qa; v[5] = c * ta * tb; v[6] = b * ta * tc;
+                v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
+                v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
+                label_to_global(lt, pt.status, ref_label, v, gF0, gM0, gS0);
+            }
+            TA_TICK(2);
+            continue;
+        }
 
         TA_TICK(2);
         if (P.flags & 0x200u) continue;   // debug: staging + codes only
