@@ -34,6 +34,17 @@ METRIC = "full_feature_pass_throughput"
 UNIT = "Gvoxel/s"
 
 
+def ncu_traffic_bytes(config, world):
+    """DRAM bytes per scan-kernel launch from the committed `ncu --set full` capture (profiles/), when one exists
+    for this workload; None otherwise (never measured live: a number taken under a profiler is not a bench value)."""
+    if config != "C3" or world != 1:
+        return None
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_scan_c3_metrics.json")))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -53,7 +64,7 @@ class ClockSampler(object):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -269,7 +280,7 @@ def main():
     own_vox = (scan.g_hi - scan.g_lo) * Y * X
     achieved = own_vox * elem / (scan_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "ta::scan_kernel", "kernel_ms": scan_ms_avg,
+                "traffic": ncu_traffic_bytes(args.config, world), "kernel": "ta::scan_kernel", "kernel_ms": scan_ms_avg,
                 "algorithmic_bytes_per_voxel": elem, "peak_source": peak_src}
 
     # ---- e2e: host volume through the C ABI (H2D + pass + D2H of the tables), rank-local slab --------------
