@@ -156,3 +156,50 @@ def test_device_generator_equals_numpy_generator():
     whole = voronoi_device((40, 48, 56), 90, 7, (1, 1, 1), True, "uint16").cpu().numpy()
     part = voronoi_device((40, 48, 56), 90, 7, (1, 1, 1), True, "uint16", zslice=(13, 29)).cpu().numpy()
     assert np.array_equal(part, whole[13:29])
+
+
+def test_time_series_frames_reuse_one_context():
+    """Config C5 in miniature: independent frames through one context; each frame equals its own oracle tables."""
+    from tissue_analysis_b200.timeseries import analyze_frames, frames_of_rank
+    frames = [tissue_image((40, 32, 24 + 3 * k), 30 + 5 * k, seed=10 + k, dome=True) for k in range(3)]
+    got = analyze_frames(frames)
+    assert sorted(got) == [0, 1, 2]
+    for k, f in enumerate(frames):
+        assert_tables_equal(got[k], oracle_tables(np.asarray(f)))
+    assert frames_of_rank(10, rank=3, world=8) == [3] and frames_of_rank(10, rank=1, world=8) == [1, 9]
+
+
+def test_c2_config_tables_against_c_oracle_and_sampled_api():
+    """BASELINE config C2: 512x512x256 uint16, 5000 seeds, voxelsize (0.2, 0.2, 0.5): tables bit-exact against the C
+    oracle, API features (incl. wall areas and inertia axes) against the loop oracle on a sample of labels."""
+    import torch
+    from oracle import c_onepass
+    from tissue_analysis_b200.synth import CONFIGS, voronoi_device
+    cfg = CONFIGS["C2"]
+    X, Y, Z = cfg["shape"]
+    zyx = voronoi_device((Z, Y, X), cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"]).cpu().numpy()
+    img = SpatialImage(zyx.transpose(2, 1, 0), voxelsize=cfg["voxelsize"])          # (x, y, z), x fastest
+    prod = SpatialImageAnalysis3D(img, background=1)
+    t = prod._tables()
+    ref = c_onepass.onepass(zyx, nrows=65536)                                          # memory order == (x, y, z) here
+    assert np.array_equal(t.count, ref["count"].astype(np.int64))
+    assert np.array_equal(t.s1, ref["s1"].astype(np.int64)) and np.array_equal(t.s2, ref["s2"].astype(np.int64))
+    assert np.array_equal(t.pair_lo, ref["lo"]) and np.array_equal(t.pair_hi, ref["hi"])
+    assert np.array_equal(t.faces, ref["faces"].astype(np.int64)) and np.array_equal(t.wall18, ref["wall18"].astype(np.int64))
+    # sampled API parity against the per-label loops of the reference restatement
+    orc = LoopOracle(np.asarray(img), voxelsize=cfg["voxelsize"], background=1)
+    rng = np.random.default_rng(0)
+    labels = sorted(rng.choice(prod.labels(), size=12, replace=False).tolist())
+    assert prod.volume(list(labels)) == orc.volume(list(labels))
+    cp, co = prod.center_of_mass(list(labels)), orc.center_of_mass(list(labels))
+    for l in labels:
+        assert np.array_equal(np.asarray(cp[l]), np.asarray(co[l]))
+        assert prod.boundingbox(l) == orc.boundingbox(l)
+        nb = sorted(map(int, orc.neighbors(l)))
+        assert sorted(prod.neighbors(l)) == nb
+        wa_o = orc.cell_wall_area(l, nb)
+        assert prod.cell_wall_area(l, nb) == dict(((int(a), int(b)), v) for (a, b), v in wa_o.items())
+    (vp, wp), (vo, wo) = prod.inertia_axis(list(labels)), orc.inertia_axis(list(labels))
+    from tests.helpers import assert_eig_close
+    for l in labels:
+        assert_eig_close(vp[l], wp[l], vo[l], np.real(wo[l]))
