@@ -203,3 +203,37 @@ def test_c2_config_tables_against_c_oracle_and_sampled_api():
     from tests.helpers import assert_eig_close
     for l in labels:
         assert_eig_close(vp[l], wp[l], vo[l], np.real(wo[l]))
+
+
+def test_pair_table_overflow_is_detected_and_retried():
+    """A pair table that is too small must never drop pairs: the C ABI reports TA_ERR_PAIR_OVERFLOW and the wrapper
+    redoes the pass with a larger table."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import tables_from_memory_order
+    rng = np.random.default_rng(5)
+    arr = rng.integers(0, 300, size=(24, 40, 64)).astype(np.uint16)          # ~45 000 distinct touching pairs
+    ctx = _native.Context()
+    ctx.bind_host(arr)
+    rc = ctx.lib.ta_run_pass(ctx.h, _native.PASS_ALL, 0, 300)                 # capacity for ~300 pairs only
+    assert rc == _native.TA_ERR_PAIR_OVERFLOW
+    with pytest.raises(_native.NativeError):
+        ctx.pair_table()                                                      # tables are invalid after an overflow
+    ctx.run_pass(pair_capacity_hint=300)                                      # wrapper: grow and redo
+    count, s1, s2, bbox = ctx.label_table()
+    lo, hi, faces, wall = ctx.pair_table()
+    ctx.close()
+    t = tables_from_memory_order(arr.shape, (2, 1, 0), count, s1, s2, bbox, lo, hi, faces, wall)
+    assert lo.size > 20000
+    assert_tables_equal(t, oracle_tables(arr))
+
+
+def test_label_beyond_hint_is_an_error():
+    from tissue_analysis_b200 import _native
+    arr = np.full((8, 8, 16), 7, np.uint32)
+    arr[3, 3, 3] = 100000
+    ctx = _native.Context()
+    ctx.bind_host(arr)
+    assert ctx.lib.ta_run_pass(ctx.h, _native.PASS_ALL, 50, 0) == _native.TA_ERR_LABEL_RANGE
+    ctx.run_pass()                                                            # hint 0: the library finds the maximum
+    assert ctx.label_table()[0][100000] == 1
+    ctx.close()
