@@ -31,8 +31,10 @@ struct ta_ctx {
     size_t lt_alloc_rows = 0;
     PairTable pt{};
     size_t pt_alloc_cap = 0;
-    uint32_t* status = nullptr;       // [4]
-    unsigned int* counters = nullptr; // [4]: brick counter, compact count, max label, spare
+    uint32_t* status = nullptr;       // [8]: status[4] (pair overflow, label range, evictions, spare) + counters[4]
+    unsigned int* counters = nullptr; // = status + 4: brick counter, compact count, max label, spare
+    uint32_t host_flags[8] = {};      // status + counters as read back at the one synchronisation of build_records
+    bool timing_pending = false;
 
     u64* sort_keys[2] = {nullptr, nullptr};
     uint32_t* sort_vals[2] = {nullptr, nullptr};
@@ -106,8 +108,8 @@ int ta_ctx_create(ta_ctx** out, int device) {
     TA_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto& e : ctx->ev) TA_CUDA(cudaEventCreate(&e));
-    TA_CUDA(cudaMalloc((void**)&ctx->status, 4 * sizeof(uint32_t)));
-    TA_CUDA(cudaMalloc((void**)&ctx->counters, 4 * sizeof(unsigned int)));
+    TA_CUDA(cudaMalloc((void**)&ctx->status, 8 * sizeof(uint32_t)));
+    ctx->counters = ctx->status + 4;
     TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ta::scan_smem_bytes<uint16_t>()));
     TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -123,7 +125,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->vol_owned);
     cudaFree(ctx->lt.count); cudaFree(ctx->lt.bmin);   // two blocks: sums (count|s1|s2) and boxes (bmin|bmax)
     cudaFree(ctx->pt.keys); cudaFree(ctx->pt.vals);
-    cudaFree(ctx->status); cudaFree(ctx->counters);
+    cudaFree(ctx->status);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
@@ -203,9 +205,10 @@ static int build_records(ta_ctx* ctx) {
     int blocks = (int)std::min<size_t>((cap + 255) / 256, (size_t)ctx->num_sms * 8);
     ta::compact_pairs_kernel<<<blocks, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], &ctx->counters[1]);
     ctx->launches++;
-    unsigned int n = 0;
-    TA_CUDA(cudaMemcpyAsync(&n, &ctx->counters[1], sizeof n, cudaMemcpyDeviceToHost, st));
+    // the only host synchronisation of a pass: status flags and the record count in one read-back
+    TA_CUDA(cudaMemcpyAsync(ctx->host_flags, ctx->status, sizeof ctx->host_flags, cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
+    const unsigned int n = ctx->host_flags[4 + 1];
     ctx->nrecords = n;
     if (n == 0) return TA_OK;
     size_t need = 0;
@@ -345,11 +348,8 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     rc = build_records(ctx);
     if (rc) return rc;
     TA_CUDA(cudaEventRecord(ctx->ev[3], st));
-    uint32_t status[4];
-    TA_CUDA(cudaMemcpyAsync(status, ctx->status, sizeof status, cudaMemcpyDeviceToHost, st));
-    TA_CUDA(cudaStreamSynchronize(st));
-    TA_CUDA(cudaEventElapsedTime(&ctx->scan_ms, ctx->ev[1], ctx->ev[2]));
-    TA_CUDA(cudaEventElapsedTime(&ctx->pass_ms, ctx->ev[0], ctx->ev[3]));
+    const uint32_t* status = ctx->host_flags;      // read back inside build_records, after the scan kernel
+    ctx->timing_pending = true;                     // events are resolved lazily by ta_last_timing
     if (phase_timing) fprintf(stderr, "[ta] moment-slot evictions: %u (%.3f per segment column)\n", status[2],
                               (double)status[2] / ((double)total * ta::NTHREADS));
     if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow: retry with a larger pair_capacity_hint");
@@ -446,9 +446,7 @@ int ta_merge_pair_records(ta_ctx* ctx, const void* device_records, uint64_t n) {
     }
     rc = build_records(ctx);
     if (rc) return rc;
-    uint32_t status[4];
-    TA_CUDA(cudaMemcpyAsync(status, ctx->status, sizeof status, cudaMemcpyDeviceToHost, st));
-    TA_CUDA(cudaStreamSynchronize(st));
+    const uint32_t* status = ctx->host_flags;
     if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow in merge");
     ctx->have_tables = true;
     return TA_OK;
@@ -543,6 +541,12 @@ int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, 
 
 int ta_last_timing(ta_ctx* ctx, float* scan_ms, float* pass_ms, float* h2d_ms) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (ctx->timing_pending) {
+        TA_CUDA(cudaEventSynchronize(ctx->ev[3]));
+        TA_CUDA(cudaEventElapsedTime(&ctx->scan_ms, ctx->ev[1], ctx->ev[2]));
+        TA_CUDA(cudaEventElapsedTime(&ctx->pass_ms, ctx->ev[0], ctx->ev[3]));
+        ctx->timing_pending = false;
+    }
     if (scan_ms) *scan_ms = ctx->scan_ms;
     if (pass_ms) *pass_ms = ctx->pass_ms;
     if (h2d_ms) *h2d_ms = ctx->h2d_ms;

@@ -112,7 +112,7 @@ class SlabScan(object):
             if max_label_hint < 0:
                 raise ValueError("labels >= 2**31 are not supported in the sharded path")
         exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
-        torch.cuda.current_stream(self.device).synchronize()
+        # no host synchronisation: the pass is enqueued on the same (torch current) stream as the NCCL waits
         self.ctx.bind_device(self.buf.data_ptr(), self.elem, nf, nm, ns, keepalive=self.buf)
         self.ctx.set_slab(self.own_lo, self.own_hi, self.g_lo - self.own_lo)
         self.ctx.run_pass(flags, max_label_hint, pair_capacity_hint)
@@ -138,8 +138,7 @@ class SlabScan(object):
         else:
             mine = torch.zeros((0, REC_WORDS), dtype=torch.int32, device=self.device)
         allrec = allgather_pair_records(mine, self.world).contiguous()
-        torch.cuda.current_stream(self.device).synchronize()
-        self.ctx.merge_pair_records(allrec.data_ptr(), allrec.shape[0])
+        self.ctx.merge_pair_records(allrec.data_ptr(), allrec.shape[0])     # same stream; synchronises internally
 
     def tables(self, ax_of_mem=(2, 1, 0)):
         """Merged tables as ScanTables (API shape = global (slow, mid, fast) unless ``ax_of_mem`` says otherwise)."""
