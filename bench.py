@@ -257,6 +257,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    scan.stage_ms.clear()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = scan.ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -326,6 +327,9 @@ def main():
         cpu_baseline = {"value": gv, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc,
                         "seconds": sec}
 
+    if rank == 0 and scan.stage_ms:
+        sys.stderr.write("[stage ms per step] " + ", ".join("%s %.3f" % (k, v / args.steps)
+                                                            for k, v in scan.stage_ms.items()) + "\n")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,

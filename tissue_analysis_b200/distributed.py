@@ -97,13 +97,27 @@ class SlabScan(object):
         self.ctx = _native.Context(self.device.index)
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._native = _native
+        self.stage_ms, self._t0 = {}, 0.0
 
     def owned(self):
         """View of the owned planes (fill it by upload or by the device generator)."""
         return self.buf[self.own_lo:self.own_hi]
 
+    def _tick(self, name):
+        """Stage timing for profiling (TA_DIST_TIMING=1): host clock after a device synchronisation."""
+        import os
+        import time
+        if not os.environ.get("TA_DIST_TIMING"):
+            return
+        torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        if name is not None:
+            self.stage_ms[name] = self.stage_ms.get(name, 0.0) + (now - self._t0) * 1e3
+        self._t0 = now
+
     def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False):
         ns, nm, nf = self.buf.shape
+        self._tick(None)
         if self.elem == 4 and not max_label_hint and self.world > 1:
             # every rank must size its dense label table identically before the all_reduce
             mx = self.owned().view(torch.int32).max().to(torch.int64).reshape(1)
@@ -112,14 +126,17 @@ class SlabScan(object):
             if max_label_hint < 0:
                 raise ValueError("labels >= 2**31 are not supported in the sharded path")
         exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
+        self._tick("halo")
         # no host synchronisation: the pass is enqueued on the same (torch current) stream as the NCCL waits
         self.ctx.bind_device(self.buf.data_ptr(), self.elem, nf, nm, ns, keepalive=self.buf)
         self.ctx.set_slab(self.own_lo, self.own_hi, self.g_lo - self.own_lo)
         self.ctx.run_pass(flags, max_label_hint, pair_capacity_hint)
+        self._tick("pass")
         if self.world > 1:
             self.merge()
         if inertia:
             self.ctx.inertia_table(fetch=False)
+        self._tick("inertia")
 
     def merge(self):
         (p_count, p_s1, p_s2, p_bmin, p_bmax), n = self.ctx.label_table_device()
@@ -132,13 +149,16 @@ class SlabScan(object):
             allreduce_label_tables(device_tensor(p_count, (n,), "<i8"), device_tensor(p_s1, (n * 3,), "<i8"),
                                    device_tensor(p_s2, (n * 6,), "<i8"), device_tensor(p_bmin, (n * 3,), "<i4"),
                                    device_tensor(p_bmax, (n * 3,), "<i4"))
+        self._tick("allreduce")
         p_rec, n_rec = self.ctx.pair_records_device()
         if n_rec:
             mine = device_tensor(p_rec, (n_rec, REC_WORDS), "<i4")
         else:
             mine = torch.zeros((0, REC_WORDS), dtype=torch.int32, device=self.device)
         allrec = allgather_pair_records(mine, self.world).contiguous()
+        self._tick("allgather")
         self.ctx.merge_pair_records(allrec.data_ptr(), allrec.shape[0])     # same stream; synchronises internally
+        self._tick("pair merge")
 
     def tables(self, ax_of_mem=(2, 1, 0)):
         """Merged tables as ScanTables (API shape = global (slow, mid, fast) unless ``ax_of_mem`` says otherwise)."""
