@@ -5,22 +5,24 @@
 // voxel itself, which reproduces the reference's "the image border contributes nothing" rule).
 //
 // Phases per brick (irregular work is compacted into worklists first so whole warps stay busy):
-//   A  stage brick + halo: 128-bit streaming loads -> shared tile.
-//   B  per row-segment uniformity code: the label if the SEG+2 voxels (segment + f-halo) are equal.
-//   C1 march: thread (fseg, m) walks s.  Moments go to two register slots per thread (the column of a thread
-//      rarely sees more than two labels): n, sum f, sum s, sum ff, sum fs, sum ss, f/s bounds; the m terms are
-//      closed forms.  Uniform segments cost a handful of adds, mixed segments are split into runs with SIMD
-//      compares.  At the end of the column the slots are merged across the warp (match.any + redux) and one lane
-//      per label updates the per-brick shared label table.  Segments whose 3x3 rows are not one label go to the
-//      SEGMENT worklist.
+//   A  stage brick + halo: 16-byte cp.async copies, all in flight at once -> shared tile.
+//   B  per row-segment uniformity code: the label if the SEG+2 voxels (segment + f-halo) are equal.  A tile that is
+//      one label altogether (background, inside of a large cell) is finished here with closed-form moments.
+//   C1 march: thread (fseg, m) walks s.  Moments go to three bit-packed register slots per thread (a column rarely
+//      sees more labels; 6 registers per slot: n|sum s|sum s^2, sum f|sum fs, sum f^2, f bounds, s bounds; the m
+//      terms are closed forms).  Mixed segments are split into runs with SIMD compares.  At the end of the column
+//      the slots are merged across the warp (a warp-uniform loop over the distinct labels with full-mask redux, 9
+//      redux per label) and the group leaders update the per-brick shared label table in one SIMT pass.  Segments
+//      whose 3x3 rows are not one label go to the SEGMENT worklist.
 //   C2 per listed segment, SIMD on the packed lanes: OR of XORs of the segment with its 18 neighbour vectors
-//      (f-shifted ones built with funnel shifts) -> exact "has a different 18-neighbour" flag per voxel; flagged
-//      voxels go to the VOXEL worklist.
-//   D  per listed voxel: 18 neighbour labels -> first other label + "only one other label" test.  The common case
-//      is merged across the warp (match.any on the pair key, redux of the packed 16-bit counters: wall18 and the
-//      +f/+m/+s faces) and one lane per pair updates the per-brick shared pair table.  Junction voxels (>= 2 other
-//      labels) go to a third worklist and are handled with a register dedup of up to 4 labels.
-//   F  flush the per-brick label table (u32 brick-local sums -> u64 global REDs) and pair table.
+//      (f-shifted ones built with funnel shifts), min.u16x2 to turn non-zero lanes into bits -> exact "has a
+//      different 18-neighbour" bit per voxel; flagged voxels go to the VOXEL worklist (tile element offsets).
+//   D  per listed voxel: 18 neighbours fetched as aligned 32-bit pairs; d0 = a ^ OR(v ^ a) and the "only {a, d0}"
+//      test min.u16x2(v ^ a, v ^ d0) == 0, two neighbours per instruction.  Packed 16-bit counters (wall18 and the
+//      +f/+m/+s faces) are summed over a thread's chunk of consecutive list entries, merged across the warp, and the
+//      group leaders update the per-brick shared pair table.  Junction voxels (>= 2 other labels) go to a third
+//      worklist and are handled with a register dedup of up to 4 labels (exact rescan beyond that).
+//   F  flush the per-brick label table (u32 brick-local sums -> shifted u64 global REDs) and pair table.
 #pragma once
 #include "ta_common.cuh"
 
