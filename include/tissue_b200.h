@@ -120,6 +120,16 @@ int ta_wall_voxel_coords(ta_ctx* ctx, const uint32_t* lo, const uint32_t* hi, ui
  * voxels (SIA:1024-1038).  `out_host` has the volume's shape and dtype. */
 int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, void* out_host);
 
+/* out[p] = lut[volume[p]] (a streaming gather).  Replaces the label -> value image builders
+ * (PropertySpatialImage.create_property_image, property_spatial_image.py:207-221; spatial_image_analysis_to_spatial_image,
+ * tissue_analysis_oalab/sia_to_spatial_image.py:26-55) and, with in_place != 0, the relabelling image mutators
+ * fuse_labels_in_image / remove_labels_from_image (SIA:1114-1165).  `lut_host` has n_lut entries of lut_elem_bytes
+ * (2 or 4) bytes; labels >= n_lut map to `fill`.  in_place: the context's own device copy of the volume is rewritten
+ * (lut_elem_bytes must equal the volume's; a borrowed device volume is refused) and the tables are invalidated.
+ * `out_host`, when not NULL, receives the mapped volume (shape of the volume, lut_elem_bytes per voxel). */
+int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_t n_lut, uint32_t fill,
+                  void* out_host, int in_place);
+
 /* Milliseconds (CUDA events on the context stream) of the last ta_run_pass: scan kernel(s) only, and the
  * whole pass including table clear / compaction / sort; and of the last host->device volume copy. */
 int ta_last_timing(ta_ctx* ctx, float* scan_ms, float* pass_ms, float* h2d_ms);

@@ -57,6 +57,17 @@ class OracleBackend(object):
             out.append(np.array(np.where(hit)).astype(np.int64).reshape(3, -1))
         return out
 
+    def map_labels(self, lut, fill=0):
+        lut = np.asarray(lut)
+        idx = np.minimum(self.img.astype(np.int64), lut.size - 1)
+        return np.where(self.img < lut.size, lut[idx], np.asarray(fill, lut.dtype))
+
+    def relabel(self, mapping):
+        src = self.img.copy()
+        for old, new in mapping.items():
+            self.img[src == old] = new          # in place: self.img aliases the caller's image
+        self.tables = oracle_tables(self.img)
+
     def voxel_first_layer(self, background, keep_background=True):
         mask = self.img == background
         layer = nd.binary_dilation(mask) & ~mask

@@ -237,3 +237,43 @@ def test_label_beyond_hint_is_an_error():
     ctx.run_pass()                                                            # hint 0: the library finds the maximum
     assert ctx.label_table()[0][100000] == 1
     ctx.close()
+
+
+def test_graph_from_image_on_the_gpu():
+    """the graph packing over the CUDA tables == the restated reference graph builder."""
+    from oracle.graph_loops import graph_from_image_oracle
+    from tests.test_graph_cpu import PROPS, compare_graph
+    from tissue_analysis_b200.temporal_graph_from_image import graph_arrays, graph_from_image
+    img = tissue_image((72, 64, 48), 80, seed=41, dome=True, voxelsize=(0.4, 0.4, 1.0), weights=(2, 2, 5))
+    g = graph_from_image(img, spatio_temporal_properties=PROPS, ignore_cells_at_stack_margins=False)
+    o = graph_from_image_oracle(np.asarray(img), properties=PROPS, voxelsize=img.voxelsize,
+                                ignore_cells_at_stack_margins=False)
+    compare_graph(g, o)
+    arr = graph_arrays(SpatialImageAnalysis3D(img, ignoredlabels=0, background=1), ignore_cells_at_stack_margins=False)
+    assert sorted(g.vertices()) == arr.labels.tolist() and g.nb_edges() == arr.edge_lo.size
+
+
+def test_mutators_and_property_image_on_the_gpu():
+    """LUT gather and in-place relabel kernels (ta_map_labels)."""
+    from tests.test_mutators_cpu import reference_mutation
+    from tissue_analysis_b200.property_spatial_image import create_property_image
+    for order in ("C", "F"):
+        img = tissue_image((52, 44, 36), 40, seed=43, dome=True)
+        arr = np.array(np.asarray(img), order=order)
+        work = SpatialImage(arr.copy(order=order), voxelsize=img.voxelsize)
+        prod = SpatialImageAnalysis3D(work, background=1)
+        labels = sorted(prod.labels())
+        vol = prod.volume(real=False)
+        some = dict((l, v) for l, v in vol.items() if l % 3 == 0)
+        out = create_property_image(prod, some, dtype=np.uint16)
+        expect = np.full(arr.shape, 1, np.uint16)
+        for l, v in some.items():
+            expect[arr == l] = np.float64(v).astype(np.uint16)
+        assert np.array_equal(np.asarray(out), expect)
+        fuse, remove = labels[1:4], labels[6:9]
+        prod.fuse_labels_in_image(list(fuse), verbose=False)
+        prod.remove_labels_from_image(list(remove), verbose=False)
+        mutated = reference_mutation(arr, fuse=fuse, remove=remove)
+        assert np.array_equal(np.asarray(work), mutated)
+        fresh = LoopOracle(mutated, voxelsize=img.voxelsize, background=1, ignoredlabels=[0])
+        compare_api(prod, fresh, check_wall_voxels=False, real_modes=(True,))

@@ -27,7 +27,7 @@ EXPORTS = [
     "ta_set_slab", "ta_run_pass", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
     "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
-    "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
+    "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     lib.ta_inertia_eig.argtypes = [vp, vp, u64, vp, vp]
     lib.ta_wall_voxel_coords.argtypes = [vp, vp, vp, u64, vp, vp]
     lib.ta_voxel_first_layer.argtypes = [vp, u32, ci, vp]
+    lib.ta_map_labels.argtypes = [vp, vp, ci, u64, u32, vp, ci]
     lib.ta_last_timing.argtypes = [vp, P(C.c_float), P(C.c_float), P(C.c_float)]
     lib.ta_launch_count.argtypes = [vp, P(u64)]
     lib.ta_synth_voronoi.argtypes = [vp, vp, ci, i64, i64, i64, i64, i64, vp, u32, vp, ci]
@@ -228,6 +229,15 @@ class Context(object):
     def voxel_first_layer(self, background, keep_background, shape_smf, dtype):
         out = np.empty(shape_smf, dtype)
         self._check(self.lib.ta_voxel_first_layer(self.h, int(background), int(bool(keep_background)), _ptr(out)))
+        return out
+
+    def map_labels(self, lut, fill, shape_smf, in_place=False, fetch=True):
+        """out[p] = lut[volume[p]] on the device; lut: 1-D uint16/uint32 array indexed by label."""
+        lut = np.ascontiguousarray(lut)
+        assert lut.dtype in (np.uint16, np.uint32) and lut.ndim == 1
+        out = np.empty(shape_smf, lut.dtype) if fetch else None
+        self._check(self.lib.ta_map_labels(self.h, _ptr(lut), lut.dtype.itemsize, lut.size, int(fill), _ptr(out),
+                                           int(bool(in_place))))
         return out
 
     def last_timing(self):

@@ -539,6 +539,43 @@ int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, 
                                       out_host, ctx->stream, ctx->num_sms, &ctx->launches, &ctx->err);
 }
 
+int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_t n_lut, uint32_t fill, void* out_host,
+                  int in_place) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "no volume bound");
+    if (!lut_host || n_lut == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_map_labels: empty lookup table");
+    if (lut_elem_bytes != 2 && lut_elem_bytes != 4) return fail(ctx, TA_ERR_BAD_ARG, "ta_map_labels: lut_elem_bytes must be 2 or 4");
+    if (in_place && (lut_elem_bytes != ctx->elem || ctx->vol != ctx->vol_owned))
+        return fail(ctx, TA_ERR_BAD_ARG, "ta_map_labels: in-place needs the context-owned volume and a table of its dtype");
+    if (((uintptr_t)ctx->vol & 15) != 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_map_labels: volume is not 16-byte aligned");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)ctx->nf * ctx->nm * ctx->ns;
+    void *d_lut = nullptr, *d_out = nullptr;
+    TA_CUDA(cudaMalloc(&d_lut, n_lut * lut_elem_bytes));
+    TA_CUDA(cudaMemcpyAsync(d_lut, lut_host, n_lut * lut_elem_bytes, cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMalloc(&d_out, n * lut_elem_bytes));
+    const int grid = ctx->num_sms * 16;
+    if (ctx->elem == 2 && lut_elem_bytes == 2)
+        ta::map_labels_kernel<uint16_t, uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)ctx->vol, (uint16_t*)d_out, (const uint16_t*)d_lut, n_lut, (uint16_t)fill, n);
+    else if (ctx->elem == 2)
+        ta::map_labels_kernel<uint16_t, uint32_t><<<grid, 256, 0, st>>>((const uint16_t*)ctx->vol, (uint32_t*)d_out, (const uint32_t*)d_lut, n_lut, fill, n);
+    else if (lut_elem_bytes == 2)
+        ta::map_labels_kernel<uint32_t, uint16_t><<<grid, 256, 0, st>>>((const uint32_t*)ctx->vol, (uint16_t*)d_out, (const uint16_t*)d_lut, n_lut, (uint16_t)fill, n);
+    else
+        ta::map_labels_kernel<uint32_t, uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)ctx->vol, (uint32_t*)d_out, (const uint32_t*)d_lut, n_lut, fill, n);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    if (in_place) {
+        TA_CUDA(cudaMemcpyAsync(ctx->vol_owned, d_out, n * lut_elem_bytes, cudaMemcpyDeviceToDevice, st));
+        ctx->have_tables = false;
+    }
+    if (out_host) TA_CUDA(cudaMemcpyAsync(out_host, d_out, n * lut_elem_bytes, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_lut); cudaFree(d_out);
+    return TA_OK;
+}
+
 int ta_last_timing(ta_ctx* ctx, float* scan_ms, float* pass_ms, float* h2d_ms) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (ctx->timing_pending) {

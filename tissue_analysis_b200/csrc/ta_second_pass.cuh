@@ -181,6 +181,25 @@ inline int wall_voxel_coords_impl(const void* vol, int elem, long long nf, long 
     return rc;
 }
 
+// out[i] = lut[vol[i]] (labels >= n_lut -> fill); one 16-byte vector of input voxels per thread iteration
+template <typename TI, typename TO>
+__global__ void map_labels_kernel(const TI* __restrict__ vol, TO* __restrict__ out, const TO* __restrict__ lut,
+                                  unsigned long long n_lut, TO fill, size_t n) {
+    constexpr int V = 16 / sizeof(TI);
+    const size_t nvec = n / V;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        TI in[V];
+        *reinterpret_cast<uint4*>(in) = *reinterpret_cast<const uint4*>(vol + i * V);
+        TO res[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) res[k] = in[k] < n_lut ? lut[in[k]] : fill;
+#pragma unroll
+        for (int k = 0; k < V; ++k) out[i * V + k] = res[k];
+    }
+    for (size_t i = nvec * V + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = vol[i] < n_lut ? lut[vol[i]] : fill;
+}
+
 template <typename T>
 __global__ void voxel_first_layer_kernel(const T* __restrict__ vol, T* __restrict__ out, VolDims D, uint32_t bg,
                                          int keep_bg) {

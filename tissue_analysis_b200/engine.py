@@ -106,6 +106,7 @@ class VolumeScan(object):
 
     def __init__(self, image, device=-1, flags=_native.PASS_ALL, max_label_hint=0, pair_capacity_hint=0):
         self.view, self.ax_of_mem = memory_layout(image)
+        self._image_ref = np.asarray(image)
         self.shape_api = tuple(np.asarray(image).shape)
         self.ctx = _native.Context(device)
         self.ctx.bind_host(self.view)
@@ -145,11 +146,34 @@ class VolumeScan(object):
             out.append(xyz)
         return out
 
+    def _to_api(self, out_smf):
+        inv = np.argsort([self.ax_of_mem[2], self.ax_of_mem[1], self.ax_of_mem[0]])
+        return np.transpose(out_smf, inv)
+
+    def map_labels(self, lut, fill=0):
+        """API-ordered image ``lut[image]`` (device gather; labels beyond the table map to ``fill``)."""
+        return self._to_api(self.ctx.map_labels(lut, fill, self.view.shape))
+
+    def relabel(self, mapping):
+        """Rewrite labels in place (device copy AND the caller's host image) and invalidate the tables.
+        ``mapping``: {old label: new label}; other labels are kept."""
+        top = max(int(np.iinfo(self.view.dtype).max) + 1 if self.view.dtype == np.uint16 else 0,
+                  max(mapping) + 1 if mapping else 0,
+                  self.tables.nrows if self.tables is not None else int(self.view.max()) + 1)
+        lut = np.arange(top, dtype=np.int64)
+        for old, new in mapping.items():
+            lut[old] = new
+        out = self.ctx.map_labels(lut.astype(self.view.dtype), 0, self.view.shape, in_place=True)
+        if np.shares_memory(self.view, self._image_ref):
+            np.copyto(self.view, out)                      # the view aliases the caller's image memory
+        else:
+            np.copyto(self.view, out)
+            self._image_ref[...] = self._to_api(out)
+        self.tables = None
+
     def voxel_first_layer(self, background, keep_background=True):
         ns, nm, nf = self.view.shape
-        out = self.ctx.voxel_first_layer(background, keep_background, (ns, nm, nf), self.view.dtype)
-        inv = np.argsort([self.ax_of_mem[2], self.ax_of_mem[1], self.ax_of_mem[0]])
-        return np.transpose(out, inv)
+        return self._to_api(self.ctx.voxel_first_layer(background, keep_background, (ns, nm, nf), self.view.dtype))
 
 
 def scan_volume(image, **kw):

@@ -86,16 +86,68 @@ class AbstractSpatialImageAnalysis(object):
     def _tables(self):
         return self._scan().tables
 
-    def invalidate(self):
-        """Drop every cache (call after editing ``self.image`` in place)."""
-        if self._backend is not None and hasattr(self._backend, "rebind"):
-            self._backend.rebind(self.image)
-        elif self._backend is not None:
-            self._backend = None
+    def _drop_caches(self):
+        """Every derived cache goes (the reference only resets ``_labels`` after its image mutators and then serves
+        stale boxes / neighbours; here the next feature request re-runs the pass on the edited volume)."""
         self._labels = self._bbox = self._neighbors = self._cell_layer1 = self._adj = self._com_all = None
         self._center_of_mass = {}
         if hasattr(self, "_voxel_layer1"):
             self._voxel_layer1 = None
+
+    def invalidate(self):
+        """Call after editing ``self.image`` by hand: the volume is bound and scanned again on the next request."""
+        self._backend = None
+        self._drop_caches()
+
+    # ------------------------------------------------------------------------------------------- image mutators
+    def fuse_labels_in_image(self, labels, verbose=True):
+        """SIA:1114-1134: every label of ``labels`` becomes the smallest one (one in-place device relabel)."""
+        assert isinstance(labels, list) and len(labels) >= 2
+        assert self.background() not in labels
+        min_lab = min(labels)
+        labels.remove(min_lab)
+        if verbose:
+            print("Fusing the following {} labels: {} to value '{}'.".format(len(labels), labels, min_lab))
+        t = self._tables()
+        present = [l for l in labels if 0 <= l < t.nrows and t.count[l] > 0]
+        for l in labels:
+            if l not in present:
+                print("No boundingbox found for cell id #{}, skipping...".format(l))
+        if present:
+            self._scan().relabel(dict((l, min_lab) for l in present))
+            self._drop_caches()
+        if verbose:
+            print("Done!")
+        return None
+
+    def remove_labels_from_image(self, labels, erase_value=0, verbose=True):
+        """SIA:1136-1165."""
+        if isinstance(labels, int):
+            labels = [labels]
+        labels = list(labels)
+        if self.background() in labels:
+            labels.remove(self.background())
+        if verbose:
+            print("Removing", len(labels), "cell-labels.")
+        t = self._tables()
+        present = [l for l in labels if 0 <= l < t.nrows and t.count[l] > 0]
+        for l in labels:
+            if l not in present:
+                print("No boundingbox found for cell id #{}, skipping...".format(l))
+        if present:
+            self._scan().relabel(dict((l, erase_value) for l in present))
+            self._drop_caches()
+        self._ignoredlabels.update([erase_value])
+        for label in labels:
+            self._ignoredlabels.discard(label)
+        if verbose:
+            print('Done !!')
+
+    def remove_stack_margin_labels_from_image(self, erase_value=0, voxel_distance_from_margin=5, verbose=True):
+        """SIA:1168-1176."""
+        if verbose:
+            print("Deleting cells at the margins of the stack from 'self.image'...")
+        self.remove_labels_from_image(self.labels_at_stack_margins(voxel_distance_from_margin), erase_value, verbose)
 
     def is3D(self):
         return False
