@@ -120,6 +120,17 @@ int ta_wall_voxel_coords(ta_ctx* ctx, const uint32_t* lo, const uint32_t* hi, ui
  * voxels (SIA:1024-1038).  `out_host` has the volume's shape and dtype. */
 int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, void* out_host);
 
+/* Wall mask of hollow_out_cells (SIA:74-94) / get_all_wall_binary_image (SIA:744-749): out[p] = volume[p] where the
+ * discrete Laplacian (scipy.ndimage.laplace: 'reflect' border, wrap-around arithmetic of the label dtype) is non-zero,
+ * else 0; with mask_only != 0 the output is 1 / 0 instead (label 0 can sit on a wall).  `out_host` has the volume's
+ * shape and dtype. */
+int ta_hollow_out_cells(ta_ctx* ctx, int mask_only, void* out_host);
+
+/* Outer voxel shell of every cell at once, cells_voxel_layer (SIA:1399-1448: mask minus its 18-connected erosion inside
+ * the cell's bounding box): out[p] = 1 where some 18-neighbour of p is outside the volume or carries another label,
+ * else 0.  `out_host` has the volume's shape and dtype. */
+int ta_cell_shell18(ta_ctx* ctx, void* out_host);
+
 /* out[p] = lut[volume[p]] (a streaming gather).  Replaces the label -> value image builders
  * (PropertySpatialImage.create_property_image, property_spatial_image.py:207-221; spatial_image_analysis_to_spatial_image,
  * tissue_analysis_oalab/sia_to_spatial_image.py:26-55) and, with in_place != 0, the relabelling image mutators

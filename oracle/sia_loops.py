@@ -82,6 +82,15 @@ def one_sided_kernels():
     return tuple(out)
 
 
+def hollow_out_cells(image, background, remove_background=True):
+    """SIA:74-94."""
+    image = np.asarray(image)
+    m = image * (nd.laplace(image) != 0)
+    if remove_background:
+        m = m * (m != background)
+    return m
+
+
 class LoopOracle(object):
     """Restates AbstractSpatialImageAnalysis + SpatialImageAnalysis3D (SIA:206-1448)."""
 
@@ -503,6 +512,54 @@ class LoopOracle(object):
         return self.convert_return(by_rows, labels), self.convert_return(vals, labels)
 
     reduced_inertia_axis = inertia_axis  # SIA:1295-1341 is the same computation
+
+    # ------------------------------------------------- remaining voxel stencils
+    def get_all_wall_binary_image(self):
+        # SIA:744-749
+        lp = nd.laplace(self.image)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return lp / lp
+
+    def cells_walls_coords(self):
+        # SIA:883-905; `self.background` (the bound method) is what the reference passes -> nothing is removed
+        m = hollow_out_cells(self.image, None, remove_background=False)
+        x, y, z = np.where(m != 0)
+        return list(x), list(y), list(z)
+
+    def region_boundingbox(self, labels):
+        # SIA:1361-1396
+        if isinstance(labels, list) and len(labels) == 1:
+            return self.boundingbox(labels[0])
+        if isinstance(labels, int):
+            return self.boundingbox(labels)
+        boxes = self.boundingbox(labels)
+        lo = [min(boxes[c][a].start for c in labels) for a in range(3)]
+        hi = [max(boxes[c][a].stop for c in labels) for a in range(3)]
+        return tuple(slice(a, b) for a, b in zip(lo, hi))
+
+    def cells_voxel_layer(self, labels, region_boundingbox=False, single_frame=False):
+        # SIA:1399-1448
+        if isinstance(labels, int):
+            labels = [labels]
+        if single_frame:
+            region_boundingbox = True
+        if region_boundingbox:
+            bbox = self.region_boundingbox(labels)
+        else:
+            bboxes = self.boundingbox(labels, real=False)
+        s18 = nd.generate_binary_structure(3, 2)
+        out = np.zeros_like(self.image[bbox], dtype=int) if single_frame else {}
+        for c in labels:
+            sub = self.image[bbox] if region_boundingbox else self.image[bboxes[c]]
+            mask = sub == c
+            layer = np.array(mask & ~nd.binary_erosion(mask, structure=s18), dtype=int)
+            if single_frame:
+                out += layer
+            else:
+                out[c] = layer
+        if len(labels) == 1:
+            return out[c]
+        return out
 
     # ------------------------------------------ labels_at_stack_margins SIA:1344-1358
     def labels_at_stack_margins(self, voxel_distance_from_margin=5):

@@ -57,6 +57,18 @@ class OracleBackend(object):
             out.append(np.array(np.where(hit)).astype(np.int64).reshape(3, -1))
         return out
 
+    def stencil_image(self, kind):
+        if kind == "hollow":
+            return self.img * (nd.laplace(self.img) != 0)
+        if kind == "laplace":
+            return (nd.laplace(self.img) != 0).astype(self.img.dtype)
+        pad = np.pad(self.img.astype(np.int64), 1, mode="constant", constant_values=-1)
+        X, Y, Z = self.img.shape
+        shell = np.zeros(self.img.shape, bool)
+        for dx, dy, dz in sia_onepass.N18:
+            shell |= pad[1 + dx:1 + dx + X, 1 + dy:1 + dy + Y, 1 + dz:1 + dz + Z] != self.img
+        return shell.astype(self.img.dtype)
+
     def map_labels(self, lut, fill=0):
         lut = np.asarray(lut)
         idx = np.minimum(self.img.astype(np.int64), lut.size - 1)
@@ -162,6 +174,20 @@ def compare_api(prod, orc, check_wall_voxels=True, rtol=1e-6, eig=True, real_mod
                     continue
                 # `real` rescales each eigenvalue by |v * voxelsize| (sign-free), so compare after the fact
                 assert_eig_close(vecp[l], valp[l], veco[l], np.real(valo[l]), rtol=rtol)
+    # remaining voxel stencils
+    assert np.array_equal(prod.get_all_wall_binary_image(), orc.get_all_wall_binary_image(), equal_nan=True)
+    assert [list(map(int, v)) for v in prod.cells_walls_coords()] == [list(map(int, v)) for v in orc.cells_walls_coords()]
+    some = labels[:6]
+    if len(some) >= 2:
+        assert prod.region_boundingbox(list(some)) == orc.region_boundingbox(list(some))
+        for kw in (dict(), dict(region_boundingbox=True)):
+            lp, lo_ = prod.cells_voxel_layer(list(some), **kw), orc.cells_voxel_layer(list(some), **kw)
+            assert set(lp) == set(lo_)
+            for l in some:
+                assert np.array_equal(lp[l], lo_[l]), (l, kw)
+        assert np.array_equal(prod.cells_voxel_layer(list(some), single_frame=True),
+                              orc.cells_voxel_layer(list(some), single_frame=True))
+        assert np.array_equal(prod.cells_voxel_layer(some[0]), orc.cells_voxel_layer(some[0]))
     # wall voxels
     if check_wall_voxels:
         wvp = prod.wall_voxels_per_cells_pairs(verbose=False)

@@ -27,7 +27,7 @@ EXPORTS = [
     "ta_set_slab", "ta_run_pass", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
     "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
-    "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
+    "ta_hollow_out_cells", "ta_cell_shell18", "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
 ]
 
 
@@ -72,6 +72,8 @@ def load():
     lib.ta_inertia_eig.argtypes = [vp, vp, u64, vp, vp]
     lib.ta_wall_voxel_coords.argtypes = [vp, vp, vp, u64, vp, vp]
     lib.ta_voxel_first_layer.argtypes = [vp, u32, ci, vp]
+    lib.ta_hollow_out_cells.argtypes = [vp, ci, vp]
+    lib.ta_cell_shell18.argtypes = [vp, vp]
     lib.ta_map_labels.argtypes = [vp, vp, ci, u64, u32, vp, ci]
     lib.ta_last_timing.argtypes = [vp, P(C.c_float), P(C.c_float), P(C.c_float)]
     lib.ta_launch_count.argtypes = [vp, P(u64)]
@@ -229,6 +231,16 @@ class Context(object):
     def voxel_first_layer(self, background, keep_background, shape_smf, dtype):
         out = np.empty(shape_smf, dtype)
         self._check(self.lib.ta_voxel_first_layer(self.h, int(background), int(bool(keep_background)), _ptr(out)))
+        return out
+
+    def stencil_image(self, kind, shape_smf, dtype):
+        """kind 'hollow' (labels where the Laplacian is non-zero), 'laplace' (the same as a 0/1 mask) or 'shell18'
+        (0/1 outer shell of every cell)."""
+        out = np.empty(shape_smf, dtype)
+        if kind == "shell18":
+            self._check(self.lib.ta_cell_shell18(self.h, _ptr(out)))
+        else:
+            self._check(self.lib.ta_hollow_out_cells(self.h, 1 if kind == "laplace" else 0, _ptr(out)))
         return out
 
     def map_labels(self, lut, fill, shape_smf, in_place=False, fetch=True):

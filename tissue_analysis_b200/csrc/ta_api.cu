@@ -539,6 +539,19 @@ int ta_voxel_first_layer(ta_ctx* ctx, uint32_t background, int keep_background, 
                                       out_host, ctx->stream, ctx->num_sms, &ctx->launches, &ctx->err);
 }
 
+static int stencil_entry(ta_ctx* ctx, int kind, void* out_host) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "no volume bound");
+    if (!out_host) return fail(ctx, TA_ERR_BAD_ARG, "null output");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    return ta::stencil_image_impl(ctx->vol, ctx->elem, ctx->nf, ctx->nm, ctx->ns, kind, out_host, ctx->stream,
+                                  ctx->num_sms, &ctx->launches, &ctx->err);
+}
+
+int ta_hollow_out_cells(ta_ctx* ctx, int mask_only, void* out_host) { return stencil_entry(ctx, mask_only ? 2 : 0, out_host); }
+
+int ta_cell_shell18(ta_ctx* ctx, void* out_host) { return stencil_entry(ctx, 1, out_host); }
+
 int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_t n_lut, uint32_t fill, void* out_host,
                   int in_place) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");

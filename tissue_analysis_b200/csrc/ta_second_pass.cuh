@@ -221,6 +221,64 @@ __global__ void voxel_first_layer_kernel(const T* __restrict__ vol, T* __restric
     }
 }
 
+// kind 0: hollow_out_cells (label where the wrap-around Laplacian is non-zero); kind 2: the same as a 0/1 mask;
+// kind 1: 18-connected outer shell
+template <typename T, int KIND>
+__global__ void stencil_image_kernel(const T* __restrict__ vol, T* __restrict__ out, VolDims D) {
+    const long long total = D.nf * D.nm * D.ns;
+    const long long plane = D.nf * D.nm;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i % D.nf, m = (i / D.nf) % D.nm, s = i / plane;
+        const T c = vol[i];
+        if (KIND == 0 || KIND == 2) {
+            // scipy.ndimage.laplace: per axis x[i-1] - 2 x[i] + x[i+1], 'reflect' border (x[-1] = x[0]), dtype wrap
+            T sum = 0;
+            sum += (T)((f > 0 ? vol[i - 1] : c) + (f + 1 < D.nf ? vol[i + 1] : c) - (T)2 * c);
+            sum += (T)((m > 0 ? vol[i - D.nf] : c) + (m + 1 < D.nm ? vol[i + D.nf] : c) - (T)2 * c);
+            sum += (T)((s > 0 ? vol[i - plane] : c) + (s + 1 < D.ns ? vol[i + plane] : c) - (T)2 * c);
+            out[i] = sum != 0 ? (KIND == 2 ? (T)1 : c) : (T)0;
+        } else {
+            bool shell = false;
+#pragma unroll 1
+            for (int k = 0; k < 27; ++k) {
+                const int df = k % 3 - 1, dm = (k / 3) % 3 - 1, ds = k / 9 - 1;
+                const int l1 = abs(df) + abs(dm) + abs(ds);
+                if (l1 < 1 || l1 > 2) continue;
+                const long long ff = f + df, mm = m + dm, ss = s + ds;
+                if (ff < 0 || ff >= D.nf || mm < 0 || mm >= D.nm || ss < 0 || ss >= D.ns) { shell = true; break; }
+                if (vol[(ss * D.nm + mm) * D.nf + ff] != c) { shell = true; break; }
+            }
+            out[i] = shell ? (T)1 : (T)0;
+        }
+    }
+}
+
+inline int stencil_image_impl(const void* vol, int elem, long long nf, long long nm, long long ns, int kind,
+                              void* out_host, cudaStream_t st, int num_sms, uint64_t* launches, std::string* err) {
+    const size_t bytes = (size_t)nf * nm * ns * elem;
+    void* d_out = nullptr;
+    TA2_CUDA(cudaMalloc(&d_out, bytes));
+    VolDims D{nf, nm, ns, 0, ns, 0};
+    const int grid = num_sms * 16;
+    if (elem == 2) {
+        const uint16_t* v = (const uint16_t*)vol; uint16_t* o = (uint16_t*)d_out;
+        if (kind == 0) stencil_image_kernel<uint16_t, 0><<<grid, 256, 0, st>>>(v, o, D);
+        else if (kind == 1) stencil_image_kernel<uint16_t, 1><<<grid, 256, 0, st>>>(v, o, D);
+        else stencil_image_kernel<uint16_t, 2><<<grid, 256, 0, st>>>(v, o, D);
+    } else {
+        const uint32_t* v = (const uint32_t*)vol; uint32_t* o = (uint32_t*)d_out;
+        if (kind == 0) stencil_image_kernel<uint32_t, 0><<<grid, 256, 0, st>>>(v, o, D);
+        else if (kind == 1) stencil_image_kernel<uint32_t, 1><<<grid, 256, 0, st>>>(v, o, D);
+        else stencil_image_kernel<uint32_t, 2><<<grid, 256, 0, st>>>(v, o, D);
+    }
+    (*launches)++;
+    TA2_CUDA(cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    TA2_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_out);
+    return TA_OK;
+}
+
 inline int voxel_first_layer_impl(const void* vol, int elem, long long nf, long long nm, long long ns,
                                   uint32_t background, int keep_background, void* out_host, cudaStream_t st,
                                   int num_sms, uint64_t* launches, std::string* err) {

@@ -150,6 +150,10 @@ class VolumeScan(object):
         inv = np.argsort([self.ax_of_mem[2], self.ax_of_mem[1], self.ax_of_mem[0]])
         return np.transpose(out_smf, inv)
 
+    def stencil_image(self, kind):
+        """'hollow': labels where the Laplacian is non-zero (SIA:74-94); 'shell18': 0/1 outer shell (SIA:1399-1448)."""
+        return self._to_api(self.ctx.stencil_image(kind, self.view.shape, self.view.dtype))
+
     def map_labels(self, lut, fill=0):
         """API-ordered image ``lut[image]`` (device gather; labels beyond the table map to ``fill``)."""
         return self._to_api(self.ctx.map_labels(lut, fill, self.view.shape))

@@ -29,6 +29,22 @@ def real_indices(slices, resolutions):
     return [(s.start * r, s.stop * r) for s, r in zip(slices, resolutions)]
 
 
+def hollow_out_cells(image, background, remove_background=True, verbose=True, device=-1, _backend=None):
+    """SIA:74-94: keep the labels where the discrete Laplacian of the label image is non-zero (cell walls), zero
+    elsewhere; optionally zero the background too.  One stencil kernel (``ta_hollow_out_cells``)."""
+    if verbose:
+        print('Hollowing out cells... ', end='')
+    if _backend is None:
+        from .engine import VolumeScan
+        _backend = VolumeScan(image, device=device)
+    m = _backend.stencil_image("hollow")
+    if remove_background:
+        m = m * (m != background)
+    if verbose:
+        print('Done !!')
+    return SpatialImage(m, voxelsize=getattr(image, "voxelsize", None))
+
+
 class AbstractSpatialImageAnalysis(object):
     def __init__(self, image, ignoredlabels=[], return_type=DICT, background=None, *, device=-1, _backend=None):
         # SIA:212-270
@@ -392,6 +408,18 @@ class AbstractSpatialImageAnalysis(object):
             return dict((k, len(v)) for k, v in nei.items())
         return len(nei)
 
+    def get_all_wall_binary_image(self):
+        """SIA:744-749: ``lp / lp`` of the Laplacian: 1.0 on walls, nan elsewhere (0 / 0)."""
+        walls = np.asarray(self._scan().stencil_image("laplace")) != 0
+        return np.where(walls, 1.0, np.nan)
+
+    def cells_walls_coords(self):
+        """SIA:883-905.  The reference passes the bound method ``self.background`` (not its value) to
+        hollow_out_cells, so the background is never removed; the same happens here."""
+        m = np.asarray(self._scan().stencil_image("hollow"))
+        x, y, z = np.where(m != 0)
+        return list(x), list(y), list(z)
+
     def get_voxel_face_surface(self):
         # SIA:751-756
         a = self._voxelsize
@@ -591,6 +619,58 @@ class SpatialImageAnalysis3D(AbstractSpatialImageAnalysis):
             dims = np.asarray(t.shape, np.int64)
             hit = present & ((t.bmin < d).any(axis=1) | ((t.bmax + 1) > (dims - d)).any(axis=1))
         return list(set(np.nonzero(hit)[0].tolist()) - set([self._background]))
+
+    def region_boundingbox(self, labels):
+        """SIA:1361-1396."""
+        if isinstance(labels, list) and len(labels) == 1:
+            return self.boundingbox(labels[0])
+        if isinstance(labels, int):
+            return self.boundingbox(labels)
+        dict_slices = self.boundingbox(labels)
+        not_found = [c for c in labels if c not in dict_slices]
+        if len(not_found) != 0:
+            warnings.warn('You have asked for unknown cells labels: ' + " ".join([str(k) for k in not_found]))
+        x_start, y_start, z_start, x_stop, y_stop, z_stop = np.inf, np.inf, np.inf, 0, 0, 0
+        for c in labels:
+            x, y, z = dict_slices[c]
+            x_start, y_start, z_start = min(x.start, x_start), min(y.start, y_start), min(z.start, z_start)
+            x_stop, y_stop, z_stop = max(x.stop, x_stop), max(y.stop, y_stop), max(z.stop, z_stop)
+        return (slice(x_start, x_stop), slice(y_start, y_stop), slice(z_start, z_stop))
+
+    def cells_voxel_layer(self, labels, region_boundingbox=False, single_frame=False):
+        """SIA:1399-1448: first voxel layer of each cell = mask minus its 18-connected erosion inside the crop.  A
+        cell voxel is eroded away iff one of its 18 neighbours is outside the crop or not the cell, which for the
+        bounding box of the cell (or any box containing it) is: outside the image or another label -> one stencil
+        kernel for all cells (``ta_cell_shell18``), cropped per cell on the host."""
+        if isinstance(labels, int):
+            labels = [labels]
+        if single_frame:
+            region_boundingbox = True
+        bbox = None
+        if not isinstance(region_boundingbox, bool):
+            if sum([isinstance(s, slice) for s in region_boundingbox]) == 3:
+                bbox = region_boundingbox
+                region_boundingbox = True
+            else:
+                print("TypeError: Wong type for 'region_boundingbox', should either be bool or la tuple of slices")
+                return None
+        elif region_boundingbox:
+            bbox = self.region_boundingbox(labels)
+        else:
+            bboxes = self.boundingbox(labels, real=False)
+        shell = np.asarray(self._scan().stencil_image("shell18")) != 0
+        img = np.asarray(self.image)
+        vox_layer = np.zeros_like(img[bbox], dtype=int) if single_frame else {}
+        for clabel in labels:
+            box = bbox if region_boundingbox else bboxes[clabel]
+            layer = np.array((img[box] == clabel) & shell[box], dtype=int)
+            if single_frame:
+                vox_layer += layer
+            else:
+                vox_layer[clabel] = layer
+        if len(labels) == 1:
+            return vox_layer[clabel]
+        return vox_layer
 
     def voxel_first_layer(self, keep_background=True):
         # SIA:1024-1046
