@@ -294,9 +294,8 @@ def main():
         ns_b, nm_b, nf_b = harr.shape
 
         def e2e_step():
-            ctx2.bind_host(harr)
-            ctx2.set_slab(scan.own_lo, scan.own_hi, scan.g_lo - scan.own_lo)
-            ctx2.run_pass(_native.PASS_ALL, hint_labels)
+            ctx2.run_pass_host(harr, _native.PASS_ALL, hint_labels,
+                               slab=(scan.own_lo, scan.own_hi, scan.g_lo - scan.own_lo))
             lt = ctx2.label_table()
             pt = ctx2.pair_table()
             return lt, pt
@@ -315,8 +314,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": nvox / float(tt[0]) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(harr.nbytes),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
-               "note": "pinned host volume -> ta_bind_volume (H2D) + ta_run_pass + ta_fetch_*_table (D2H); "
-                       "per-rank slab, no cross-rank merge"}
+               "note": "pinned host volume -> ta_run_pass_host (chunked H2D overlapped with the scan) + "
+                       "ta_fetch_*_table (D2H); per-rank slab, no cross-rank merge"}
         ctx2.close()
 
     cpu_baseline = None

@@ -73,6 +73,17 @@ int ta_set_slab(ta_ctx* ctx, int64_t own_lo, int64_t own_hi, int64_t slow_offset
  * TA_ERR_PAIR_OVERFLOW (tables invalid) if the pair table filled up. */
 int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint);
 
+/* ta_bind_volume(host) + ta_run_pass with the copy and the scan overlapped: the host volume (pinned memory makes the
+ * copy asynchronous) goes to the context-owned device buffer in chunks of `chunk_planes` slow-axis planes (0 = about
+ * 64 MiB) on a copy stream, and the scan of each chunk is queued behind its copy, accumulating into the same tables.
+ * Same results and error codes as the two calls; afterwards the volume is bound (second passes, ta_run_pass again).
+ * This is what the reference's `SpatialImageAnalysis(image)` + first feature request costs end to end (SIA:212-270,
+ * 1231): the image lives in host memory.  uint32 volumes with max_label_hint == 0 are copied first (the table height
+ * needs the largest label) and then scanned. */
+int ta_run_pass_host(ta_ctx* ctx, const void* host_data, int elem_bytes, int64_t n_fast, int64_t n_mid, int64_t n_slow,
+                     const int64_t* slab /* NULL, or {own_lo, own_hi, slow_offset} as in ta_set_slab */,
+                     uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint, int64_t chunk_planes);
+
 /* Per-label table, dense by label value: rows 0..n-1.
  *   count[n]     voxels                                  (SIA:1231)
  *   s1[n][3]     sum of fast/mid/slow global indices      (SIA:466)

@@ -277,3 +277,72 @@ def test_mutators_and_property_image_on_the_gpu():
         assert np.array_equal(np.asarray(work), mutated)
         fresh = LoopOracle(mutated, voxelsize=img.voxelsize, background=1, ignoredlabels=[0])
         compare_api(prod, fresh, check_wall_voxels=False, real_modes=(True,))
+
+
+@pytest.mark.parametrize("shape", [(5, 3, 2), (17, 16, 8), (129, 17, 9), (131, 5, 3), (260, 40, 21)])
+@pytest.mark.parametrize("dtype,nlab", [(np.uint16, 9), (np.uint16, 16), (np.uint16, 23), (np.uint32, 30), (np.uint32, 40)])
+def test_noise_within_the_one_hot_id_budget(shape, dtype, nlab):
+    """Noise on the one-hot pair path of the scan kernel: junctions of many labels, ragged rows, sparse label values.
+    With more labels than ids in a quarter (23 / 40) the brick is staged again and takes the per-voxel path."""
+    rng = np.random.default_rng(sum(shape) + nlab)
+    names = rng.choice(np.arange(2, 60000), size=nlab, replace=False)
+    arr = names[rng.integers(0, nlab, size=shape[::-1])].astype(dtype)
+    img = SpatialImage(arr.transpose(2, 1, 0))
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout, tables_from_memory_order
+    view, ax = memory_layout(img)
+    ctx = _native.Context()
+    ctx.bind_host(np.ascontiguousarray(view))
+    ctx.run_pass(_native.PASS_ALL | 0x1000)              # one-hot pair path for uint16 too
+    count, s1, s2, bbox = ctx.label_table()
+    lo, hi, faces, wall = ctx.pair_table()
+    ctx.close()
+    t = tables_from_memory_order(img.shape, ax, count, s1, s2, bbox, lo, hi, faces, wall)
+    assert_tables_equal(t, oracle_tables(np.asarray(img)))
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint32])
+def test_one_hot_pair_path_equals_per_voxel_pair_path(dtype):
+    """Flag 0x800 forces phases C2 / D / D2 (per-voxel neighbour tests) for every brick, 0x1000 the one-hot phases
+    R / S wherever a brick has few enough labels.  Same tables bit for bit, and both equal the oracle."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout
+    img = tissue_image((150, 70, 33), 260, seed=21, dome=True, dtype=dtype)
+    view, _ = memory_layout(img)
+    out = []
+    for extra in (0x1000, 0x800):
+        ctx = _native.Context()
+        ctx.bind_host(np.ascontiguousarray(view))
+        ctx.run_pass(_native.PASS_ALL | extra)
+        out.append((ctx.label_table(), ctx.pair_table()))
+        ctx.close()
+    for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+        assert np.array_equal(a, b)
+    assert_tables_equal(SpatialImageAnalysis3D(img, background=1)._tables(), oracle_tables(np.asarray(img)))
+
+
+@pytest.mark.parametrize("chunk", [0, 2, 3, 8, 1000])
+def test_overlapped_host_pass_equals_bind_then_pass(chunk):
+    """ta_run_pass_host (chunked H2D, the scan of each chunk queued behind its copy) == ta_bind_volume +
+    ta_run_pass, for any chunk height, whole volume and slab ownership."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout
+    img = tissue_image((70, 41, 29), 90, seed=8, dome=True)
+    view = np.ascontiguousarray(memory_layout(img)[0])
+    for slab in (None, (4, 21, 100)):
+        ref = _native.Context()
+        ref.bind_host(view)
+        if slab:
+            ref.set_slab(*slab)
+        ref.run_pass()
+        want = ref.label_table() + ref.pair_table()
+        ref.close()
+        ctx = _native.Context()
+        ctx.run_pass_host(view, chunk_planes=chunk, slab=slab)
+        got = ctx.label_table() + ctx.pair_table()
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        ctx.run_pass()                       # the volume stays bound: an ordinary pass gives the same tables again
+        for a, b in zip(ctx.label_table() + ctx.pair_table(), want):
+            assert np.array_equal(a, b)
+        ctx.close()

@@ -24,7 +24,7 @@ PASS_MOMENTS, PASS_PAIRS6, PASS_WALL18, PASS_ALL = 1, 2, 4, 7
 # every symbol include/tissue_b200.h declares (tests/test_cabi_symbols.py checks header <-> library)
 EXPORTS = [
     "ta_version", "ta_ctx_create", "ta_ctx_destroy", "ta_last_error", "ta_set_stream", "ta_bind_volume",
-    "ta_set_slab", "ta_run_pass", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
+    "ta_set_slab", "ta_run_pass", "ta_run_pass_host", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
     "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
     "ta_hollow_out_cells", "ta_cell_shell18", "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
@@ -60,6 +60,7 @@ def load():
     lib.ta_bind_volume.argtypes = [vp, vp, ci, ci, i64, i64, i64]
     lib.ta_set_slab.argtypes = [vp, i64, i64, i64]
     lib.ta_run_pass.argtypes = [vp, u32, u32, u64]
+    lib.ta_run_pass_host.argtypes = [vp, vp, ci, i64, i64, i64, P(i64), u32, u32, u64, i64]
     lib.ta_label_table_size.argtypes = [vp, P(u64)]
     lib.ta_fetch_label_table.argtypes = [vp, vp, vp, vp, vp]
     lib.ta_pair_table_size.argtypes = [vp, P(u64)]
@@ -144,6 +145,21 @@ class Context(object):
                 continue
             self._check(rc)
             return
+
+    def run_pass_host(self, arr, flags=PASS_ALL, max_label_hint=0, pair_capacity_hint=0, chunk_planes=0,
+                      max_retries=4, slab=None):
+        """bind_host(arr) [+ set_slab(*slab)] + run_pass() with the H2D copy and the scan overlapped."""
+        assert arr.flags["C_CONTIGUOUS"] and arr.ndim == 3
+        ns, nm, nf = arr.shape
+        self._keepalive = None
+        slab_c = (C.c_int64 * 3)(*[int(v) for v in slab]) if slab is not None else None
+        rc = self.lib.ta_run_pass_host(self.h, _ptr(arr), arr.dtype.itemsize, nf, nm, ns, slab_c, flags,
+                                       int(max_label_hint), int(pair_capacity_hint), int(chunk_planes))
+        if rc == TA_ERR_PAIR_OVERFLOW and max_retries > 0:
+            # the volume is resident by now: grow the table and redo the pass on the device copy
+            cap = int(pair_capacity_hint)
+            return self.run_pass(flags, max_label_hint, max(cap * 4, 1 << 20) if cap else 1 << 22, max_retries - 1)
+        self._check(rc)
 
     def label_table(self):
         n = C.c_uint64()

@@ -51,6 +51,8 @@ struct ta_ctx {
     u64* phase_cycles = nullptr;
 
     cudaEvent_t ev[6] = {};
+    cudaStream_t copy_stream = nullptr;          // H2D chunks of ta_run_pass_host
+    std::vector<cudaEvent_t> chunk_ev;
     float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
     uint64_t launches = 0;
 };
@@ -130,6 +132,8 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return TA_OK;
@@ -141,25 +145,38 @@ int ta_set_stream(ta_ctx* ctx, void* cuda_stream) {
     return TA_OK;
 }
 
-int ta_bind_volume(ta_ctx* ctx, const void* data, int is_device, int elem_bytes, int64_t n_fast, int64_t n_mid,
-                   int64_t n_slow) {
+static int check_volume_args(ta_ctx* ctx, const void* data, int elem_bytes, int64_t n_fast, int64_t n_mid,
+                             int64_t n_slow) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!data) return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: data is null");
     if (elem_bytes != 2 && elem_bytes != 4) return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: elem_bytes must be 2 or 4");
     if (n_fast <= 0 || n_mid <= 0 || n_slow <= 0 || n_fast > 0x7FFFFFF0LL || n_mid > 0x7FFFFFF0LL ||
         n_slow > 0x7FFFFFF0LL)
         return fail(ctx, TA_ERR_BAD_ARG, "ta_bind_volume: bad shape");
+    return TA_OK;
+}
+
+static int ensure_owned_volume(ta_ctx* ctx, size_t bytes) {
+    if (ctx->vol_owned_bytes < bytes) {
+        if (ctx->vol_owned) TA_CUDA(cudaFree(ctx->vol_owned));
+        ctx->vol_owned = nullptr; ctx->vol_owned_bytes = 0;
+        TA_CUDA(cudaMalloc(&ctx->vol_owned, bytes));
+        ctx->vol_owned_bytes = bytes;
+    }
+    return TA_OK;
+}
+
+int ta_bind_volume(ta_ctx* ctx, const void* data, int is_device, int elem_bytes, int64_t n_fast, int64_t n_mid,
+                   int64_t n_slow) {
+    int rc0 = check_volume_args(ctx, data, elem_bytes, n_fast, n_mid, n_slow);
+    if (rc0) return rc0;
     TA_CUDA(cudaSetDevice(ctx->device));
     size_t bytes = (size_t)n_fast * n_mid * n_slow * elem_bytes;
     if (is_device) {
         ctx->vol = data;
     } else {
-        if (ctx->vol_owned_bytes < bytes) {
-            if (ctx->vol_owned) TA_CUDA(cudaFree(ctx->vol_owned));
-            ctx->vol_owned = nullptr; ctx->vol_owned_bytes = 0;
-            TA_CUDA(cudaMalloc(&ctx->vol_owned, bytes));
-            ctx->vol_owned_bytes = bytes;
-        }
+        rc0 = ensure_owned_volume(ctx, bytes);
+        if (rc0) return rc0;
         TA_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
         TA_CUDA(cudaMemcpyAsync(ctx->vol_owned, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
         TA_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -248,7 +265,29 @@ static int ensure_pair_table(ta_ctx* ctx, size_t cap) {
     return TA_OK;
 }
 
-int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint) {
+// One launch of the scan kernel over owned planes [own_lo, own_hi) of the bound buffer; tables accumulate.
+static int launch_scan(ta_ctx* ctx, ScanParams P, long long own_lo, long long own_hi) {
+    cudaStream_t st = ctx->stream;
+    P.own_lo = own_lo; P.own_hi = own_hi;
+    P.nbs = (int)((own_hi - own_lo + ta::BS - 1) / ta::BS);
+    const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
+    if (total > 0xFFFFFFF0ull) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass");
+    if (total == 0) return TA_OK;
+    TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
+    int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
+    if (ctx->elem == 2)
+        ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt);
+    else
+        ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+// host_src != nullptr: the bound (context-owned) buffer is filled from host_src in chunks of `chunk_planes` planes on
+// a copy stream while the scan kernel already works on the planes that have arrived.
+static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint,
+                         const void* host_src, long long chunk_planes) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "ta_run_pass: no volume bound");
     if ((flags & (TA_PASS_ALL | 0x300u)) == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass: empty flags");
@@ -316,33 +355,65 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     P.phase_cycles = nullptr;
     const bool phase_timing = getenv("TA_PHASE_TIMING") != nullptr;
     if (phase_timing) {
-        if (!ctx->phase_cycles) TA_CUDA(cudaMalloc((void**)&ctx->phase_cycles, 8 * sizeof(u64)));
-        TA_CUDA(cudaMemsetAsync(ctx->phase_cycles, 0, 8 * sizeof(u64), st));
+        if (!ctx->phase_cycles) TA_CUDA(cudaMalloc((void**)&ctx->phase_cycles, 16 * sizeof(u64)));
+        TA_CUDA(cudaMemsetAsync(ctx->phase_cycles, 0, 16 * sizeof(u64), st));
         P.phase_cycles = ctx->phase_cycles;
     }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
-    if (total > 0xFFFFFFF0ull) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass");
-    TA_CUDA(cudaEventRecord(ctx->ev[1], st));
-    if (total > 0) {
-        int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
-        if (ctx->elem == 2)
-            ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt);
-        else
-            ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt);
-        ctx->launches++;
-        TA_CUDA(cudaGetLastError());
+    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" for every brick
+        if (!strcmp(pp, "voxel")) P.flags |= 0x800u;
+        else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
     }
+    TA_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if (!host_src) {
+        rc = launch_scan(ctx, P, ctx->own_lo, ctx->own_hi);
+        if (rc) return rc;
+    } else {
+        // chunk k = planes [c_k, c_k+1) is copied on the copy stream; the scan of planes [c_k - 1, c_k+1 - 1) (the last
+        // chunk runs to the end) follows on the pass stream as soon as the chunk has landed: it needs plane c_k+1 - 1 as
+        // its upper halo and nothing beyond.
+        const long long ns = ctx->ns, cp = std::max<long long>(chunk_planes, 2);
+        const size_t plane_bytes = (size_t)ctx->nf * ctx->nm * ctx->elem;
+        const size_t nchunks = (size_t)((ns + cp - 1) / cp);
+        if (!ctx->copy_stream) TA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        while (ctx->chunk_ev.size() < nchunks + 1) {
+            cudaEvent_t e;
+            TA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->chunk_ev.push_back(e);
+        }
+        // the copy stream starts after everything queued on the pass stream so far (table resets included)
+        TA_CUDA(cudaEventRecord(ctx->chunk_ev[nchunks], st));
+        TA_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+        TA_CUDA(cudaEventRecord(ctx->ev[4], ctx->copy_stream));
+        for (size_t k = 0; k < nchunks; ++k) {
+            const long long c0 = (long long)k * cp, c1 = std::min<long long>(c0 + cp, ns);
+            TA_CUDA(cudaMemcpyAsync((char*)ctx->vol_owned + (size_t)c0 * plane_bytes,
+                                    (const char*)host_src + (size_t)c0 * plane_bytes, (size_t)(c1 - c0) * plane_bytes,
+                                    cudaMemcpyHostToDevice, ctx->copy_stream));
+            TA_CUDA(cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+            TA_CUDA(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+            const long long lo = std::max<long long>(c0 - 1, ctx->own_lo);
+            const long long hi = std::min<long long>((c1 == ns) ? ns : c1 - 1, ctx->own_hi);
+            if (lo < hi) {
+                rc = launch_scan(ctx, P, lo, hi);
+                if (rc) return rc;
+            }
+        }
+        TA_CUDA(cudaEventRecord(ctx->ev[5], ctx->copy_stream));
+    }
+    (void)total;
     TA_CUDA(cudaEventRecord(ctx->ev[2], st));
     if (phase_timing) {
-        u64 cyc[8];
+        u64 cyc[16];
         TA_CUDA(cudaMemcpyAsync(cyc, ctx->phase_cycles, sizeof cyc, cudaMemcpyDeviceToHost, st));
         TA_CUDA(cudaStreamSynchronize(st));
         double tot = 0;
-        for (int k = 0; k < 8; ++k) tot += (double)cyc[k];
-        const char* nm[8] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush"};
+        for (int k = 0; k < 10; ++k) tot += (double)cyc[k];
+        const char* nm[10] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush",
+                              "R one-hot", "S stencil"};
         fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
-        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
-        fprintf(stderr, "\n");
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
+        fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[10], cyc[11]);
     }
 
     rc = build_records(ctx);
@@ -356,6 +427,46 @@ int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t p
     if (status[1]) return fail(ctx, TA_ERR_LABEL_RANGE, "a label exceeds max_label_hint");
     ctx->have_tables = true;
     return TA_OK;
+}
+
+int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint) {
+    return run_pass_impl(ctx, flags, max_label_hint, pair_capacity_hint, nullptr, 0);
+}
+
+int ta_run_pass_host(ta_ctx* ctx, const void* host_data, int elem_bytes, int64_t n_fast, int64_t n_mid, int64_t n_slow,
+                     const int64_t* slab, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint,
+                     int64_t chunk_planes) {
+    int rc = check_volume_args(ctx, host_data, elem_bytes, n_fast, n_mid, n_slow);
+    if (rc) return rc;
+    if (slab && (slab[0] < 0 || slab[1] > n_slow || slab[0] > slab[1] || slab[2] < 0))
+        return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass_host: bad plane range");
+    if (elem_bytes == 4 && max_label_hint == 0) {
+        // the height of the label table needs the largest label first: copy, then the ordinary pass
+        rc = ta_bind_volume(ctx, host_data, 0, elem_bytes, n_fast, n_mid, n_slow);
+        if (!rc && slab) rc = ta_set_slab(ctx, slab[0], slab[1], slab[2]);
+        return rc ? rc : run_pass_impl(ctx, flags, max_label_hint, pair_capacity_hint, nullptr, 0);
+    }
+    TA_CUDA(cudaSetDevice(ctx->device));
+    rc = ensure_owned_volume(ctx, (size_t)n_fast * n_mid * n_slow * elem_bytes);
+    if (rc) return rc;
+    ctx->vol = ctx->vol_owned;
+    ctx->elem = elem_bytes;
+    ctx->nf = n_fast; ctx->nm = n_mid; ctx->ns = n_slow;
+    ctx->own_lo = 0; ctx->own_hi = n_slow; ctx->slow_offset = 0;
+    if (slab) { ctx->own_lo = slab[0]; ctx->own_hi = slab[1]; ctx->slow_offset = slab[2]; }
+    if (chunk_planes <= 0) {
+        // about 64 MiB per chunk: long enough to run PCIe at full rate, short enough that the last chunk's scan is a
+        // small tail; a multiple of the brick height
+        const size_t plane_bytes = (size_t)n_fast * n_mid * elem_bytes;
+        chunk_planes = (int64_t)std::max<size_t>(ta::BS, ((64u << 20) / std::max<size_t>(plane_bytes, 1)) / ta::BS * ta::BS);
+    }
+    rc = run_pass_impl(ctx, flags, max_label_hint, pair_capacity_hint, host_data, chunk_planes);
+    if (rc == TA_OK || rc == TA_ERR_PAIR_OVERFLOW || rc == TA_ERR_LABEL_RANGE) {
+        // the whole volume is resident now (second passes, retries with ta_run_pass)
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaEventElapsedTime(&ctx->h2d_ms, ctx->ev[4], ctx->ev[5]);
+    }
+    return rc;
 }
 
 int ta_label_table_size(ta_ctx* ctx, uint64_t* n) {

@@ -37,7 +37,7 @@ struct ScanParams {
     uint32_t flags;
     int vec_ok;                  // rows are 16-byte aligned: 128-bit loads allowed
     unsigned int* brick_counter; // dynamic brick scheduler
-    u64* phase_cycles;           // optional [8]: per-phase clock64 totals of thread 0 of every CTA (profiling aid)
+    u64* phase_cycles;           // optional [16]: per-phase clock64 totals of thread 0 of every CTA (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t ta_hash64(u64 k) {

@@ -109,14 +109,23 @@ class VolumeScan(object):
         self._image_ref = np.asarray(image)
         self.shape_api = tuple(np.asarray(image).shape)
         self.ctx = _native.Context(device)
-        self.ctx.bind_host(self.view)
+        self._bound = False              # the first pass copies and scans in one overlapped call (ta_run_pass_host)
         self.flags = flags
         self.max_label_hint = max_label_hint
         self.pair_capacity_hint = pair_capacity_hint
         self.tables = None
 
+    def _bind(self):
+        if not self._bound:
+            self.ctx.bind_host(self.view)
+            self._bound = True
+
     def run(self):
-        self.ctx.run_pass(self.flags, self.max_label_hint, self.pair_capacity_hint)
+        if self._bound:
+            self.ctx.run_pass(self.flags, self.max_label_hint, self.pair_capacity_hint)
+        else:
+            self.ctx.run_pass_host(self.view, self.flags, self.max_label_hint, self.pair_capacity_hint)
+            self._bound = True
         count, s1, s2, bbox = self.ctx.label_table()
         lo, hi, faces, wall = self.ctx.pair_table()
         self.tables = tables_from_memory_order(self.shape_api, self.ax_of_mem, count, s1, s2, bbox, lo, hi, faces,
@@ -134,6 +143,7 @@ class VolumeScan(object):
 
     def wall_voxel_coords(self, lo, hi):
         """-> list of int64[3, n_i] in API axis order, each sorted lexicographically by (x, y, z)."""
+        self._bind()
         _, blocks = self.ctx.wall_voxel_coords(lo, hi)
         out = []
         for blk in blocks:
@@ -152,10 +162,12 @@ class VolumeScan(object):
 
     def stencil_image(self, kind):
         """'hollow': labels where the Laplacian is non-zero (SIA:74-94); 'shell18': 0/1 outer shell (SIA:1399-1448)."""
+        self._bind()
         return self._to_api(self.ctx.stencil_image(kind, self.view.shape, self.view.dtype))
 
     def map_labels(self, lut, fill=0):
         """API-ordered image ``lut[image]`` (device gather; labels beyond the table map to ``fill``)."""
+        self._bind()
         return self._to_api(self.ctx.map_labels(lut, fill, self.view.shape))
 
     def relabel(self, mapping):
@@ -167,6 +179,7 @@ class VolumeScan(object):
         lut = np.arange(top, dtype=np.int64)
         for old, new in mapping.items():
             lut[old] = new
+        self._bind()
         out = self.ctx.map_labels(lut.astype(self.view.dtype), 0, self.view.shape, in_place=True)
         if np.shares_memory(self.view, self._image_ref):
             np.copyto(self.view, out)                      # the view aliases the caller's image memory
@@ -177,6 +190,7 @@ class VolumeScan(object):
 
     def voxel_first_layer(self, background, keep_background=True):
         ns, nm, nf = self.view.shape
+        self._bind()
         return self._to_api(self.ctx.voxel_first_layer(background, keep_background, (ns, nm, nf), self.view.dtype))
 
 

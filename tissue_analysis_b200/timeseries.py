@@ -28,8 +28,7 @@ def analyze_frames(frames, device=-1, flags=_native.PASS_ALL, rank=None, world=N
         for k in frames_of_rank(len(frames), rank, world):
             img = frames[k]() if callable(frames[k]) else frames[k]
             view, ax = memory_layout(img)
-            ctx.bind_host(view)
-            ctx.run_pass(flags)
+            ctx.run_pass_host(view, flags)
             count, s1, s2, bbox = ctx.label_table()
             lo, hi, faces, wall = ctx.pair_table()
             out[k] = tables_from_memory_order(np.asarray(img).shape, ax, count, s1, s2, bbox, lo, hi, faces, wall)

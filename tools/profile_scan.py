@@ -11,8 +11,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C2")
 ap.add_argument("--passes", type=int, default=3)
 ap.add_argument("--flags", type=int, default=7)
+ap.add_argument("--ncell", type=int, default=0, help="override the number of seeds (cell size study)")
 a = ap.parse_args()
-cfg = CONFIGS[a.config]
+cfg = dict(CONFIGS[a.config])
+if a.ncell:
+    cfg["ncell"] = a.ncell
 X, Y, Z = cfg["shape"]
 vol = voronoi_device((Z, Y, X), cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"])
 ctx = _native.Context()
