@@ -265,8 +265,40 @@ static int ensure_pair_table(ta_ctx* ctx, size_t cap) {
     return TA_OK;
 }
 
+// Tensor map of the bound buffer for the scan kernel's TMA staging: dims (fast, mid, slow), box = one tile (brick +
+// halo; 18 segments x 18 rows x 10 planes), no swizzle, out-of-bounds elements read as zero (the kernel re-clamps
+// them).  false: TMA not usable (encoder missing or it rejected the shape) -> the kernel stages with cp.async.
+typedef CUresult (*ta_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map) {
+    static ta_encode_tiled_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = (ta_encode_tiled_fn)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    const int seg = 16 / ctx->elem;
+    const cuuint64_t dims[3] = {(cuuint64_t)ctx->nf, (cuuint64_t)ctx->nm, (cuuint64_t)ctx->ns};
+    const cuuint64_t strides[2] = {(cuuint64_t)ctx->nf * ctx->elem, (cuuint64_t)ctx->nf * ctx->nm * ctx->elem};
+    const cuuint32_t box[3] = {(cuuint32_t)(ta::ROWV * seg), (cuuint32_t)(ta::BM + 2), (cuuint32_t)(ta::BS + 2)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, ctx->elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
+                        const_cast<void*>(ctx->vol), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // One launch of the scan kernel over owned planes [own_lo, own_hi) of the bound buffer; tables accumulate.
-static int launch_scan(ta_ctx* ctx, ScanParams P, long long own_lo, long long own_hi) {
+static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long long own_lo, long long own_hi) {
     cudaStream_t st = ctx->stream;
     P.own_lo = own_lo; P.own_hi = own_hi;
     P.nbs = (int)((own_hi - own_lo + ta::BS - 1) / ta::BS);
@@ -276,9 +308,9 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, long long own_lo, long long ow
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     if (ctx->elem == 2)
-        ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt);
+        ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt, tmap);
     else
-        ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt);
+        ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt, tmap);
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     return TA_OK;
@@ -351,6 +383,9 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     P.nbs = (int)((ctx->own_hi - ctx->own_lo + ta::BS - 1) / ta::BS);
     P.flags = flags;
     P.vec_ok = ((ctx->nf % seg) == 0) && (((uintptr_t)ctx->vol & 15) == 0);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    P.use_tma = (P.vec_ok && !getenv("TA_NO_TMA") && make_tile_map(ctx, &tmap)) ? 1 : 0;
     P.brick_counter = &ctx->counters[0];
     P.phase_cycles = nullptr;
     const bool phase_timing = getenv("TA_PHASE_TIMING") != nullptr;
@@ -366,7 +401,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (!host_src) {
-        rc = launch_scan(ctx, P, ctx->own_lo, ctx->own_hi);
+        rc = launch_scan(ctx, P, tmap, ctx->own_lo, ctx->own_hi);
         if (rc) return rc;
     } else {
         // chunk k = planes [c_k, c_k+1) is copied on the copy stream; the scan of planes [c_k - 1, c_k+1 - 1) (the last
@@ -395,7 +430,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
             const long long lo = std::max<long long>(c0 - 1, ctx->own_lo);
             const long long hi = std::min<long long>((c1 == ns) ? ns : c1 - 1, ctx->own_hi);
             if (lo < hi) {
-                rc = launch_scan(ctx, P, lo, hi);
+                rc = launch_scan(ctx, P, tmap, lo, hi);
                 if (rc) return rc;
             }
         }

@@ -1,6 +1,7 @@
 // Shared device-side definitions for libtissue_b200 (sm_100a only).
 #pragma once
 #include <cstdint>
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #define TA_EMPTY64 0xFFFFFFFFFFFFFFFFull
@@ -36,6 +37,7 @@ struct ScanParams {
     int nbf, nbm, nbs;           // bricks per axis over the owned region
     uint32_t flags;
     int vec_ok;                  // rows are 16-byte aligned: 128-bit loads allowed
+    int use_tma;                 // the tile (brick + halo) is one TMA box copy (needs vec_ok and a tensor map)
     unsigned int* brick_counter; // dynamic brick scheduler
     u64* phase_cycles;           // optional [16]: per-phase clock64 totals of thread 0 of every CTA (profiling aid)
 };

@@ -99,6 +99,28 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- TMA staging: one 3-D box copy (brick + halo) per tile, completion on an mbarrier ------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 template <typename T> struct BrickShared {
     uint4* tile;                       // [TILE_SEGS]
     typename Vox<T>::Code* codes;      // [TILE_ROWS * NFS]
@@ -723,7 +745,7 @@ TA_HD void oh_segment_pairs(const uint4* tile, const T* edg, int r, int fs, int 
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 3)
-scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
+scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::Code Code;
     typedef typename Vox<T>::PKey PKey;
     constexpr int SEG = Vox<T>::SEG;
@@ -733,7 +755,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     constexpr int PLANEE = (BM + 2) * ROWE;        // elements per tile plane
     constexpr int BF = NFS * SEG;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     BrickShared<T> sh;
     sh.tile = reinterpret_cast<uint4*>(smem_raw);
     sh.lt_key = reinterpret_cast<uint32_t*>(sh.tile + TILE_SEGS);
@@ -776,6 +798,15 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
     for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
     for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
 
+    // TMA completion barrier (one arrival: the issuing thread's expect_tx); ctr[12..13] is 8-byte aligned
+    uint64_t* tma_bar = reinterpret_cast<uint64_t*>(sh.ctr + 12);
+    uint32_t tma_parity = 0u;
+    const bool use_tma = P.use_tma && ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u) == 0u;
+    if (use_tma && tid == 0) {
+        mbar_init(tma_bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
     long long tp = 0;
     if (P.phase_cycles && tid == 0) tp = clock64();
 #define TA_TICK(k) if (P.phase_cycles && tid == 0) { long long now_ = clock64(); atomicAdd(&P.phase_cycles[k], (u64)(now_ - tp)); tp = now_; }
@@ -798,6 +829,45 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt) {
 
         // ---- phase A: stage brick + halo (clamped) ------------------------------------------------------------
         auto stage_tile = [&]() {
+        if (use_tma) {
+            // the callers' barrier ordered every earlier generic-proxy access of the tile before this point
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
+                tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
+            }
+            unsigned spins = 0;
+            while (!mbar_try_wait(tma_bar, tma_parity)) {
+                if (++spins > (1u << 26)) __trap();          // a lost copy must not hang the box
+            }
+            tma_parity ^= 1u;
+            // Elements outside the buffer arrive as zeros; the tile wants them clamped (replicated edge voxels).  Only
+            // bricks on a face of the buffer pay for the patch: f lanes, then m rows, then s planes.
+            const bool edge = (F0 == 0) | (F0 + BF + 1 > nf) | (M0 == 0) | (M0 + BM + 1 > nm) | (S0 < 1) | (S0 + BS + 1 > ns);
+            if (edge) {
+                T* tw = reinterpret_cast<T*>(sh.tile);
+                const int xl = (F0 == 0) ? SEG : 0;                       // lanes [0, xl) <- lane xl
+                const int xr = min(ROWE, nf - F0 + SEG);                  // lanes [xr, ROWE) <- lane xr - 1
+                for (int r = tid; r < TILE_ROWS; r += NTHREADS) {
+                    T* row = tw + r * ROWE;
+                    if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
+                    if (xr < ROWE) { const T v = row[xr - 1]; for (int x = xr; x < ROWE; ++x) row[x] = v; }
+                }
+                __syncthreads();
+                for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+                    const int r = i / ROWV, m = r % (BM + 2) - 1;
+                    const int mc = min(max(M0 + m, 0), nm - 1) - M0;
+                    if (mc != m) sh.tile[i] = sh.tile[i + (mc - m) * ROWV];
+                }
+                __syncthreads();
+                for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+                    const int s = i / PLANEV - 1;
+                    const int sc = min(max(S0 + s, 0), ns - 1) - S0;
+                    if (sc != s) sh.tile[i] = sh.tile[i + (sc - s) * PLANEV];
+                }
+            }
+            return;
+        }
         for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
             const int fs = i % ROWV - 1;
             const int r = i / ROWV;
