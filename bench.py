@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="edge of the CPU baseline crops (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--equal-planes", action="store_true", help="N > 1: slabs of equal height instead of equal work")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -238,7 +239,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert args.gpus == world or world == 1, "launch N>1 with torch.distributed.run"
 
-    scan = SlabScan(shape_zyx, torch.uint16 if elem == 2 else torch.uint32, rank=rank, world=world)
+    bounds = None
+    if world > 1 and cfg["dome"] and not args.equal_planes:
+        # Partition step (outside the timed region, as a loader would do it once per volume): plane boundaries of equal
+        # estimated work instead of equal height -- a dome leaves the end slabs mostly background.
+        from tissue_analysis_b200.distributed import partition_planes, partition_planes_weighted, plane_work_weights
+        b0 = partition_planes(shape_zyx[0], world)
+        part = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"],
+                              zslice=(b0[rank], b0[rank + 1]))
+        w = plane_work_weights(part, 1)
+        del part
+        cap = max(b0[r + 1] - b0[r] for r in range(world))
+        mine = torch.zeros(cap, dtype=torch.float64, device="cuda")
+        mine[:w.numel()] = w
+        allw = torch.empty(world * cap, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allw, mine)
+        allw = allw.cpu().numpy()
+        weights = np.concatenate([allw[r * cap:r * cap + (b0[r + 1] - b0[r])] for r in range(world)])
+        bounds = partition_planes_weighted(weights, world)
+    scan = SlabScan(shape_zyx, torch.uint16 if elem == 2 else torch.uint32, rank=rank, world=world, bounds=bounds)
     gen = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"],
                          zslice=(scan.g_lo, scan.g_hi))
     scan.owned().copy_(gen)
@@ -274,6 +293,11 @@ def main():
     t = torch.tensor([ms, float(np.mean(scan_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+    per_rank[rank] = float(np.mean(scan_ms))
+    if world > 1:
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    scan_ms_per_rank = [round(float(v), 4) for v in per_rank.tolist()]
     ms, scan_ms_avg = float(t[0]), float(t[1])
     value = nvox / (ms * 1e-3) / 1e9
 
@@ -282,7 +306,7 @@ def main():
     achieved = own_vox * elem / (scan_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_bytes(args.config, world), "kernel": "ta::scan_kernel", "kernel_ms": scan_ms_avg,
-                "algorithmic_bytes_per_voxel": elem, "peak_source": peak_src}
+                "kernel_ms_per_rank": scan_ms_per_rank, "algorithmic_bytes_per_voxel": elem, "peak_source": peak_src}
 
     # ---- e2e: host volume through the C ABI (H2D + pass + D2H of the tables), rank-local slab --------------
     e2e = None
@@ -334,7 +358,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u16" if elem == 2 else "u32",
                 "data": "synthetic",
-                "config": {"workload": workload, "sharding": "z-slabs x%d" % world,
+                "config": {"workload": workload, "sharding": "z-slabs x%d%s" % (world, (", plane boundaries of equal estimated work %s" % list(bounds)) if bounds else ""),
                            "l2": "input (%.1f GiB) larger than L2, no flush needed" % (nvox * elem / 2 ** 30),
                            "step": "halo exchange + scan + table compaction/sort + cross-rank merge + inertia eig"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),

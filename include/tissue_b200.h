@@ -45,6 +45,9 @@ enum {
 #define TA_PASS_PAIRS6 2u
 #define TA_PASS_WALL18 4u
 #define TA_PASS_ALL 7u
+/* Leave the pair records in hash order (no sort by (lo, hi)): for passes whose records only feed
+ * ta_merge_pair_records on the ranks of a sharded run, which sorts the merged table anyway. */
+#define TA_PASS_UNSORTED 0x2000u
 
 const char* ta_version(void);
 
@@ -72,6 +75,13 @@ int ta_set_slab(ta_ctx* ctx, int64_t own_lo, int64_t own_hi, int64_t slow_offset
  * pair_capacity_hint: expected number of distinct touching pairs (0 = default).  Returns
  * TA_ERR_PAIR_OVERFLOW (tables invalid) if the pair table filled up. */
 int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint);
+
+/* ta_run_pass for a bound volume whose planes become valid in stages (no reference equivalent; the sharded driver
+ * overlaps the NCCL halo exchange with the scan of the interior planes).  Range k = owned planes
+ * [lo_hi[2k], lo_hi[2k+1]) is scanned after CUDA event wait_events[k] (cudaEvent_t, NULL = at once).  The ranges must
+ * tile the owned planes exactly; empty ranges are skipped.  Results are those of ta_run_pass. */
+int ta_run_pass_ranges(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint, int n_ranges,
+                       const int64_t* lo_hi, void* const* wait_events);
 
 /* ta_bind_volume(host) + ta_run_pass with the copy and the scan overlapped: the host volume (pinned memory makes the
  * copy asynchronous) goes to the context-owned device buffer in chunks of `chunk_planes` slow-axis planes (0 = about

@@ -19,7 +19,11 @@ def main():
     ok = True
     for shape, ncell, dt, seed in (((77, 96, 160), 300, "uint16", 5), ((64, 40, 72), 120, "uint32", 6)):
         tdt = torch.uint16 if dt == "uint16" else torch.uint32
-        scan = SlabScan(shape, tdt, rank=rank, world=world)
+        # unequal slabs (one of them a single plane when world >= 4) for the first volume, equal planes for the second
+        bounds = None
+        if seed == 5:
+            bounds = {2: [0, 20, 77], 4: [0, 10, 30, 31, 77]}.get(world)
+        scan = SlabScan(shape, tdt, rank=rank, world=world, bounds=bounds)
         scan.owned().copy_(voronoi_device(shape, ncell, seed, (1, 1, 1), True, dt, zslice=(scan.g_lo, scan.g_hi)))
         torch.cuda.synchronize()
         scan.run(inertia=True)

@@ -97,3 +97,20 @@ def test_partition_covers_all_planes():
         for w in (1, 2, 3, 4, 8):
             b = D.partition_planes(ns, w)
             assert b[0] == 0 and b[-1] == ns and all(b[i] <= b[i + 1] for i in range(w))
+
+
+def test_weighted_partition_balances_a_dome():
+    """Plane boundaries of equal estimated work: every rank gets at least one plane, the boundaries are monotone, and
+    the heaviest slab of a dome-like weight profile is much lighter than with equal heights."""
+    z = np.arange(256)
+    w = np.maximum(0.0, 1.0 - ((z - 140.0) / 100.0) ** 2) * 1000 + 12.0      # tissue in the middle, background elsewhere
+    for world in (2, 3, 4, 8):
+        b = D.partition_planes_weighted(w, world)
+        assert b[0] == 0 and b[-1] == 256 and all(b[i] < b[i + 1] for i in range(world))
+        heavy = max(w[b[r]:b[r + 1]].sum() for r in range(world))
+        e = D.partition_planes(256, world)
+        heavy_equal = max(w[e[r]:e[r + 1]].sum() for r in range(world))
+        assert heavy <= heavy_equal
+        assert heavy <= w.sum() / world * 1.08
+    assert D.partition_planes_weighted(np.zeros(10), 4) == D.partition_planes(10, 4)
+    assert D.partition_planes_weighted([5, 0, 0, 0], 4) == [0, 1, 2, 3, 4]

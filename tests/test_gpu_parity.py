@@ -346,3 +346,24 @@ def test_overlapped_host_pass_equals_bind_then_pass(chunk):
         for a, b in zip(ctx.label_table() + ctx.pair_table(), want):
             assert np.array_equal(a, b)
         ctx.close()
+
+
+def test_pass_in_plane_ranges_equals_one_pass():
+    """ta_run_pass_ranges (the sharded driver's overlap of halo exchange and interior scan): any tiling of the owned
+    planes, in any order, with empty and single-plane ranges, gives the tables of ta_run_pass."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout
+    img = tissue_image((60, 37, 41), 80, seed=12, dome=True)
+    view = np.ascontiguousarray(memory_layout(img)[0])
+    ctx = _native.Context()
+    ctx.bind_host(view)
+    ctx.set_slab(2, 39, 7)
+    ctx.run_pass()
+    want = ctx.label_table() + ctx.pair_table()
+    for ranges in ([(3, 38), (2, 3), (38, 39)], [(20, 39), (2, 2), (2, 20)], [(2, 39)], [(2, 3), (3, 4), (4, 39)]):
+        ctx.run_pass_ranges(ranges, [None] * len(ranges))
+        for a, b in zip(ctx.label_table() + ctx.pair_table(), want):
+            assert np.array_equal(a, b)
+    with pytest.raises(_native.NativeError):
+        ctx.run_pass_ranges([(2, 10), (11, 39)], [None, None])          # a gap
+    ctx.close()

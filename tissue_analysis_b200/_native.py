@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtissue_b200.so")
+# TA_LIB_PATH: a differently built copy of the same library (kernel tuning experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("TA_LIB_PATH") or os.path.join(_HERE, "libtissue_b200.so")
 
 TA_OK = 0
 TA_ERR_CUDA = -1
@@ -20,11 +21,12 @@ TA_ERR_NO_VOLUME = -5
 TA_ERR_NO_TABLES = -6
 
 PASS_MOMENTS, PASS_PAIRS6, PASS_WALL18, PASS_ALL = 1, 2, 4, 7
+PASS_UNSORTED = 0x2000   # pair records stay in hash order (input of merge_pair_records only)
 
 # every symbol include/tissue_b200.h declares (tests/test_cabi_symbols.py checks header <-> library)
 EXPORTS = [
     "ta_version", "ta_ctx_create", "ta_ctx_destroy", "ta_last_error", "ta_set_stream", "ta_bind_volume",
-    "ta_set_slab", "ta_run_pass", "ta_run_pass_host", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
+    "ta_set_slab", "ta_run_pass", "ta_run_pass_host", "ta_run_pass_ranges", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
     "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
     "ta_hollow_out_cells", "ta_cell_shell18", "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
@@ -60,6 +62,7 @@ def load():
     lib.ta_bind_volume.argtypes = [vp, vp, ci, ci, i64, i64, i64]
     lib.ta_set_slab.argtypes = [vp, i64, i64, i64]
     lib.ta_run_pass.argtypes = [vp, u32, u32, u64]
+    lib.ta_run_pass_ranges.argtypes = [vp, u32, u32, u64, ci, P(i64), P(vp)]
     lib.ta_run_pass_host.argtypes = [vp, vp, ci, i64, i64, i64, P(i64), u32, u32, u64, i64]
     lib.ta_label_table_size.argtypes = [vp, P(u64)]
     lib.ta_fetch_label_table.argtypes = [vp, vp, vp, vp, vp]
@@ -142,6 +145,20 @@ class Context(object):
             rc = self.lib.ta_run_pass(self.h, flags, int(max_label_hint), cap)
             if rc == TA_ERR_PAIR_OVERFLOW and attempt < max_retries:
                 cap = max(cap * 4, 1 << 20) if cap else 1 << 22   # never drop pairs: grow and redo the pass
+                continue
+            self._check(rc)
+            return
+
+    def run_pass_ranges(self, ranges, events, flags=PASS_ALL, max_label_hint=0, pair_capacity_hint=0, max_retries=4):
+        """ranges: [(lo, hi), ...] tiling the owned planes; events: cudaEvent_t handles (ints) or None per range."""
+        n = len(ranges)
+        flat = (C.c_int64 * (2 * n))(*[int(v) for r in ranges for v in r])
+        evs = (C.c_void_p * n)(*[C.c_void_p(int(e)) if e else None for e in events])
+        cap = int(pair_capacity_hint)
+        for attempt in range(max_retries + 1):
+            rc = self.lib.ta_run_pass_ranges(self.h, flags, int(max_label_hint), cap, n, flat, evs)
+            if rc == TA_ERR_PAIR_OVERFLOW and attempt < max_retries:
+                cap = max(cap * 4, 1 << 20) if cap else 1 << 22
                 continue
             self._check(rc)
             return

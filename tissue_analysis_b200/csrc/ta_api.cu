@@ -202,7 +202,7 @@ int ta_set_slab(ta_ctx* ctx, int64_t own_lo, int64_t own_hi, int64_t slow_offset
 }
 
 // compaction + sort + gather of the pair hash into ctx->records
-static int build_records(ta_ctx* ctx) {
+static int build_records(ta_ctx* ctx, bool sorted = true) {
     cudaStream_t st = ctx->stream;
     size_t cap = (size_t)ctx->pt.cap_mask + 1;
     if (ctx->sort_alloc < cap) {
@@ -228,6 +228,15 @@ static int build_records(ta_ctx* ctx) {
     const unsigned int n = ctx->host_flags[4 + 1];
     ctx->nrecords = n;
     if (n == 0) return TA_OK;
+    if (!sorted) {
+        int rc0 = ensure(ctx, &ctx->records, &ctx->records_alloc, (size_t)n * ta::REC_WORDS);
+        if (rc0) return rc0;
+        ta::gather_records_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], n,
+                                                                  ctx->records);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
     size_t need = 0;
     const int end_bit = (ctx->elem == 2) ? 48 : 64;   // uint16 labels: key bits 16..31 and 48..63 are zero
     TA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals[0],
@@ -318,8 +327,14 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
 
 // host_src != nullptr: the bound (context-owned) buffer is filled from host_src in chunks of `chunk_planes` planes on
 // a copy stream while the scan kernel already works on the planes that have arrived.
+struct PassRanges {           // ta_run_pass_ranges: plane ranges of the owned region, each behind an optional event
+    int n = 0;
+    const int64_t* lo_hi = nullptr;
+    void* const* wait_events = nullptr;
+};
+
 static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint,
-                         const void* host_src, long long chunk_planes) {
+                         const void* host_src, long long chunk_planes, const PassRanges* ranges = nullptr) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->vol) return fail(ctx, TA_ERR_NO_VOLUME, "ta_run_pass: no volume bound");
     if ((flags & (TA_PASS_ALL | 0x300u)) == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass: empty flags");
@@ -400,7 +415,14 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
-    if (!host_src) {
+    if (ranges) {
+        for (int k = 0; k < ranges->n; ++k) {
+            if (ranges->wait_events && ranges->wait_events[k])
+                TA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ranges->wait_events[k], 0));
+            rc = launch_scan(ctx, P, tmap, ranges->lo_hi[2 * k], ranges->lo_hi[2 * k + 1]);
+            if (rc) return rc;
+        }
+    } else if (!host_src) {
         rc = launch_scan(ctx, P, tmap, ctx->own_lo, ctx->own_hi);
         if (rc) return rc;
     } else {
@@ -451,7 +473,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[10], cyc[11]);
     }
 
-    rc = build_records(ctx);
+    rc = build_records(ctx, !(flags & TA_PASS_UNSORTED));
     if (rc) return rc;
     TA_CUDA(cudaEventRecord(ctx->ev[3], st));
     const uint32_t* status = ctx->host_flags;      // read back inside build_records, after the scan kernel
@@ -466,6 +488,26 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
 
 int ta_run_pass(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint) {
     return run_pass_impl(ctx, flags, max_label_hint, pair_capacity_hint, nullptr, 0);
+}
+
+int ta_run_pass_ranges(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, uint64_t pair_capacity_hint, int n_ranges,
+                       const int64_t* lo_hi, void* const* wait_events) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (n_ranges <= 0 || !lo_hi) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass_ranges: no ranges");
+    // the ranges must tile the owned planes exactly once (any order)
+    std::vector<std::pair<int64_t, int64_t>> r;
+    for (int k = 0; k < n_ranges; ++k)
+        if (lo_hi[2 * k] < lo_hi[2 * k + 1]) r.push_back({lo_hi[2 * k], lo_hi[2 * k + 1]});
+    std::sort(r.begin(), r.end());
+    int64_t at = ctx->own_lo;
+    for (auto& x : r) {
+        if (x.first != at) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass_ranges: ranges must tile the owned planes");
+        at = x.second;
+    }
+    if (at != ctx->own_hi) return fail(ctx, TA_ERR_BAD_ARG, "ta_run_pass_ranges: ranges must tile the owned planes");
+    PassRanges pr;
+    pr.n = n_ranges; pr.lo_hi = lo_hi; pr.wait_events = wait_events;
+    return run_pass_impl(ctx, flags, max_label_hint, pair_capacity_hint, nullptr, 0, &pr);
 }
 
 int ta_run_pass_host(ta_ctx* ctx, const void* host_data, int elem_bytes, int64_t n_fast, int64_t n_mid, int64_t n_slow,

@@ -1174,7 +1174,10 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 // D: listed voxels.  Each thread takes DCH consecutive list entries (they come from one segment, so
                 // they mostly share the label pair) and sums their packed counters in registers; one warp merge per
                 // chunk then updates the shared pair table.
-                constexpr int DCH = 4;
+#ifndef TA_DCH
+#define TA_DCH 4          // voxels per thread and sweep in phase D (2 and 8 measured slower on C3)
+#endif
+                constexpr int DCH = TA_DCH;
                 const int nv = (int)*nvox;
                 for (int ib = 0; ib < nv; ib += NTHREADS * DCH) {
                     PKey key = Vox<T>::PEMPTY;

@@ -4,7 +4,9 @@ The reference is a single Python process (no parallelism of any kind: SURVEY.md 
 form of the same pass.  Every output of the scan is a commutative reduction, so a rank needs only its planes
 plus one halo plane on each side:
 
-  1. halo exchange     boundary planes to both neighbours (NCCL send/recv over NVLink; 2 MiB per face at C3)
+  0. partition         contiguous plane ranges, equal planes or equal estimated work (``partition_planes_weighted``)
+  1. halo exchange     boundary planes to both neighbours (NCCL send/recv over NVLink; 2 MiB per face at C3), on a
+                       side stream, overlapped with the scan of the interior planes (``ta_run_pass_ranges``)
   2. local pass        ownership rules of ``ta_set_slab``: a face belongs to the rank owning its lower voxel, an
                        18-connected wall voxel to the rank owning the voxel
   3. label table       all_reduce SUM of the exact u64 sums, MIN / MAX of the bounding boxes
@@ -24,6 +26,38 @@ REC_WORDS = 9
 def partition_planes(n_slow, world):
     """Contiguous, balanced plane ranges: rank r owns [b[r], b[r+1])."""
     return [(n_slow * r) // world for r in range(world + 1)]
+
+
+def partition_planes_weighted(weights, world):
+    """Contiguous plane ranges of (nearly) equal total weight: rank r owns [b[r], b[r+1]).  ``weights``: one
+    non-negative work estimate per plane (see ``plane_work_weights``).  Every rank gets at least one plane."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    assert n >= world
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    if total <= 0:
+        return partition_planes(n, world)
+    b = [0]
+    for r in range(1, world):
+        cut = int(np.searchsorted(cum, total * r / world, side="left"))
+        # the plane boundary nearest to the ideal cumulative weight
+        if cut > 0 and abs(cum[cut - 1] - total * r / world) <= abs(cum[min(cut, n)] - total * r / world):
+            cut -= 1
+        cut = min(max(cut, b[-1] + 1), n - (world - r))
+        b.append(cut)
+    b.append(n)
+    return b
+
+
+BACKGROUND_PLANE_WEIGHT = 0.12     # a voxel of a one-label brick costs about this much of a tissue voxel (DESIGN.md 6)
+
+
+def plane_work_weights(slab, background):
+    """Work estimate per plane of a (planes, mid, fast) label tensor: tissue voxels + a small share for background."""
+    tissue = (slab != background).sum(dim=(1, 2)).to(torch.float64)
+    per_plane = float(slab.shape[1] * slab.shape[2])
+    return tissue + BACKGROUND_PLANE_WEIGHT * (per_plane - tissue)
 
 
 def exchange_halo_planes(buf, own_lo, own_hi, rank, world):
@@ -80,13 +114,16 @@ def device_tensor(ptr, shape, typestr):
 class SlabScan(object):
     """One rank of the z-slab sharded scan.  ``global_shape`` is (slow, mid, fast)."""
 
-    def __init__(self, global_shape, dtype=torch.uint16, rank=None, world=None, device=None):
+    def __init__(self, global_shape, dtype=torch.uint16, rank=None, world=None, device=None, bounds=None):
+        """``bounds``: world + 1 plane boundaries (e.g. from ``partition_planes_weighted``); default: equal planes."""
         from . import _native
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.global_shape = tuple(int(v) for v in global_shape)
         ns, nm, nf = self.global_shape
-        b = partition_planes(ns, self.world)
+        b = partition_planes(ns, self.world) if bounds is None else [int(v) for v in bounds]
+        assert len(b) == self.world + 1 and b[0] == 0 and b[-1] == ns and all(b[i] < b[i + 1] for i in range(self.world))
+        self.bounds = b
         self.g_lo, self.g_hi = b[self.rank], b[self.rank + 1]
         self.has_lo, self.has_hi = self.rank > 0, self.rank < self.world - 1
         self.own_lo = 1 if self.has_lo else 0
@@ -98,6 +135,7 @@ class SlabScan(object):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._native = _native
         self.stage_ms, self._t0 = {}, 0.0
+        self._halo_stream = self._halo_event = None
 
     def owned(self):
         """View of the owned planes (fill it by upload or by the device generator)."""
@@ -125,12 +163,28 @@ class SlabScan(object):
             max_label_hint = int(mx.item())
             if max_label_hint < 0:
                 raise ValueError("labels >= 2**31 are not supported in the sharded path")
-        exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
-        self._tick("halo")
-        # no host synchronisation: the pass is enqueued on the same (torch current) stream as the NCCL waits
         self.ctx.bind_device(self.buf.data_ptr(), self.elem, nf, nm, ns, keepalive=self.buf)
         self.ctx.set_slab(self.own_lo, self.own_hi, self.g_lo - self.own_lo)
-        self.ctx.run_pass(flags, max_label_hint, pair_capacity_hint)
+        if self.world == 1:
+            self.ctx.run_pass(flags, max_label_hint, pair_capacity_hint)
+        else:
+            # The halo exchange runs on a side stream while the pass stream already scans the interior planes (they need
+            # no halo); the first and the last owned plane follow behind the exchange's event.  No host synchronisation.
+            main = torch.cuda.current_stream(self.device)
+            if self._halo_stream is None:
+                self._halo_stream = torch.cuda.Stream(self.device)
+                self._halo_event = torch.cuda.Event()
+            self._halo_stream.wait_stream(main)
+            with torch.cuda.stream(self._halo_stream):
+                exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
+                self._halo_event.record(self._halo_stream)
+            lo, hi = self.own_lo, self.own_hi
+            first = (lo, min(lo + 1, hi)) if self.has_lo else (lo, lo)
+            last = (max(hi - 1, first[1]), hi) if self.has_hi else (hi, hi)
+            ev = self._halo_event.cuda_event
+            # the local records only feed the merge, which sorts: skip the local sort
+            self.ctx.run_pass_ranges([(first[1], last[0]), first, last], [None, ev, ev],
+                                     flags | self._native.PASS_UNSORTED, max_label_hint, pair_capacity_hint)
         self._tick("pass")
         if self.world > 1:
             self.merge()
@@ -143,8 +197,15 @@ class SlabScan(object):
         if p_s1 == p_count + 8 * n and p_s2 == p_s1 + 24 * n:
             # the library keeps count | s1 | s2 in one block: one SUM collective for all ten u64 columns
             dist.all_reduce(device_tensor(p_count, (n * 10,), "<i8"), op=dist.ReduceOp.SUM)
-            dist.all_reduce(device_tensor(p_bmin, (n * 3,), "<i4"), op=dist.ReduceOp.MIN)
-            dist.all_reduce(device_tensor(p_bmax, (n * 3,), "<i4"), op=dist.ReduceOp.MAX)
+            if p_bmax == p_bmin + 12 * n:
+                # bmin | bmax are one block too: MAX(x) = -MIN(-x), one collective for both halves of the boxes
+                box = device_tensor(p_bmin, (n * 6,), "<i4")
+                box[n * 3:].neg_()
+                dist.all_reduce(box, op=dist.ReduceOp.MIN)
+                box[n * 3:].neg_()
+            else:
+                dist.all_reduce(device_tensor(p_bmin, (n * 3,), "<i4"), op=dist.ReduceOp.MIN)
+                dist.all_reduce(device_tensor(p_bmax, (n * 3,), "<i4"), op=dist.ReduceOp.MAX)
         else:
             allreduce_label_tables(device_tensor(p_count, (n,), "<i8"), device_tensor(p_s1, (n * 3,), "<i8"),
                                    device_tensor(p_s2, (n * 6,), "<i8"), device_tensor(p_bmin, (n * 3,), "<i4"),
