@@ -367,3 +367,31 @@ def test_pass_in_plane_ranges_equals_one_pass():
     with pytest.raises(_native.NativeError):
         ctx.run_pass_ranges([(2, 10), (11, 39)], [None, None])          # a gap
     ctx.close()
+
+
+def test_kernel_variants_give_the_same_tables(monkeypatch, capfd):
+    """Every instantiation of the scan kernel -- phase clocks on (TA_PHASE_TIMING=1), TMA or cp.async staging
+    (TA_NO_TMA=1), per-voxel or one-hot pair path -- fills identical tables."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout
+    img = tissue_image((160, 48, 27), 120, seed=31, dome=True)
+    view = np.ascontiguousarray(memory_layout(img)[0])
+
+    def tables(extra_flags=0):
+        ctx = _native.Context()
+        ctx.bind_host(view)
+        ctx.run_pass(_native.PASS_ALL | extra_flags)
+        out = ctx.label_table() + ctx.pair_table()
+        ctx.close()
+        return out
+
+    want = tables()
+    for env in ({"TA_PHASE_TIMING": "1"}, {"TA_NO_TMA": "1"}, {"TA_PHASE_TIMING": "1", "TA_NO_TMA": "1"}):
+        for flags in (0, 0x1000):
+            with monkeypatch.context() as m:
+                for k, v in env.items():
+                    m.setenv(k, v)
+                got = tables(flags)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (env, flags)
+    capfd.readouterr()        # the phase shares go to stderr

@@ -49,6 +49,8 @@ struct ta_ctx {
     double* d_evecs = nullptr;
     size_t eig_alloc_rows = 0;
     u64* phase_cycles = nullptr;
+    u64* diag_host = nullptr;         // host-mapped [8], survives a kernel trap
+    u64* diag_dev = nullptr;
 
     cudaEvent_t ev[6] = {};
     cudaStream_t copy_stream = nullptr;          // H2D chunks of ta_run_pass_host
@@ -87,11 +89,37 @@ template <typename P> static int ensure(ta_ctx* ctx, P** ptr, size_t* have, size
     return TA_OK;
 }
 
+// The scan kernel's instantiations: label width x pair path (per-voxel | one-hot, flag 0x1000) x phase clocks
+// (TA_PHASE_TIMING=1).  The product path is (width, per-voxel, no clocks).
+typedef void (*scan_kernel_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
+static scan_kernel_fn scan_kernel_variant(int elem, bool onehot, bool timing) {
+    if (elem == 2) {
+        if (onehot) return timing ? ta::scan_kernel<uint16_t, true, true> : ta::scan_kernel<uint16_t, true, false>;
+        return timing ? ta::scan_kernel<uint16_t, false, true> : ta::scan_kernel<uint16_t, false, false>;
+    }
+    if (onehot) return timing ? ta::scan_kernel<uint32_t, true, true> : ta::scan_kernel<uint32_t, true, false>;
+    return timing ? ta::scan_kernel<uint32_t, false, true> : ta::scan_kernel<uint32_t, false, false>;
+}
+
 extern "C" {
 
 const char* ta_version(void) { return "tissue_b200 0.1 (sm_100a)"; }
 
-const char* ta_last_error(ta_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+const char* ta_last_error(ta_ctx* ctx) {
+    if (!ctx) return g_err.c_str();
+    if (ctx->diag_host && ctx->diag_host[0] && ctx->err.find("tile copy") == std::string::npos) {
+        const u64* d = ctx->diag_host;
+        char buf[384];
+        snprintf(buf, sizeof buf,
+                 " [scan kernel: a TMA tile copy did not complete: %llu waits timed out; first: CTA %llu thread %llu, "
+                 "iteration %llu brick %llu, parity %llu next brick %llu, mbarrier word 0x%016llx, box origin (%d, %d, %d)]",
+                 d[0], d[1] >> 32, d[1] & 0xFFFFFFFFull, d[2] >> 32, d[2] & 0xFFFFFFFFull, d[3] >> 32,
+                 d[3] & 0xFFFFFFFFull, d[4], (int)(d[5] >> 32), (int)(int16_t)((d[5] >> 16) & 0xFFFF),
+                 (int)(int16_t)(d[5] & 0xFFFF));
+        ctx->err += buf;
+    }
+    return ctx->err.c_str();
+}
 
 int ta_ctx_create(ta_ctx** out, int device) {
     ta_ctx* ctx = nullptr;
@@ -112,10 +140,12 @@ int ta_ctx_create(ta_ctx** out, int device) {
     for (auto& e : ctx->ev) TA_CUDA(cudaEventCreate(&e));
     TA_CUDA(cudaMalloc((void**)&ctx->status, 8 * sizeof(uint32_t)));
     ctx->counters = ctx->status + 4;
-    TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::scan_smem_bytes<uint16_t>()));
-    TA_CUDA(cudaFuncSetAttribute(ta::scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::scan_smem_bytes<uint32_t>()));
+    for (int e = 0; e < 2; ++e)
+        for (int oh = 0; oh < 2; ++oh)
+            for (int tm = 0; tm < 2; ++tm)
+                TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, oh != 0, tm != 0),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
     *out = ctx;
     return TA_OK;
 }
@@ -316,10 +346,9 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     if (total == 0) return TA_OK;
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
-    if (ctx->elem == 2)
-        ta::scan_kernel<uint16_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint16_t>(), st>>>(P, ctx->lt, ctx->pt, tmap);
-    else
-        ta::scan_kernel<uint32_t><<<grid, ta::NTHREADS, ta::scan_smem_bytes<uint32_t>(), st>>>(P, ctx->lt, ctx->pt, tmap);
+    const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
+    const size_t smem = ctx->elem == 2 ? ta::scan_smem_bytes<uint16_t>() : ta::scan_smem_bytes<uint32_t>();
+    scan_kernel_variant(ctx->elem, onehot, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     return TA_OK;
@@ -402,6 +431,16 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     memset(&tmap, 0, sizeof tmap);
     P.use_tma = (P.vec_ok && !getenv("TA_NO_TMA") && make_tile_map(ctx, &tmap)) ? 1 : 0;
     P.brick_counter = &ctx->counters[0];
+    if (!ctx->diag_host) {
+        if (cudaHostAlloc((void**)&ctx->diag_host, 8 * sizeof(u64), cudaHostAllocMapped) == cudaSuccess) {
+            memset(ctx->diag_host, 0, 8 * sizeof(u64));
+            if (cudaHostGetDevicePointer((void**)&ctx->diag_dev, ctx->diag_host, 0) != cudaSuccess) ctx->diag_dev = nullptr;
+        } else {
+            cudaGetLastError();
+            ctx->diag_host = nullptr;
+        }
+    }
+    P.diag = ctx->diag_dev;
     P.phase_cycles = nullptr;
     const bool phase_timing = getenv("TA_PHASE_TIMING") != nullptr;
     if (phase_timing) {
@@ -470,7 +509,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
                               "R one-hot", "S stencil"};
         fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
         for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
-        fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[10], cyc[11]);
+        fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[12], cyc[13]);
     }
 
     rc = build_records(ctx, !(flags & TA_PASS_UNSORTED));

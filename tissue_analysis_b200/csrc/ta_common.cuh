@@ -40,6 +40,7 @@ struct ScanParams {
     int use_tma;                 // the tile (brick + halo) is one TMA box copy (needs vec_ok and a tensor map)
     unsigned int* brick_counter; // dynamic brick scheduler
     u64* phase_cycles;           // optional [16]: per-phase clock64 totals of thread 0 of every CTA (profiling aid)
+    u64* diag;                   // [8] host-mapped: what a CTA was doing when it gave up waiting for a tile copy
 };
 
 __device__ __forceinline__ uint32_t ta_hash64(u64 k) {

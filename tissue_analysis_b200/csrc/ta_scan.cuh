@@ -24,14 +24,16 @@
 //      worklist and are handled with a register dedup of up to 4 labels (exact rescan beyond that).
 //   F  flush the per-brick label table (u32 brick-local sums -> shifted u64 global REDs) and pair table.
 //
-// One-hot pair path (bricks whose tile holds at most NID distinct labels, NID = bits of a label word; the usual case):
-//   B  also inserts every label of the tile into a NID-slot table; the slot index is the brick-local id.
-//   R  after the march the tile is rewritten in place: label -> one-hot word (1 << id).
+// One-hot pair path (instantiation OH = true, flag 0x1000; an experiment kept testable, not the default -- it is exact
+// but slower than C2 / D / D2 on every measured configuration):
+//   R  after the march the tile is rewritten in place: label -> one-hot word (1 << id) of a brick-local id.  Ids come
+//      from NID-slot tables (NID = bits of a label word), one per quarter of the row for uint16 so that 16 ids suffice;
+//      the two lanes either side of a quarter boundary are kept in both encodings (edge array).
 //   S  per listed segment, SIMD on the packed lanes: the OR of the 18 neighbour words is the SET of labels around
 //      each voxel (the de-duplication of the wall18 definition is the OR itself); `& ~own` leaves the other labels.
-//      Counts per (own id, other id) are popcounts of one bit column; they go to a direct-indexed NID x NID table of
-//      packed 16-bit counters [wall18 | +f] [+m | +s] after a warp merge.  No per-voxel work, no junction special case.
-//   Bricks with more labels (noise-like data) use C2 / D / D2 on the untouched tile.
+//      Counts per (own id, other id) are sums of one bit column; they go to a direct-indexed table of packed 16-bit
+//      counters [wall18 | +f] [+m | +s] after a warp merge.  No per-voxel work, no junction special case.
+//   A quarter with more labels than ids (noise-like data): the brick is staged again and takes C2 / D / D2.
 #pragma once
 #include "ta_common.cuh"
 
@@ -81,7 +83,7 @@ template <> struct Vox<uint32_t> {
 template <typename T> constexpr size_t scan_smem_bytes() {
     return (size_t)TILE_SEGS * 16 + (size_t)TILE_ROWS * NFS * sizeof(typename Vox<T>::Code) + LT_SLOTS * 4 +
            LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + PT_SLOTS * PT_WORDS * 4 +
-           SEGLIST_CAP * 2 + 2 * VOXLIST_CAP * 2 + 64 + 256;
+           SEGLIST_CAP * 2 + 2 * VOXLIST_CAP * 2 + 64 + 256 + 128;
 }
 
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
@@ -743,7 +745,10 @@ TA_HD void oh_segment_pairs(const uint4* tile, const T* edg, int r, int fs, int 
     }
 }
 
-template <typename T>
+// OH: compile the one-hot pair path (phases R + S) in.  The product launches OH = false (per-voxel pair path only, the
+// faster one on every measured configuration) unless flag 0x1000 asks for the one-hot path.
+// TIMING: compile the per-phase clocks in (profiling aid, TA_PHASE_TIMING=1).  The product kernel carries none of it.
+template <typename T, bool OH, bool TIMING>
 __global__ void __launch_bounds__(NTHREADS, 3)
 scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::Code Code;
@@ -784,9 +789,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
     const bool do_pairs = do_p6 || do_w18;
-    // Pair path: one-hot (R + S) or per-voxel (C2 / D / D2).  Both are exact; the default follows the measurements in
-    // DESIGN.md section 6 (uint32: one-hot; uint16: per-voxel).  0x800 forces per-voxel, 0x1000 forces one-hot.
-    const bool oh_enabled = do_pairs && !(P.flags & 0x800u) && (sizeof(T) == 4 || (P.flags & 0x1000u));
+    // Pair path: per-voxel (C2 / D / D2) or, in the OH instantiation, one-hot (R + S).  Both are exact.
+    const bool oh_enabled = OH && do_pairs && !(P.flags & 0x800u);
     const int nf = (int)P.nf, nm = (int)P.nm, ns = (int)P.ns;
 
     // reset the per-brick tables once; the flush at the end of each brick re-arms them
@@ -807,9 +811,14 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    long long tp = 0;
-    if (P.phase_cycles && tid == 0) tp = clock64();
-#define TA_TICK(k) if (P.phase_cycles && tid == 0) { long long now_ = clock64(); atomicAdd(&P.phase_cycles[k], (u64)(now_ - tp)); tp = now_; }
+    // Phase clocks (TIMING only): thread 0 keeps per-phase cycle totals and the last time stamp in shared memory -- no
+    // register lives across the phases for it -- and adds the totals to P.phase_cycles once, when the CTA is done.
+    u64* sh_tick = reinterpret_cast<u64*>(sh.junclist + VOXLIST_CAP);       // [16]: [0..11] totals, [15] last stamp
+    if (TIMING && tid == 0) {
+        for (int k = 0; k < 15; ++k) sh_tick[k] = 0ull;
+        sh_tick[15] = (u64)clock64();
+    }
+#define TA_TICK(k) if (TIMING && tid == 0) { const u64 now_ = (u64)clock64(); sh_tick[k] += now_ - sh_tick[15]; sh_tick[15] = now_; }
 
     if (tid == 0) sh.ctr[6] = atomicAdd(P.brick_counter, 1u);
     __syncthreads();
@@ -836,9 +845,24 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
                 tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
             }
+            // Thread 0 may still be in a divergent tail of the previous iteration (table flush, phase clocks) when its
+            // warp mates get here.  They must not start polling before it has issued the copy: a warp whose other lanes
+            // spin in try_wait can starve the one lane the barrier is waiting for (seen as a lost copy with
+            // TA_PHASE_TIMING=1).  Converge the warp first.
+            __syncwarp();
             unsigned spins = 0;
             while (!mbar_try_wait(tma_bar, tma_parity)) {
-                if (++spins > (1u << 26)) __trap();          // a lost copy must not hang the box
+                if (++spins > (1u << 18)) {                  // ~1 s: a lost copy must not hang the box; fail loudly
+                    if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
+                        P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
+                        P.diag[2] = ((u64)iter << 32) | (u64)brick;
+                        P.diag[3] = ((u64)tma_parity << 32) | (u64)sh.ctr[6 + ((iter + 1u) & 1u)];
+                        P.diag[4] = *reinterpret_cast<volatile u64*>(tma_bar);
+                        P.diag[5] = ((u64)(uint32_t)(F0 - SEG) << 32) | ((u64)(uint32_t)(M0 - 1) << 16) | (u64)(uint32_t)(S0 - 1);
+                        __threadfence_system();
+                    }
+                    __trap();
+                }
             }
             tma_parity ^= 1u;
             // Elements outside the buffer arrive as zeros; the tile wants them clamped (replicated edge voxels).  Only
@@ -973,7 +997,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                     else if (victim == 1) { const MomSlot t = S1_; S1_ = S2_; S2_ = t; }
                     if (last == 2) last = victim; else if (prev == 2) prev = victim;   // the old S2_ moved there
                     if (S2_.pS) {
-                        if (P.phase_cycles) atomicAdd(&pt.status[2], 1u);   // profiling aid: eviction count
+                        if (TIMING) atomicAdd(&pt.status[2], 1u);   // profiling aid: eviction count
                         uint32_t v[LT_FIELDS];
                         S2_.fields(v, (uint32_t)m);
                         label_add<T>(sh, lt, pt.status, S2_.label, v, gF0, gM0, gS0);
@@ -1072,7 +1096,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 __syncthreads();
             }
         }
-        if (P.phase_cycles && tid == 0 && do_pairs) atomicAdd(&P.phase_cycles[use_oh ? 10 : 11], 1ull);   // bricks per path
+        if (TIMING && tid == 0 && do_pairs && P.phase_cycles) atomicAdd(&P.phase_cycles[use_oh ? 12 : 13], 1ull);   // bricks per path
         if (use_oh) {
             const int nseg = (int)sh.ctr[1];
             const T* edg = reinterpret_cast<const T*>(sh.edg);
@@ -1366,6 +1390,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         TA_TICK(7);
     }
 #undef TA_TICK
+    if (TIMING && tid == 0 && P.phase_cycles)
+        for (int k = 0; k < 12; ++k) atomicAdd(&P.phase_cycles[k], sh_tick[k]);
 }
 
 }  // namespace ta
