@@ -681,10 +681,12 @@ class SpatialImageAnalysis3D(AbstractSpatialImageAnalysis):
 
 
 def SpatialImageAnalysis(image, *args, **kwd):
-    """SIA:1663-1680: dispatch on dimensionality.  The reference routes 2D input (and shape[2] == 1) to a
+    """SIA:1663-1680: a file name is read first (SIA:1668-1671), then dispatch on dimensionality.  The reference
+    routes 2D input (and shape[2] == 1) to a
     ``SpatialImageAnalysis2D`` class that is not defined anywhere in it; that path raises here as well."""
     if isinstance(image, str):
-        raise NotImplementedError("file input needs openalea.image.serial.basics.imread (SIA:1670), not available")
+        from .serial import imread          # SIA:1668-1671 (openalea's imread; INRIMAGE-4 stacks here)
+        image = imread(image)
     assert len(image.shape) in [2, 3]
     if len(image.shape) == 2 or image.shape[2] == 1:
         raise NotImplementedError("SpatialImageAnalysis2D is referenced but never defined by the reference (SIA:1677)")
