@@ -1,0 +1,167 @@
+// Block-bitmask feature extraction: groundwork for the next scan kernel (NOT launched by the product yet).
+//
+// Motivation (tools/simt_stats.py): the current pair phases work per segment / per voxel and run
+// at a third to a half of their per-thread cost estimate because a warp executes the maximum over its lanes of every
+// data-dependent loop.  Here the work unit is a small 3-D block, one per thread -- a brick of 128 x 16 x 8 voxels is
+// exactly 256 blocks of 8 x 4 x 2 -- and everything after the discovery of the block's labels is straight-line bit
+// algebra:
+//
+//   window   the block plus a one-voxel halo: 10 x 6 x 4 voxels = four planes of 60 bits (bit = row * 10 + x);
+//   labels   at most BLK_MAXLAB distinct labels in the window (41 % of the windows of a C3-like tissue hold one label,
+//            38 % two, 16 % three, 4 % four, 0.9 % more: those blocks report `overflow` and take the per-voxel path);
+//   masks    one window mask per label: a SIMD compare of every window row against the label, collapsed to bits;
+//   moments  of a label = row-wise (count, sum x, sum x^2) of its centre bits, weighted by the row / plane index;
+//   pairs    wall18(i -> j) = popcount(centre_i & dilate18(mask_j)); faces = popcount(centre_i & shifted mask_j).
+//
+// No atomics, no hash, no worklist inside the block.  Everything here is host-compilable (TA_HD);
+// tests/host/block_host_check.cu runs it over whole tiles against a brute-force count.  Label width: uint16 (a block
+// row is one 16-byte segment); the uint32 form needs a 4-voxel-wide block and is not written yet.
+#pragma once
+#include "ta_scan.cuh"
+
+namespace ta {
+
+constexpr int BLK_M = 4, BLK_S = 2;            // block rows and planes; its f extent is one segment (SEG voxels)
+constexpr int BLK_MAXLAB = 4;
+constexpr int BLK_ROWBITS = 10;                // SEG + 2 window positions per row (uint16)
+constexpr u64 BLK_PLANE_ALL = (1ull << 60) - 1ull;
+
+TA_HD int ta_popc64(u64 x) { return ta_popc((uint32_t)x) + ta_popc((uint32_t)(x >> 32)); }
+TA_HD int ta_ffs64(u64 x) {                    // 1-based index of the lowest set bit, 0 if none
+    const uint32_t lo = (uint32_t)x;
+    if (lo) return ta_ffs(lo);
+    const uint32_t hi = (uint32_t)(x >> 32);
+    return hi ? 32 + ta_ffs(hi) : 0;
+}
+
+// 10-bit mask of one window row (vector index t of its segment in the tile): bit 0 = the lane left of the segment,
+// bits 1..8 = the segment's lanes, bit 9 = the lane right of it; set where the voxel equals label L.
+TA_HD uint32_t block_row_mask(const uint4* tile, int t, uint32_t L) {
+    const uint4 c = tile[t];
+    const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
+    const uint32_t pat = L * 0x00010001u, one = 0x00010001u;
+    // 1 in every lane that DIFFERS from L, collapsed to one bit per lane (same collapse as the kernel's boundary flags)
+    const uint32_t tt = ta_vminu2(c.x ^ pat, one) | (ta_vminu2(c.y ^ pat, one) << 2) | (ta_vminu2(c.z ^ pat, one) << 4) |
+                        (ta_vminu2(c.w ^ pat, one) << 6);
+    const uint32_t neq = (tt & 0x55u) | ((tt >> 15) & 0xAAu);
+    return ((~neq & 0xFFu) << 1) | ((uint32_t)e[-1] == L ? 1u : 0u) | ((uint32_t)e[8] == L ? 0x200u : 0u);
+}
+
+// Window masks of label L: plane p = tile plane (s0 - 1 + p), rows (m0 - 1 .. m0 + 4).  `t0` = vector index of the
+// window's first row (m0 - 1, s0 - 1) at the block's segment.
+TA_HD void block_label_masks(const uint4* tile, int t0, uint32_t L, u64 mask[4]) {
+#pragma unroll
+    for (int p = 0; p < BLK_S + 2; ++p) {
+        u64 m = 0ull;
+#pragma unroll
+        for (int r = 0; r < BLK_M + 2; ++r)
+            m |= (u64)block_row_mask(tile, t0 + p * PLANEV + r * ROWV, L) << (BLK_ROWBITS * r);
+        mask[p] = m;
+    }
+}
+
+// (count, sum x, sum x^2) of the set bits of a byte, x = bit position 0..7, packed as n | sx << 8 | sxx << 16.
+TA_HD uint32_t block_byte_moments(uint32_t b) {
+    const uint32_t n = ta_popc(b);
+    const uint32_t b0 = ta_popc(b & 0xAAu), b1 = ta_popc(b & 0xCCu), b2 = ta_popc(b & 0xF0u);
+    const uint32_t sx = b0 + 2u * b1 + 4u * b2;
+    // x^2 = (x0 + 2 x1 + 4 x2)^2 = x0 + 4 x1 + 16 x2 + 4 x0 x1 + 8 x0 x2 + 16 x1 x2 for bit values x0, x1, x2
+    const uint32_t sxx = b0 + 4u * b1 + 16u * b2 + 4u * ta_popc(b & 0x88u) + 8u * ta_popc(b & 0xA0u) + 16u * ta_popc(b & 0xC0u);
+    return n | (sx << 8) | (sxx << 16);
+}
+
+// 18-neighbourhood dilation of a label's window masks, for the two centre planes (p = 1, 2).  Bits outside the centre
+// (halo columns / rows, bits >= 60) are not meaningful: the callers AND with centre masks.
+TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) {
+    u64 own[4], cross[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const u64 P = mask[p];
+        const u64 hx = (P << 1) | (P >> 1);
+        const u64 hy = (P << BLK_ROWBITS) | (P >> BLK_ROWBITS);
+        own[p] = hx | hy | (hx << BLK_ROWBITS) | (hx >> BLK_ROWBITS);      // the 8 in-plane neighbours
+        cross[p] = P | hx | hy;                                            // the 5 neighbours in an adjacent plane
+    }
+    dil[0] = own[1] | cross[0] | cross[2];
+    dil[1] = own[2] | cross[1] | cross[3];
+}
+
+// One block.  tile: the brick tile of the scan kernel (labels, clamped halo); (fs, m0, s0): the block's segment, first
+// row and first plane inside the brick; nvf / nvm / nvs: how many of its 8 x 4 x 2 voxels per axis lie inside the volume
+// and the owned plane range (ragged edges).
+//   on_label(L, v[16]): n, sf, sm, ss, sff, sfm, sfs, smm, sms, sss, fmin, mmin, smin, fmax, mmax, smax -- block-local
+//                       coordinates, the field order of the kernel's per-brick label table;
+//   on_pair(La, Lb, w18, ff, fm, fs): seen from the voxels of La: wall18 voxels towards Lb and +f / +m / +s faces whose
+//                       lower voxel is La and upper voxel Lb.
+// false: more than BLK_MAXLAB labels in the window (nothing was emitted).
+template <typename OnLabel, typename OnPair>
+TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
+                          OnPair&& on_pair) {
+    const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);          // tile row (m0 - 1, s0 - 1): the tile itself has a halo
+    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+    uint32_t lab[BLK_MAXLAB];
+    u64 mask[BLK_MAXLAB][4];
+    u64 rest[4] = {BLK_PLANE_ALL, BLK_PLANE_ALL, BLK_PLANE_ALL, BLK_PLANE_ALL};
+    int k = 0;
+    for (;;) {
+        int p = 0;
+        while (p < 4 && rest[p] == 0ull) ++p;
+        if (p == 4) break;
+        if (k == BLK_MAXLAB) return false;
+        const int bit = ta_ffs64(rest[p]) - 1, r = bit / BLK_ROWBITS, x = bit % BLK_ROWBITS;
+        // window position (x, r, p) = tile element of row t0 + p * PLANEV + r * ROWV, lane x - 1
+        const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * 8 + (x - 1)];
+        lab[k] = L;
+        block_label_masks(tile, t0, L, mask[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rest[q] &= ~mask[k][q];
+        ++k;
+    }
+    // centre voxels inside the volume: x = 1 .. nvf, rows 1 .. nvm, planes 1 .. nvs
+    u64 cv = 0ull;
+    for (int r = 1; r <= nvm; ++r) cv |= (u64)(((1u << nvf) - 1u) << 1) << (BLK_ROWBITS * r);
+    const u64 cvp[2] = {nvs >= 1 ? cv : 0ull, nvs >= 2 ? cv : 0ull};
+
+    u64 cen[BLK_MAXLAB][2], dil[BLK_MAXLAB][2];
+    for (int i = 0; i < k; ++i) {
+        cen[i][0] = mask[i][1] & cvp[0];
+        cen[i][1] = mask[i][2] & cvp[1];
+        block_dilate18(mask[i], dil[i]);
+    }
+    for (int i = 0; i < k; ++i) {
+        if (!(cen[i][0] | cen[i][1])) continue;
+        // ---- moments of label i over its centre voxels
+        uint32_t v[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+        uint32_t colmask = 0u;
+        for (int p = 0; p < 2; ++p)
+            for (int r = 0; r < BLK_M; ++r) {
+                const uint32_t b = (uint32_t)(cen[i][p] >> (BLK_ROWBITS * (r + 1) + 1)) & 0xFFu;
+                if (!b) continue;
+                const uint32_t t = block_byte_moments(b), n = t & 0xFFu, sx = (t >> 8) & 0xFFu, sxx = t >> 16;
+                const uint32_t m = (uint32_t)r, s = (uint32_t)p;
+                v[0] += n; v[1] += sx; v[2] += m * n; v[3] += s * n;
+                v[4] += sxx; v[5] += m * sx; v[6] += s * sx; v[7] += m * m * n; v[8] += m * s * n; v[9] += s * s * n;
+                colmask |= b;
+                v[11] = v[11] < m ? v[11] : m; v[14] = v[14] > m ? v[14] : m;
+                v[12] = v[12] < s ? v[12] : s; v[15] = v[15] > s ? v[15] : s;
+            }
+        v[10] = (uint32_t)ta_ffs(colmask) - 1u;
+        uint32_t top = 7u;
+        while (!((colmask >> top) & 1u)) --top;
+        v[13] = top;
+        on_label(lab[i], v);
+        // ---- pairs seen from label i
+        for (int j = 0; j < k; ++j) {
+            if (j == i) continue;
+            const uint32_t w18 = ta_popc64(cen[i][0] & dil[j][0]) + ta_popc64(cen[i][1] & dil[j][1]);
+            const uint32_t ff = ta_popc64(cen[i][0] & (mask[j][1] >> 1)) + ta_popc64(cen[i][1] & (mask[j][2] >> 1));
+            const uint32_t fm = ta_popc64(cen[i][0] & (mask[j][1] >> BLK_ROWBITS)) +
+                                ta_popc64(cen[i][1] & (mask[j][2] >> BLK_ROWBITS));
+            const uint32_t fsl = ta_popc64(cen[i][0] & mask[j][2]) + ta_popc64(cen[i][1] & mask[j][3]);
+            if (w18 | ff | fm | fsl) on_pair(lab[i], lab[j], w18, ff, fm, fsl);
+        }
+    }
+    return true;
+}
+
+}  // namespace ta

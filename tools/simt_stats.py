@@ -147,6 +147,29 @@ def main():
     print("labels per tile (130x18x10): mean %.1f, > 16: %.1f %%;  per row quarter (34x18x10): mean %.1f, > 16: %.2f %%" % (
         per_tile.mean(), 100 * (per_tile > 16).mean(), per_quarter.mean(), 100 * (per_quarter > 16).mean()))
 
+    # ---- labels in the window of a small 3-D block (candidate work unit: one thread per block) -------------------
+    for (bx, by, bz) in ((8, 4, 2), (8, 2, 4), (4, 4, 4), (8, 4, 4), (8, 8, 2)):
+        ks = []
+        for z0 in range(0, Z - bz + 1, bz):
+            zs = slice(z0, z0 + bz + 2)
+            for y0 in range(0, Y - by + 1, by):
+                ys = slice(y0, y0 + by + 2)
+                row = pad[zs, ys, :]
+                for x0 in range(0, X - bx + 1, bx):
+                    w = row[:, :, x0:x0 + bx + 2]
+                    a = w.flat[0]
+                    if (w == a).all():
+                        ks.append(1)
+                    else:
+                        ks.append(len(np.unique(w)))
+        ks = np.array(ks)
+        n = (len(ks) // 32) * 32
+        wk = ks[:n].reshape(-1, 32)                      # 32 consecutive blocks along x = one warp
+        print("block %dx%dx%d (window %dx%dx%d): labels in the window 1: %.1f %%, 2: %.1f %%, 3: %.1f %%, 4: %.1f %%, > 4: %.2f %%; "
+              "mean %.2f, warp max mean %.2f" % (bx, by, bz, bx + 2, by + 2, bz + 2, 100 * (ks == 1).mean(), 100 * (ks == 2).mean(),
+                                                100 * (ks == 3).mean(), 100 * (ks == 4).mean(), 100 * (ks > 4).mean(), ks.mean(),
+                                                wk.max(1).mean()))
+
 
 if __name__ == "__main__":
     main()
