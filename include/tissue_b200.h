@@ -48,6 +48,9 @@ enum {
 /* Leave the pair records in hash order (no sort by (lo, hi)): for passes whose records only feed
  * ta_merge_pair_records on the ranks of a sharded run, which sorts the merged table anyway. */
 #define TA_PASS_UNSORTED 0x2000u
+/* Measurement switches, never needed for results (every combination fills identical tables, tests/test_gpu_parity.py):
+ * 0x1000 launches the scan kernel's one-hot pair-counting instantiation, 0x800 forces the default per-voxel one;
+ * 0x100 / 0x200 / 0x400 stop the kernel after staging / after the uniformity codes / before the table flush. */
 
 const char* ta_version(void);
 
