@@ -95,3 +95,31 @@ def test_requests_for_absent_labels():
         SpatialImageAnalysis3D(img, background=1.5, _backend=OracleBackend(img))
     with pytest.raises(ValueError):
         prod.label_request(3.2)
+
+
+def test_wall_areas_fast_path_equals_the_per_label_loop():
+    """wall_areas answers the usual input with one table lookup; the floats must be those of the reference's per-label
+    loop (SIA:986-992), for real and voxel units, anisotropic voxels, subsets, lists with repeated labels (loop path)
+    and neighbours that do not touch."""
+    from tissue_analysis_b200 import SpatialImage
+    img = SpatialImage(np.asarray(tissue_image((30, 26, 22), 25, seed=9, dome=True)), voxelsize=(0.21, 0.37, 0.53))
+    sia = SpatialImageAnalysis3D(img, background=1, _backend=OracleBackend(img))
+
+    def loop(neighbors, real):
+        areas = {}
+        for label_id, lneighbors in neighbors.items():
+            neigh = [n for n in lneighbors if n > label_id]
+            if neigh:
+                for key, val in sia.cell_wall_area(label_id, neigh, real=real).items():
+                    areas[key] = areas.get(key, 0.0) + val
+        return areas
+
+    full = sia.neighbors(verbose=False)
+    some = dict(list(full.items())[3:9])
+    far = {2: [3, 4, 5, 26, 27], 5: [9, 2]}                                   # mostly not touching
+    twice = {k: v + v[:1] for k, v in some.items()}                            # repeated labels: the loop path
+    for nb in (full, some, far, twice):
+        for real in (True, False):
+            got, want = sia.wall_areas(nb, real=real), loop(nb, real)
+            assert list(got.keys()) == list(want.keys())
+            assert all(got[k] == want[k] and type(got[k]) is type(want[k]) for k in want)

@@ -84,6 +84,8 @@ class AbstractSpatialImageAnalysis(object):
         self._backend = _backend
         self._adj = None
         self._com_all = None
+        self._max_label_of = None
+        self._max_label_value = 0
 
     # ------------------------------------------------------------------------------------------- the scan
     def _scan(self):
@@ -281,8 +283,12 @@ class AbstractSpatialImageAnalysis(object):
 
     # ------------------------------------------------------------------------------------------- boundingbox
     def _max_label(self):
-        present = np.nonzero(self._tables().count)[0]
-        return int(present[-1]) if present.size else 0
+        t = self._tables()
+        if self._max_label_of is not t:                   # one scan of the count column per set of tables
+            present = np.nonzero(t.count)[0]
+            self._max_label_value = int(present[-1]) if present.size else 0
+            self._max_label_of = t
+        return self._max_label_value
 
     def _bbox_entry(self, i):
         """``nd.find_objects(image)[i-1]`` (SIA:517, 526, 533) including its list-indexing behaviour."""
@@ -467,6 +473,9 @@ class AbstractSpatialImageAnalysis(object):
         # SIA:962-993
         if neighbors is None:
             neighbors = self.neighbors()
+        fast = self._wall_areas_vectorised(neighbors, real)
+        if fast is not None:
+            return fast
         areas = {}
         for label_id, lneighbors in neighbors.items():
             neigh = [n for n in lneighbors if n > label_id]
@@ -475,6 +484,37 @@ class AbstractSpatialImageAnalysis(object):
                 for key in lareas:
                     areas[key] = areas.get(key, 0.0) + lareas[key]
         return areas
+
+    def _wall_areas_vectorised(self, neighbors, real):
+        """``wall_areas`` for the usual input (int labels, no label twice in a list) in one table lookup: the same
+        keys in the same order and, element by element, the same left fold over the six directions as the per-label
+        loop (SIA:947-956, 986-992), so the floats are bit-identical.  None: take the loop."""
+        src, dst = [], []
+        for label_id, lneighbors in neighbors.items():
+            if not isinstance(lneighbors, list):
+                return None
+            neigh = [n for n in lneighbors if n > label_id]
+            if len(set(neigh)) != len(neigh):
+                return None
+            src.extend([label_id] * len(neigh))
+            dst.extend(neigh)
+        if not src:
+            return {}
+        try:
+            a = np.asarray(src, dtype=np.int64)
+            b = np.asarray(dst, dtype=np.int64)
+        except (TypeError, ValueError, OverflowError):
+            return None
+        if a.shape != b.shape or a.ndim != 1:
+            return None
+        t = self._tables()
+        rows = t.find_pairs(a, b)
+        counts = np.where(rows[:, None] >= 0, t.faces[np.maximum(rows, 0)], 0)     # label_id < n: slots as stored
+        resolution = self.get_voxel_face_surface()
+        total = np.zeros(len(src))
+        for k in range(6):
+            total = total + (counts[:, k] * resolution[k // 2] if real else counts[:, k])
+        return dict(zip(zip(src, dst), total.tolist()))
 
     # ------------------------------------------------------------------------------------------- layers
     def cell_first_layer(self, filter_by_area=True, minimal_external_area=10, real_area=True):
