@@ -163,6 +163,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->diag_host) cudaFreeHost(ctx->diag_host);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
