@@ -72,7 +72,20 @@ static int run_case(int nf, int nm, int ns, int nlabels, int mode, unsigned seed
             LabelMap gotL, refL;
             PairMap gotP, refP;
             ++*nblocks;
-            if (!block_features(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&gotL}, OnPair{&gotP})) { ++*noverflow; continue; }
+            if (!block_features(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&gotL}, OnPair{&gotP})) {
+                LabelMap l2; PairMap p2;
+                if (block_features_reg<BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2})) ++bad;
+                ++*noverflow;
+                continue;
+            }
+            {
+                // the register-resident form must agree with the reference form, also with a smaller slot budget
+                LabelMap l2, l3; PairMap p2, p3;
+                const bool ok4 = block_features_reg<BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2});
+                const bool ok3 = block_features_reg<3>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l3}, OnPair{&p3});
+                if (!ok4 || l2 != gotL || p2 != gotP) ++bad;
+                if (ok3 && (l3 != gotL || p3 != gotP)) ++bad;
+            }
             for (int ds = 0; ds < nvs; ++ds) for (int dm = 0; dm < nvm; ++dm) for (int df = 0; df < nvf; ++df) {
                 const int f = fs * SEG + df, m = m0 + dm, s = s0 + ds;
                 const uint32_t a = at(f, m, s);
