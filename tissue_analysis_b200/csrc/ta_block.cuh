@@ -88,6 +88,20 @@ TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) {
     dil[1] = own[2] | cross[1] | cross[3];
 }
 
+// Move a label's sums from coordinates local to a block (or brick) to coordinates shifted by (F, M, S): the algebra of
+// the kernel's label_to_global, in 32 bits (a brick: coordinates < 128, at most 16 384 voxels, sums < 2^32).
+TA_HD void block_shift_moments(uint32_t v[16], uint32_t F, uint32_t M, uint32_t S) {
+    const uint32_t n = v[0], sf = v[1], sm = v[2], ss = v[3];
+    v[4] += 2u * F * sf + n * F * F;
+    v[5] += F * sm + M * sf + n * F * M;
+    v[6] += F * ss + S * sf + n * F * S;
+    v[7] += 2u * M * sm + n * M * M;
+    v[8] += M * ss + S * sm + n * M * S;
+    v[9] += 2u * S * ss + n * S * S;
+    v[1] += n * F; v[2] += n * M; v[3] += n * S;
+    v[10] += F; v[11] += M; v[12] += S; v[13] += F; v[14] += M; v[15] += S;
+}
+
 // One block.  tile: the brick tile of the scan kernel (labels, clamped halo); (fs, m0, s0): the block's segment, first
 // row and first plane inside the brick; nvf / nvm / nvs: how many of its 8 x 4 x 2 voxels per axis lie inside the volume
 // and the owned plane range (ragged edges).
