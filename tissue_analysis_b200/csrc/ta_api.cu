@@ -13,6 +13,9 @@
 #include "ta_common.cuh"
 #include "ta_kernels.cuh"
 #include "ta_scan.cuh"
+#ifdef TA_WITH_BLOCK_KERNEL           // experimental, not part of the product build: TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL
+#include "ta_scan_block.cuh"
+#endif
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -348,6 +351,24 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
+#ifdef TA_WITH_BLOCK_KERNEL
+    if ((P.flags & 0x4000u) && ctx->elem == 2) {
+        // experimental block-bitmask kernel (ta_scan_block.cuh): only on request, configured on first use so that the
+        // product path never depends on it
+        static bool configured = false;
+        if (!configured) {
+            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ta::scan_block_smem_bytes()));
+            configured = true;
+        }
+        ta::scan_block_kernel<<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
+#else
+    if (P.flags & 0x4000u) return fail(ctx, TA_ERR_BAD_ARG, "the block kernel is not compiled in (-DTA_WITH_BLOCK_KERNEL)");
+#endif
     const size_t smem = ctx->elem == 2 ? ta::scan_smem_bytes<uint16_t>() : ta::scan_smem_bytes<uint32_t>();
     scan_kernel_variant(ctx->elem, onehot, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
     ctx->launches++;
@@ -450,9 +471,10 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         P.phase_cycles = ctx->phase_cycles;
     }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
-    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" for every brick
+    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" / "block" for every brick
         if (!strcmp(pp, "voxel")) P.flags |= 0x800u;
         else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
+        else if (!strcmp(pp, "block")) P.flags |= 0x4000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {
