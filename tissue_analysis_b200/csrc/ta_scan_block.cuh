@@ -6,9 +6,9 @@
 // 8 x 4 x 2 block per thread, results added to the per-brick shared tables with plain atomics, no warp merges yet.  It
 // compiles for sm_100a but was written after the round's GPU budget was spent: it has NOT run on a GPU, and it is NOT
 // part of the product build (ta_api.cu includes it only under -DTA_WITH_BLOCK_KERNEL; a product library answers flag
-// 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: compiling it takes minutes (the fully unrolled label slots)
-// and ptxas spills ~140 bytes at 80 registers inside the kernel although the block function alone fits -- the first
-// things to fix.  Plan and cost model: DESIGN.md section 6.
+// 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: the table updates and the per-voxel fallback are out of
+// line (inlined, the kernel took minutes to compile), so the 16 moments of a label travel through local memory, and
+// ptxas spills ~150 bytes at 80 registers -- the first things to fix.  Plan and cost model: DESIGN.md section 6.
 //
 // First run (needs a B200):
 //   TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$PWD/build/libtissue_b200_block.so bash tissue_analysis_b200/csrc/build.sh
@@ -26,7 +26,7 @@ constexpr size_t scan_block_smem_bytes() {
 
 // per-voxel fallback for one voxel of a block whose window holds more labels than slots: moments of the voxel and its
 // pairs by a register de-duplication of the 18 neighbours (the logic of phase D2 of the product kernel)
-__device__ __forceinline__ void block_fallback_voxel(const BrickShared<uint16_t>& sh, const LabelTable& lt,
+__device__ __noinline__ void block_fallback_voxel(const BrickShared<uint16_t>& sh, const LabelTable& lt,
                                                      const PairTable& pt, const unsigned short* p, uint32_t f, uint32_t m,
                                                      uint32_t s, u64 gF0, u64 gM0, u64 gS0, bool do_mom, bool do_p6,
                                                      bool do_w18) {
