@@ -36,11 +36,12 @@ struct OnPair {
     }
 };
 
+template <typename T>
 static int run_case(int nf, int nm, int ns, int nlabels, int mode, unsigned seed, long* nblocks, long* noverflow) {
-    constexpr int SEG = 8, ROWE = ROWV * SEG;
+    constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG;
     std::mt19937 rng(seed);
     std::vector<uint32_t> vol((size_t)nf * nm * ns), names(nlabels);
-    for (auto& n : names) n = rng() % 65535u;
+    for (auto& n : names) n = sizeof(T) == 2 ? rng() % 65535u : rng() % 0xFFFFFFF0u;
     if (mode == 0) {
         for (auto& v : vol) v = names[rng() % nlabels];
     } else {
@@ -60,10 +61,10 @@ static int run_case(int nf, int nm, int ns, int nlabels, int mode, unsigned seed
         return vol[((size_t)s * nm + m) * nf + f];
     };
     std::vector<uint4> tile(TILE_SEGS);
-    unsigned short* tl = reinterpret_cast<unsigned short*>(tile.data());
+    T* tl = reinterpret_cast<T*>(tile.data());
     for (int r = 0; r < TILE_ROWS; ++r) {
         const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
-        for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (unsigned short)at(e - SEG, m, s);
+        for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (T)at(e - SEG, m, s);
     }
     int bad = 0;
     for (int s0 = 0; s0 < std::min(ns, BS); s0 += BLK_S) for (int m0 = 0; m0 < std::min(nm, BM); m0 += BLK_M)
@@ -72,17 +73,17 @@ static int run_case(int nf, int nm, int ns, int nlabels, int mode, unsigned seed
             LabelMap gotL, refL;
             PairMap gotP, refP;
             ++*nblocks;
-            if (!block_features(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&gotL}, OnPair{&gotP})) {
+            if (!block_features<T>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&gotL}, OnPair{&gotP})) {
                 LabelMap l2; PairMap p2;
-                if (block_features_reg<BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2})) ++bad;
+                if (block_features_reg<T, BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2})) ++bad;
                 ++*noverflow;
                 continue;
             }
             {
                 // the register-resident form must agree with the reference form, also with a smaller slot budget
                 LabelMap l2, l3; PairMap p2, p3;
-                const bool ok4 = block_features_reg<BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2});
-                const bool ok3 = block_features_reg<3>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l3}, OnPair{&p3});
+                const bool ok4 = block_features_reg<T, BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l2}, OnPair{&p2});
+                const bool ok3 = block_features_reg<T, 3>(tile.data(), fs, m0, s0, nvf, nvm, nvs, OnLabel{&l3}, OnPair{&p3});
                 if (!ok4 || l2 != gotL || p2 != gotP) ++bad;
                 if (ok3 && (l3 != gotL || p3 != gotP)) ++bad;
             }
@@ -129,11 +130,14 @@ int main(int argc, char** argv) {
     std::mt19937 rng(seed0);
     long bad = 0, nblocks = 0, noverflow = 0;
     for (int c = 0; c < 300; ++c) {
-        int nf = 1 + rng() % (NFS * 8), nm = 1 + rng() % BM, ns = 1 + rng() % BS;
-        if (c % 5 == 0) { nf = NFS * 8; nm = BM; ns = BS; }
+        const bool wide = (c & 1) != 0;                         // uint32 labels: 4-voxel segments, 64-voxel rows
+        const int maxf = NFS * (wide ? 4 : 8);
+        int nf = 1 + rng() % maxf, nm = 1 + rng() % BM, ns = 1 + rng() % BS;
+        if (c % 5 == 0) { nf = maxf; nm = BM; ns = BS; }
         const int nl = 1 + rng() % (c % 4 == 0 ? 30 : 9);
         const int mode = (c % 3 == 0) ? 0 : 1;
-        bad += run_case(nf, nm, ns, nl, mode, rng(), &nblocks, &noverflow);
+        bad += wide ? run_case<uint32_t>(nf, nm, ns, nl, mode, rng(), &nblocks, &noverflow)
+                    : run_case<uint16_t>(nf, nm, ns, nl, mode, rng(), &nblocks, &noverflow);
     }
     printf("block_host_check: %ld blocks, %ld with more than %d labels in the window (skipped), %ld mismatching blocks\n",
            nblocks, noverflow, BLK_MAXLAB, bad);

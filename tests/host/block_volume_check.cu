@@ -84,13 +84,14 @@ struct OnPair {
     }
 };
 
+template <typename T>
 static int run_case(int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode, unsigned seed,
                     long* nover) {
-    constexpr int SEG = 8, ROWE = ROWV * SEG, BF = NFS * SEG;
+    constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG, BF = NFS * SEG;
     std::mt19937 rng(seed);
     Vol V{nf, nm, nbuf, std::vector<uint32_t>((size_t)nf * nm * nbuf)};
     std::vector<uint32_t> names(nlabels);
-    for (auto& n : names) n = 1 + rng() % 65000u;
+    for (auto& n : names) n = 1 + (sizeof(T) == 2 ? rng() % 65000u : rng() % 0xFFFFFF00u);
     if (mode == 0) {
         for (auto& v : V.d) v = names[rng() % nlabels];
     } else {
@@ -109,18 +110,18 @@ static int run_case(int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_
     for (int s = own_lo; s < own_hi; ++s) for (int m = 0; m < nm; ++m) for (int f = 0; f < nf; ++f)
         add_voxel(V, f, m, s, slow_offset, refL, refP);
     std::vector<uint4> tile(TILE_SEGS);
-    unsigned short* tl = reinterpret_cast<unsigned short*>(tile.data());
+    T* tl = reinterpret_cast<T*>(tile.data());
     for (int S0 = own_lo; S0 < own_hi; S0 += BS) for (int M0 = 0; M0 < nm; M0 += BM) for (int F0 = 0; F0 < nf; F0 += BF) {
         for (int r = 0; r < TILE_ROWS; ++r) {
             const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
-            for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (unsigned short)V.at(F0 + e - SEG, M0 + m, S0 + s);
+            for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (T)V.at(F0 + e - SEG, M0 + m, S0 + s);
         }
         for (int s0 = 0; s0 < BS && S0 + s0 < own_hi; s0 += BLK_S) for (int m0 = 0; m0 < BM && M0 + m0 < nm; m0 += BLK_M)
             for (int fs = 0; fs < NFS && F0 + fs * SEG < nf; ++fs) {
                 const int nvf = std::min(SEG, nf - F0 - fs * SEG), nvm = std::min(BLK_M, nm - M0 - m0),
                           nvs = std::min(BLK_S, own_hi - S0 - s0);
                 OnLabel ol{&gotL, (uint32_t)(fs * SEG), (uint32_t)m0, (uint32_t)s0, (u64)F0, (u64)M0, (u64)(S0 + slow_offset)};
-                if (!block_features_reg<BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, ol, OnPair{&gotP})) {
+                if (!block_features_reg<T, BLK_MAXLAB>(tile.data(), fs, m0, s0, nvf, nvm, nvs, ol, OnPair{&gotP})) {
                     ++*nover;       // more labels than slots: the per-voxel path
                     for (int ds = 0; ds < nvs; ++ds) for (int dm = 0; dm < nvm; ++dm) for (int df = 0; df < nvf; ++df)
                         add_voxel(V, F0 + fs * SEG + df, M0 + m0 + dm, S0 + s0 + ds, slow_offset, gotL, gotP);
@@ -143,7 +144,9 @@ int main(int argc, char** argv) {
         const int nf = 1 + rng() % 300, nm = 1 + rng() % 40, nbuf = 1 + rng() % 22;
         int lo = 0, hi = nbuf; long off = 0;
         if (c % 3 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }     // a slab with halo planes
-        bad += run_case(nf, nm, nbuf, lo, hi, off, 1 + rng() % (c % 4 == 0 ? 40 : 12), c % 3 == 0 ? 0 : 1, rng(), &nover);
+        const int nl = 1 + rng() % (c % 4 == 0 ? 40 : 12), mode = c % 3 == 0 ? 0 : 1;
+        bad += (c & 1) ? run_case<uint32_t>(nf, nm, nbuf, lo, hi, off, nl, mode, rng(), &nover)
+                       : run_case<uint16_t>(nf, nm, nbuf, lo, hi, off, nl, mode, rng(), &nover);
     }
     printf("block_volume_check: 60 volumes, %ld blocks on the per-voxel fallback, %d mismatching volumes\n", nover, bad);
     return bad ? 1 : 0;

@@ -14,8 +14,8 @@
 //   pairs    wall18(i -> j) = popcount(centre_i & dilate18(mask_j)); faces = popcount(centre_i & shifted mask_j).
 //
 // No atomics, no hash, no worklist inside the block.  Everything here is host-compilable (TA_HD);
-// tests/host/block_host_check.cu runs it over whole tiles against a brute-force count.  Label width: uint16 (a block
-// row is one 16-byte segment); the uint32 form needs a 4-voxel-wide block and is not written yet.
+// tests/host/block_host_check.cu runs it over whole tiles against a brute-force count.  Both label widths: a block row is
+// one 16-byte segment, i.e. 8 x 4 x 2 voxels for uint16 (window planes of 60 bits) and 4 x 4 x 2 for uint32 (36 bits).
 #pragma once
 #include "ta_scan.cuh"
 
@@ -23,8 +23,13 @@ namespace ta {
 
 constexpr int BLK_M = 4, BLK_S = 2;            // block rows and planes; its f extent is one segment (SEG voxels)
 constexpr int BLK_MAXLAB = 4;
-constexpr int BLK_ROWBITS = 10;                // SEG + 2 window positions per row (uint16)
-constexpr u64 BLK_PLANE_ALL = (1ull << 60) - 1ull;
+// per label width: a window row has SEG + 2 positions (10 for uint16, 6 for uint32), a window plane BLK_M + 2 rows
+template <typename T> struct Blk {
+    static constexpr int SEG = Vox<T>::SEG;
+    static constexpr int ROWBITS = SEG + 2;
+    static constexpr u64 PLANE_ALL = (1ull << (ROWBITS * (BLK_M + 2))) - 1ull;
+    static constexpr uint32_t LANES = (1u << SEG) - 1u;
+};
 
 TA_HD int ta_popc64(u64 x) { return ta_popc((uint32_t)x) + ta_popc((uint32_t)(x >> 32)); }
 TA_HD int ta_ffs64(u64 x) {                    // 1-based index of the lowest set bit, 0 if none
@@ -34,9 +39,10 @@ TA_HD int ta_ffs64(u64 x) {                    // 1-based index of the lowest se
     return hi ? 32 + ta_ffs(hi) : 0;
 }
 
-// 10-bit mask of one window row (vector index t of its segment in the tile): bit 0 = the lane left of the segment,
-// bits 1..8 = the segment's lanes, bit 9 = the lane right of it; set where the voxel equals label L.
-TA_HD uint32_t block_row_mask(const uint4* tile, int t, uint32_t L) {
+// Mask of one window row (vector index t of its segment in the tile): bit 0 = the lane left of the segment, bits
+// 1 .. SEG = the segment's lanes, bit SEG + 1 = the lane right of it; set where the voxel equals label L.
+template <typename T> TA_HD uint32_t block_row_mask(const uint4* tile, int t, uint32_t L);
+template <> TA_HD uint32_t block_row_mask<uint16_t>(const uint4* tile, int t, uint32_t L) {
     const uint4 c = tile[t];
     const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
     const uint32_t pat = L * 0x00010001u, one = 0x00010001u;
@@ -46,9 +52,16 @@ TA_HD uint32_t block_row_mask(const uint4* tile, int t, uint32_t L) {
     const uint32_t neq = (tt & 0x55u) | ((tt >> 15) & 0xAAu);
     return ((~neq & 0xFFu) << 1) | ((uint32_t)e[-1] == L ? 1u : 0u) | ((uint32_t)e[8] == L ? 0x200u : 0u);
 }
+template <> TA_HD uint32_t block_row_mask<uint32_t>(const uint4* tile, int t, uint32_t L) {
+    const uint4 c = tile[t];
+    const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
+    return (e[-1] == L ? 1u : 0u) | (c.x == L ? 2u : 0u) | (c.y == L ? 4u : 0u) | (c.z == L ? 8u : 0u) |
+           (c.w == L ? 16u : 0u) | (e[4] == L ? 32u : 0u);
+}
 
 // Window masks of label L: plane p = tile plane (s0 - 1 + p), rows (m0 - 1 .. m0 + 4).  `t0` = vector index of the
 // window's first row (m0 - 1, s0 - 1) at the block's segment.
+template <typename T>
 TA_HD void block_label_masks(const uint4* tile, int t0, uint32_t L, u64 mask[4]) {
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
@@ -57,7 +70,7 @@ TA_HD void block_label_masks(const uint4* tile, int t0, uint32_t L, u64 mask[4])
         // register budget of the label slots (fully unrolled, ptxas hoists all 24 row loads and spills)
 #pragma unroll 2
         for (int r = 0; r < BLK_M + 2; ++r)
-            m |= (u64)block_row_mask(tile, t0 + p * PLANEV + r * ROWV, L) << (BLK_ROWBITS * r);
+            m |= (u64)block_row_mask<T>(tile, t0 + p * PLANEV + r * ROWV, L) << (Blk<T>::ROWBITS * r);
         mask[p] = m;
     }
 }
@@ -73,8 +86,10 @@ TA_HD uint32_t block_byte_moments(uint32_t b) {
 }
 
 // 18-neighbourhood dilation of a label's window masks, for the two centre planes (p = 1, 2).  Bits outside the centre
-// (halo columns / rows, bits >= 60) are not meaningful: the callers AND with centre masks.
+// (halo columns / rows, bits beyond the plane) are not meaningful: the callers AND with centre masks.
+template <typename T>
 TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) {
+    constexpr int BLK_ROWBITS = Blk<T>::ROWBITS;
     u64 own[4], cross[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -110,11 +125,13 @@ TA_HD void block_shift_moments(uint32_t v[16], uint32_t F, uint32_t M, uint32_t 
 //   on_pair(La, Lb, w18, ff, fm, fs): seen from the voxels of La: wall18 voxels towards Lb and +f / +m / +s faces whose
 //                       lower voxel is La and upper voxel Lb.
 // false: more than BLK_MAXLAB labels in the window (nothing was emitted).
-template <typename OnLabel, typename OnPair>
+template <typename T, typename OnLabel, typename OnPair>
 TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
                           OnPair&& on_pair) {
+    constexpr int SEG = Blk<T>::SEG, BLK_ROWBITS = Blk<T>::ROWBITS;
+    constexpr u64 BLK_PLANE_ALL = Blk<T>::PLANE_ALL;
     const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);          // tile row (m0 - 1, s0 - 1): the tile itself has a halo
-    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+    const T* tl = reinterpret_cast<const T*>(tile);
     uint32_t lab[BLK_MAXLAB];
     u64 mask[BLK_MAXLAB][4];
     u64 rest[4] = {BLK_PLANE_ALL, BLK_PLANE_ALL, BLK_PLANE_ALL, BLK_PLANE_ALL};
@@ -126,9 +143,9 @@ TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, in
         if (k == BLK_MAXLAB) return false;
         const int bit = ta_ffs64(rest[p]) - 1, r = bit / BLK_ROWBITS, x = bit % BLK_ROWBITS;
         // window position (x, r, p) = tile element of row t0 + p * PLANEV + r * ROWV, lane x - 1
-        const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * 8 + (x - 1)];
+        const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
         lab[k] = L;
-        block_label_masks(tile, t0, L, mask[k]);
+        block_label_masks<T>(tile, t0, L, mask[k]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) rest[q] &= ~mask[k][q];
         ++k;
@@ -142,7 +159,7 @@ TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, in
     for (int i = 0; i < k; ++i) {
         cen[i][0] = mask[i][1] & cvp[0];
         cen[i][1] = mask[i][2] & cvp[1];
-        block_dilate18(mask[i], dil[i]);
+        block_dilate18<T>(mask[i], dil[i]);
     }
     for (int i = 0; i < k; ++i) {
         if (!(cen[i][0] | cen[i][1])) continue;
@@ -151,7 +168,7 @@ TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, in
         uint32_t colmask = 0u;
         for (int p = 0; p < 2; ++p)
             for (int r = 0; r < BLK_M; ++r) {
-                const uint32_t b = (uint32_t)(cen[i][p] >> (BLK_ROWBITS * (r + 1) + 1)) & 0xFFu;
+                const uint32_t b = (uint32_t)(cen[i][p] >> (BLK_ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
                 if (!b) continue;
                 const uint32_t t = block_byte_moments(b), n = t & 0xFFu, sx = (t >> 8) & 0xFFu, sxx = t >> 16;
                 const uint32_t m = (uint32_t)r, s = (uint32_t)p;
@@ -185,11 +202,13 @@ TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, in
 // Per slot: the label, planes 1 .. 3 of its window mask (plane 0 is folded into the dilation at once) and the dilation
 // of the two centre planes: five 64-bit words.  Same callbacks and results as block_features; this is the form a kernel
 // would unroll into slot-wise warp merges.
-template <int MAXLAB, typename OnLabel, typename OnPair>
+template <typename T, int MAXLAB, typename OnLabel, typename OnPair>
 TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
                               OnPair&& on_pair) {
+    constexpr int SEG = Blk<T>::SEG, BLK_ROWBITS = Blk<T>::ROWBITS;
+    constexpr u64 BLK_PLANE_ALL = Blk<T>::PLANE_ALL;
     const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
-    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+    const T* tl = reinterpret_cast<const T*>(tile);
     uint32_t lab[MAXLAB];
     u64 M1[MAXLAB], M2[MAXLAB], M3[MAXLAB], D0[MAXLAB], D1[MAXLAB];
     u64 r0 = BLK_PLANE_ALL, r1 = BLK_PLANE_ALL, r2 = BLK_PLANE_ALL, r3 = BLK_PLANE_ALL;
@@ -202,12 +221,12 @@ TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf
             const int p = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
             const u64 rp = r0 ? r0 : r1 ? r1 : r2 ? r2 : r3;
             const int bit = ta_ffs64(rp) - 1, r = bit / BLK_ROWBITS, x = bit % BLK_ROWBITS;
-            const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * 8 + (x - 1)];
+            const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
             u64 m[4];
-            block_label_masks(tile, t0, L, m);
+            block_label_masks<T>(tile, t0, L, m);
             r0 &= ~m[0]; r1 &= ~m[1]; r2 &= ~m[2]; r3 &= ~m[3];
             u64 d[2];
-            block_dilate18(m, d);
+            block_dilate18<T>(m, d);
             lab[sl] = L; M1[sl] = m[1]; M2[sl] = m[2]; M3[sl] = m[3]; D0[sl] = d[0]; D1[sl] = d[1];
             k = sl + 1;
         }
@@ -227,7 +246,7 @@ TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf
         for (int p = 0; p < 2; ++p)
 #pragma unroll
             for (int r = 0; r < BLK_M; ++r) {
-                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (BLK_ROWBITS * (r + 1) + 1)) & 0xFFu;
+                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (BLK_ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
                 const uint32_t t = block_byte_moments(b), n = t & 0xFFu, sx = (t >> 8) & 0xFFu, sxx = t >> 16;
                 n_ += n; sf += sx; sm += r * n; ss += p * n; sff += sxx; sfm += r * sx; sfs += p * sx; smm += r * r * n;
                 colmask |= b;
@@ -236,7 +255,7 @@ TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf
         const uint32_t n1 = (uint32_t)ta_popc64(c1);                 // voxels in the upper plane: s = 1
         uint32_t sm1 = 0u;                                          // sum of m over the upper plane
 #pragma unroll
-        for (int r = 0; r < BLK_M; ++r) sm1 += r * (uint32_t)ta_popc((uint32_t)(c1 >> (BLK_ROWBITS * (r + 1) + 1)) & 0xFFu);
+        for (int r = 0; r < BLK_M; ++r) sm1 += r * (uint32_t)ta_popc((uint32_t)(c1 >> (BLK_ROWBITS * (r + 1) + 1)) & Blk<T>::LANES);
         const uint32_t mrows = (rows | (rows >> BLK_M)) & ((1u << BLK_M) - 1u);
         uint32_t v[16];
         v[0] = n_; v[1] = sf; v[2] = sm; v[3] = ss; v[4] = sff; v[5] = sfm; v[6] = sfs; v[7] = smm; v[8] = sm1; v[9] = n1;

@@ -231,7 +231,7 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
                       nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
             if (nvf > 0 && nvm > 0 && nvs > 0) {
                 const uint32_t bF = (uint32_t)(fs * SEG), bM = (uint32_t)m0, bS = (uint32_t)s0;
-                const bool ok = block_features_reg<BLK_MAXLAB>(
+                const bool ok = block_features_reg<T, BLK_MAXLAB>(
                     sh.tile, fs, m0, s0, nvf, nvm, nvs,
                     [&](uint32_t L, const uint32_t vin[16]) {
                         if (do_mom) block_emit_label(sh, lt, pt.status, L, vin, bF, bM, bS, gF0, gM0, gS0);
