@@ -5,7 +5,9 @@
 // voxel itself, which reproduces the reference's "the image border contributes nothing" rule).
 //
 // Phases per brick (irregular work is compacted into worklists first so whole warps stay busy):
-//   A  stage brick + halo: 16-byte cp.async copies, all in flight at once -> shared tile.
+//   A  stage brick + halo: one TMA box copy (cp.async.bulk.tensor.3d, completion on an mbarrier) issued by thread 0;
+//      bricks on a face of the buffer re-clamp the zero-filled out-of-bounds elements in shared memory.  Rows that are
+//      not 16-byte multiples (and TA_NO_TMA=1) take 16-byte cp.async copies / scalar loads instead.
 //   B  per row-segment uniformity code: the label if the SEG+2 voxels (segment + f-halo) are equal.  A tile that is
 //      one label altogether (background, inside of a large cell) is finished here with closed-form moments.
 //   C1 march: thread (fseg, m) walks s.  Moments go to three bit-packed register slots per thread (a column rarely
