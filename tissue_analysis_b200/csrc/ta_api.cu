@@ -357,11 +357,16 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
         // product path never depends on it
         static bool configured = false;
         if (!configured) {
-            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ta::scan_block_smem_bytes()));
+            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ta::scan_block_smem_bytes()));
             configured = true;
         }
-        ta::scan_block_kernel<<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
+        if (P.flags & 0x8000u)
+            ta::scan_block_kernel<false><<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
+        else
+            ta::scan_block_kernel<true><<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
         ctx->launches++;
         TA_CUDA(cudaGetLastError());
         return TA_OK;
@@ -475,6 +480,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         if (!strcmp(pp, "voxel")) P.flags |= 0x800u;
         else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
         else if (!strcmp(pp, "block")) P.flags |= 0x4000u;
+        else if (!strcmp(pp, "block_simple")) P.flags |= 0x4000u | 0x8000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {

@@ -200,88 +200,117 @@ TA_HD bool block_features(const uint4* tile, int fs, int m0, int s0, int nvf, in
 // The same block in register-resident form: every array index is a compile-time constant after unrolling (label slots
 // 0 .. MAXLAB - 1, a slot is used iff its index is below the number of labels found), so nothing lives in local memory.
 // Per slot: the label, planes 1 .. 3 of its window mask (plane 0 is folded into the dilation at once) and the dilation
-// of the two centre planes: five 64-bit words.  Same callbacks and results as block_features; this is the form a kernel
-// would unroll into slot-wise warp merges.
-template <typename T, int MAXLAB, typename OnLabel, typename OnPair>
-TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
-                              OnPair&& on_pair) {
-    constexpr int SEG = Blk<T>::SEG, BLK_ROWBITS = Blk<T>::ROWBITS;
-    constexpr u64 BLK_PLANE_ALL = Blk<T>::PLANE_ALL;
-    const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
-    const T* tl = reinterpret_cast<const T*>(tile);
+// of the two centre planes: five 64-bit words.  A kernel calls discover() once and then label_moments(i) /
+// pair_counts(i, j) from loops with the same trip count in every lane (empty slots answer false), so that the warp
+// merges around them stay full-mask.
+template <typename T, int MAXLAB> struct BlockSlots {
     uint32_t lab[MAXLAB];
     u64 M1[MAXLAB], M2[MAXLAB], M3[MAXLAB], D0[MAXLAB], D1[MAXLAB];
-    u64 r0 = BLK_PLANE_ALL, r1 = BLK_PLANE_ALL, r2 = BLK_PLANE_ALL, r3 = BLK_PLANE_ALL;
-    int k = 0;
+    u64 cv0, cv1;             // centre voxels inside the volume, planes 1 and 2 of the window
+    int k;                    // labels found
+
+    TA_HD void clear() {                              // every slot empty
+        k = 0; cv0 = cv1 = 0ull;
 #pragma unroll
-    for (int sl = 0; sl < MAXLAB; ++sl) {
-        lab[sl] = 0u; M1[sl] = M2[sl] = M3[sl] = D0[sl] = D1[sl] = 0ull;
-        if (r0 | r1 | r2 | r3) {
-            // first window position that no label found so far covers
-            const int p = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
-            const u64 rp = r0 ? r0 : r1 ? r1 : r2 ? r2 : r3;
-            const int bit = ta_ffs64(rp) - 1, r = bit / BLK_ROWBITS, x = bit % BLK_ROWBITS;
-            const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
-            u64 m[4];
-            block_label_masks<T>(tile, t0, L, m);
-            r0 &= ~m[0]; r1 &= ~m[1]; r2 &= ~m[2]; r3 &= ~m[3];
-            u64 d[2];
-            block_dilate18<T>(m, d);
-            lab[sl] = L; M1[sl] = m[1]; M2[sl] = m[2]; M3[sl] = m[3]; D0[sl] = d[0]; D1[sl] = d[1];
-            k = sl + 1;
-        }
+        for (int sl = 0; sl < MAXLAB; ++sl) { lab[sl] = 0u; M1[sl] = M2[sl] = M3[sl] = D0[sl] = D1[sl] = 0ull; }
     }
-    if (r0 | r1 | r2 | r3) return false;
-    u64 cv = 0ull;
+
+    // false: more than MAXLAB labels in the window
+    TA_HD bool discover(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs) {
+        constexpr int SEG = Blk<T>::SEG, ROWBITS = Blk<T>::ROWBITS;
+        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
+        const T* tl = reinterpret_cast<const T*>(tile);
+        u64 r0 = ALL, r1 = ALL, r2 = ALL, r3 = ALL;
+        k = 0;
 #pragma unroll
-    for (int r = 1; r <= BLK_M; ++r)
-        if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (BLK_ROWBITS * r);
-    const u64 cv0 = nvs >= 1 ? cv : 0ull, cv1 = nvs >= 2 ? cv : 0ull;
+        for (int sl = 0; sl < MAXLAB; ++sl) {
+            lab[sl] = 0u; M1[sl] = M2[sl] = M3[sl] = D0[sl] = D1[sl] = 0ull;
+            if (r0 | r1 | r2 | r3) {
+                // first window position that no label found so far covers
+                const int p = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
+                const u64 rp = r0 ? r0 : r1 ? r1 : r2 ? r2 : r3;
+                const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
+                const uint32_t L = tl[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
+                u64 m[4];
+                block_label_masks<T>(tile, t0, L, m);
+                r0 &= ~m[0]; r1 &= ~m[1]; r2 &= ~m[2]; r3 &= ~m[3];
+                u64 d[2];
+                block_dilate18<T>(m, d);
+                lab[sl] = L; M1[sl] = m[1]; M2[sl] = m[2]; M3[sl] = m[3]; D0[sl] = d[0]; D1[sl] = d[1];
+                k = sl + 1;
+            }
+        }
+        u64 cv = 0ull;
 #pragma unroll
-    for (int i = 0; i < MAXLAB; ++i) {
+        for (int r = 1; r <= BLK_M; ++r)
+            if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (ROWBITS * r);
+        cv0 = nvs >= 1 ? cv : 0ull;
+        cv1 = nvs >= 2 ? cv : 0ull;
+        return !(r0 | r1 | r2 | r3);
+    }
+
+    // moments and box of slot i over its centre voxels, block-local coordinates (field order of the per-brick label
+    // table); false: the slot is empty or has no centre voxel
+    TA_HD bool label_moments(int i, uint32_t v[16]) const {
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        if (i >= k) return false;
         const u64 c0 = M1[i] & cv0, c1 = M2[i] & cv1;
-        if (i >= k || !(c0 | c1)) continue;
-        uint32_t n_ = 0u, sf = 0u, sm = 0u, ss = 0u, sff = 0u, sfm = 0u, sfs = 0u, smm = 0u, colmask = 0u, rows = 0u;
+        if (!(c0 | c1)) return false;
+        uint32_t n_ = 0u, sf = 0u, sm = 0u, ss = 0u, sff = 0u, sfm = 0u, sfs = 0u, smm = 0u, sm1 = 0u, colmask = 0u, rows = 0u;
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
             for (int r = 0; r < BLK_M; ++r) {
-                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (BLK_ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
+                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
                 const uint32_t t = block_byte_moments(b), n = t & 0xFFu, sx = (t >> 8) & 0xFFu, sxx = t >> 16;
                 n_ += n; sf += sx; sm += r * n; ss += p * n; sff += sxx; sfm += r * sx; sfs += p * sx; smm += r * r * n;
+                sm1 += p * r * n;
                 colmask |= b;
                 rows |= b ? (1u << (p * BLK_M + r)) : 0u;
             }
-        const uint32_t n1 = (uint32_t)ta_popc64(c1);                 // voxels in the upper plane: s = 1
-        uint32_t sm1 = 0u;                                          // sum of m over the upper plane
-#pragma unroll
-        for (int r = 0; r < BLK_M; ++r) sm1 += r * (uint32_t)ta_popc((uint32_t)(c1 >> (BLK_ROWBITS * (r + 1) + 1)) & Blk<T>::LANES);
         const uint32_t mrows = (rows | (rows >> BLK_M)) & ((1u << BLK_M) - 1u);
+        v[0] = n_; v[1] = sf; v[2] = sm; v[3] = ss; v[4] = sff; v[5] = sfm; v[6] = sfs; v[7] = smm;
+        v[8] = sm1;                  // sum m * s: s is 0 or 1
+        v[9] = ss;                   // sum s * s = sum s
+        v[10] = (uint32_t)ta_ffs(colmask) - 1u; v[11] = (uint32_t)ta_ffs(mrows) - 1u; v[12] = (rows & ((1u << BLK_M) - 1u)) ? 0u : 1u;
+        uint32_t ftop = Blk<T>::SEG - 1, mtop = BLK_M - 1;
+        while (!((colmask >> ftop) & 1u)) --ftop;
+        while (!((mrows >> mtop) & 1u)) --mtop;
+        v[13] = ftop; v[14] = mtop; v[15] = (rows >> BLK_M) ? 1u : 0u;
+        return true;
+    }
+
+    // seen from the voxels of slot i towards slot j: wall18 voxels and +f / +m / +s faces whose lower voxel is i and upper
+    // voxel j; false: nothing (or an empty slot)
+    TA_HD bool pair_counts(int i, int j, uint32_t& w18, uint32_t& ff, uint32_t& fm, uint32_t& fsl) const {
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        w18 = ff = fm = fsl = 0u;
+        if (i >= k || j >= k || i == j) return false;
+        const u64 c0 = M1[i] & cv0, c1 = M2[i] & cv1;
+        w18 = ta_popc64(c0 & D0[j]) + ta_popc64(c1 & D1[j]);
+        ff = ta_popc64(c0 & (M1[j] >> 1)) + ta_popc64(c1 & (M2[j] >> 1));
+        fm = ta_popc64(c0 & (M1[j] >> ROWBITS)) + ta_popc64(c1 & (M2[j] >> ROWBITS));
+        fsl = ta_popc64(c0 & M2[j]) + ta_popc64(c1 & M3[j]);
+        return (w18 | ff | fm | fsl) != 0u;
+    }
+};
+
+// block_features on top of BlockSlots: same callbacks and results as the reference form above.
+template <typename T, int MAXLAB, typename OnLabel, typename OnPair>
+TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
+                              OnPair&& on_pair) {
+    BlockSlots<T, MAXLAB> b;
+    if (!b.discover(tile, fs, m0, s0, nvf, nvm, nvs)) return false;
+#pragma unroll
+    for (int i = 0; i < MAXLAB; ++i) {
         uint32_t v[16];
-        v[0] = n_; v[1] = sf; v[2] = sm; v[3] = ss; v[4] = sff; v[5] = sfm; v[6] = sfs; v[7] = smm; v[8] = sm1; v[9] = n1;
-        v[10] = (uint32_t)ta_ffs(colmask) - 1u; v[11] = (uint32_t)ta_ffs(mrows) - 1u; v[12] = (rows & 0xFu) ? 0u : 1u;
-        v[13] = 31u - (uint32_t)
-#ifdef __CUDA_ARCH__
-            __clz(colmask);
-#else
-            __builtin_clz(colmask);
-#endif
-        v[14] = 31u - (uint32_t)
-#ifdef __CUDA_ARCH__
-            __clz(mrows);
-#else
-            __builtin_clz(mrows);
-#endif
-        v[15] = (rows >> BLK_M) ? 1u : 0u;
-        on_label(lab[i], v);
+        if (!b.label_moments(i, v)) continue;
+        on_label(b.lab[i], v);
 #pragma unroll
         for (int j = 0; j < MAXLAB; ++j) {
-            if (j == i || j >= k) continue;
-            const uint32_t w18 = ta_popc64(c0 & D0[j]) + ta_popc64(c1 & D1[j]);
-            const uint32_t ff = ta_popc64(c0 & (M1[j] >> 1)) + ta_popc64(c1 & (M2[j] >> 1));
-            const uint32_t fm = ta_popc64(c0 & (M1[j] >> BLK_ROWBITS)) + ta_popc64(c1 & (M2[j] >> BLK_ROWBITS));
-            const uint32_t fsl = ta_popc64(c0 & M2[j]) + ta_popc64(c1 & M3[j]);
-            if (w18 | ff | fm | fsl) on_pair(lab[i], lab[j], w18, ff, fm, fsl);
+            uint32_t w18, ff, fm, fsl;
+            if (b.pair_counts(i, j, w18, ff, fm, fsl)) on_pair(b.lab[i], b.lab[j], w18, ff, fm, fsl);
         }
     }
     return true;

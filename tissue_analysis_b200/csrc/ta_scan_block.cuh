@@ -2,26 +2,30 @@
 //
 // STATUS: the block arithmetic, the block -> brick -> global transforms, the pair slot conventions and the slab
 // ownership rules are validated on the CPU (tests/host/block_host_check.cu, block_volume_check.cu).  This kernel wires
-// them to the staging, the per-brick tables and the flush of the product kernel in the simplest possible way -- one
-// 8 x 4 x 2 block per thread, results added to the per-brick shared tables with plain atomics, no warp merges yet.  It
+// them to the staging, the per-brick tables and the flush of the product kernel: one 8 x 4 x 2 block per thread; the
+// results go to the per-brick shared tables through slot-wise warp merges (MERGE = true) or, in the simpler form kept
+// to bisect against, with plain atomics per block (MERGE = false).  It
 // compiles for sm_100a but was written after the round's GPU budget was spent: it has NOT run on a GPU, and it is NOT
 // part of the product build (ta_api.cu includes it only under -DTA_WITH_BLOCK_KERNEL; a product library answers flag
-// 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: the table updates and the per-voxel fallback are out of
-// line (inlined, the kernel took minutes to compile), so the 16 moments of a label travel through local memory, and
-// ptxas spills ~150 bytes at 80 registers -- the first things to fix.  Plan and cost model: DESIGN.md section 6.
+// 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: the per-voxel fallback and the plain-atomics updates are
+// out of line (inlined, the kernel took minutes to compile); at 80 registers ptxas spills ~130 bytes in the simple form
+// and ~460 bytes in the merged form (four label slots of five 64-bit planes plus 16 merged fields) -- 2 CTAs/SM with 128
+// registers, or a three-slot limit, are the first things to try.  Plan and cost model: DESIGN.md section 6.
 //
 // First run (needs a B200):
 //   TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$PWD/build/libtissue_b200_block.so bash tissue_analysis_b200/csrc/build.sh
 //   TA_LIB_PATH=$PWD/build/libtissue_b200_block.so TA_PAIR_PATH=block python -m pytest tests/test_gpu_parity.py -x -q
 //   TA_LIB_PATH=$PWD/build/libtissue_b200_block.so TA_PAIR_PATH=block python tools/profile_scan.py --config C3
-// (TA_PAIR_PATH=block sets flag 0x4000 for every pass of uint16 volumes, so the whole parity suite runs on this kernel.)
+// (TA_PAIR_PATH=block sets flag 0x4000 for every pass of uint16 volumes, so the whole parity suite runs on this kernel;
+//  TA_PAIR_PATH=block_simple selects the form without warp merges.)
 #pragma once
 #include "ta_block.cuh"
 
 namespace ta {
 
 constexpr size_t scan_block_smem_bytes() {
-    return (size_t)TILE_SEGS * 16 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * 4 + PT_SLOTS * PT_WORDS * 4 + 64;
+    return (size_t)TILE_SEGS * 16 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * 4 + PT_SLOTS * PT_WORDS * 4 + 64 +
+           NTHREADS * 2;                        // + the list of blocks that take the per-voxel path
 }
 
 // per-voxel fallback for one voxel of a block whose window holds more labels than slots: moments of the voxel and its
@@ -82,6 +86,63 @@ __device__ __noinline__ void block_emit_pair(const BrickShared<uint16_t>& sh, co
     if (inc[0] | inc[1] | inc[2] | inc[3]) pair_add_packed<uint16_t>(sh, pt, Vox<uint16_t>::key(a, b), inc);
 }
 
+// Warp merges (all 32 lanes call; lanes without a contribution pass has = false).  One shared-table update per
+// distinct label / pair of the warp: uniform loop over the distinct keys, full-mask redux, the group leaders add.  Same
+// pattern as the column flush and phase D of the product kernel.
+__device__ __forceinline__ void block_merge_label(const BrickShared<uint16_t>& sh, const LabelTable& lt, uint32_t* status,
+                                                  bool has, uint32_t L, const uint32_t v[LT_FIELDS], u64 gF0, u64 gM0,
+                                                  u64 gS0, int lane) {
+    unsigned pending = __ballot_sync(0xffffffffu, has);
+    uint32_t tot[LT_FIELDS];
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t Lk = __shfl_sync(0xffffffffu, L, leader);
+        const bool mine = has && (L == Lk);
+        const bool lead = (lane == leader);
+#pragma unroll
+        for (int f = 0; f < 10; ++f) {
+            const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? v[f] : 0u);
+            if (lead) tot[f] = r;
+        }
+#pragma unroll
+        for (int f = 10; f < 13; ++f) {
+            const uint32_t r = __reduce_min_sync(0xffffffffu, mine ? v[f] : 0xFFFFFFFFu);
+            if (lead) tot[f] = r;
+        }
+#pragma unroll
+        for (int f = 13; f < 16; ++f) {
+            const uint32_t r = __reduce_max_sync(0xffffffffu, mine ? v[f] : 0u);
+            if (lead) tot[f] = r;
+        }
+        am_leader = am_leader || lead;
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (am_leader) label_add<uint16_t>(sh, lt, status, L, tot, gF0, gM0, gS0);
+}
+__device__ __forceinline__ void block_merge_pair(const BrickShared<uint16_t>& sh, const PairTable& pt, uint32_t key,
+                                                 const uint32_t inc[PT_WORDS], int lane) {
+    unsigned pending = __ballot_sync(0xffffffffu, key != Vox<uint16_t>::PEMPTY);
+    uint32_t tot[PT_WORDS] = {0u, 0u, 0u, 0u};
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t kk = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = (key == kk);
+#pragma unroll
+        for (int w = 0; w < PT_WORDS; ++w) {
+            const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? inc[w] : 0u);
+            if (lane == leader) tot[w] = r;
+        }
+        am_leader = am_leader || (lane == leader);
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (am_leader) pair_add_packed<uint16_t>(sh, pt, key, tot);
+}
+
+// MERGE = true: slot-wise uniform loops with warp merges (flag 0x4000); false: plain atomics per block (0x4000 | 0x8000),
+// kept as the simpler form to bisect against.
+template <bool MERGE>
 __global__ void __launch_bounds__(NTHREADS, 3)
 scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef uint16_t T;
@@ -97,9 +158,11 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
     sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
     sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
+    unsigned short* crowded = reinterpret_cast<unsigned short*>(sh.ctr + 16);      // [NTHREADS] blocks for the per-voxel path
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const T* vol = reinterpret_cast<const T*>(P.vol);
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
@@ -126,7 +189,7 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     for (unsigned iter = 0;; ++iter) {
         const unsigned int brick = sh.ctr[6 + (iter & 1u)];
         if (brick >= total) break;
-        if (tid == 0) sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
+        if (tid == 0) { sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u); sh.ctr[1] = 0u; }
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
@@ -225,7 +288,62 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         }
 
         // ---- one block per thread ------------------------------------------------------------------------------------------
-        {
+        if (MERGE) {
+            const int fs = tid % NFS, m0 = ((tid / NFS) % (BM / BLK_M)) * BLK_M, s0 = (tid / (NFS * (BM / BLK_M))) * BLK_S;
+            const int nvf = min(SEG, nf - (F0 + fs * SEG)), nvm = min(BLK_M, nm - (M0 + m0)),
+                      nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
+            const uint32_t bF = (uint32_t)(fs * SEG), bM = (uint32_t)m0, bS = (uint32_t)s0;
+            BlockSlots<T, BLK_MAXLAB> b;
+            bool ok = (nvf > 0 && nvm > 0 && nvs > 0);
+            if (ok && !b.discover(sh.tile, fs, m0, s0, nvf, nvm, nvs)) {
+                crowded[atomicAdd(&sh.ctr[1], 1u)] = (unsigned short)tid;        // more labels than slots: per-voxel path
+                ok = false;
+            }
+            if (!ok) b.clear();                                                    // every slot answers "empty"
+            // the same trip counts in every lane: the merges are full-mask
+#pragma unroll
+            for (int i = 0; i < BLK_MAXLAB; ++i) {
+                uint32_t v[LT_FIELDS];
+                const bool has = do_mom && b.label_moments(i, v);
+                if (has) block_shift_moments(v, bF, bM, bS);                       // block -> brick coordinates
+                block_merge_label(sh, lt, pt.status, has, b.lab[i], v, gF0, gM0, gS0, lane);
+            }
+            if (do_p6 || do_w18) {
+#pragma unroll
+                for (int i = 0; i < BLK_MAXLAB; ++i) {
+#pragma unroll
+                    for (int j = 0; j < BLK_MAXLAB; ++j) {
+                        if (i == j) continue;
+                        uint32_t w18, ff, fm, fsl;
+                        const bool has = b.pair_counts(i, j, w18, ff, fm, fsl);
+                        if (!do_w18) w18 = 0u;
+                        if (!do_p6) ff = fm = fsl = 0u;
+                        const uint32_t a = b.lab[i], c = b.lab[j];
+                        const bool lo = a < c;                 // seen from a at the lower-index voxel: slot 2k, else 2k + 1
+                        uint32_t inc[PT_WORDS];                // [w18|f0] [f1|f2] [f3|f4] [f5|-]
+                        inc[0] = w18 | ((lo ? ff : 0u) << 16);
+                        inc[1] = (lo ? 0u : ff) | ((lo ? fm : 0u) << 16);
+                        inc[2] = (lo ? 0u : fm) | ((lo ? fsl : 0u) << 16);
+                        inc[3] = lo ? 0u : fsl;
+                        const bool any = has && (inc[0] | inc[1] | inc[2] | inc[3]);
+                        block_merge_pair(sh, pt, any ? Vox<T>::key(a, c) : Vox<T>::PEMPTY, inc, lane);
+                    }
+                }
+            }
+            __syncthreads();
+            // crowded blocks: all threads share their voxels (64 per block)
+            const int ncrowded = (int)sh.ctr[1];
+            constexpr int BV = SEG * BLK_M * BLK_S;
+            for (int q = tid; q < ncrowded * BV; q += NTHREADS) {
+                const int blk = crowded[q / BV], w = q % BV;
+                const int cfs = blk % NFS, cm0 = ((blk / NFS) % (BM / BLK_M)) * BLK_M, cs0 = (blk / (NFS * (BM / BLK_M))) * BLK_S;
+                const int df = w % SEG, dm = (w / SEG) % BLK_M, ds = w / (SEG * BLK_M);
+                const uint32_t f = (uint32_t)(cfs * SEG + df), m = (uint32_t)(cm0 + dm), sp = (uint32_t)(cs0 + ds);
+                if (F0 + (int)f >= nf || M0 + (int)m >= nm || S0 + (int)sp >= (int)P.own_hi) continue;
+                const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + f;
+                block_fallback_voxel(sh, lt, pt, p, f, m, sp, gF0, gM0, gS0, do_mom, do_p6, do_w18);
+            }
+        } else {
             const int fs = tid % NFS, m0 = ((tid / NFS) % (BM / BLK_M)) * BLK_M, s0 = (tid / (NFS * (BM / BLK_M))) * BLK_S;
             const int nvf = min(SEG, nf - (F0 + fs * SEG)), nvm = min(BLK_M, nm - (M0 + m0)),
                       nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
