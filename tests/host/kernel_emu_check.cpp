@@ -1,0 +1,157 @@
+// Runs the scan kernels THEMSELVES on the CPU (tests/host/emu/cuda_emu.h: fibers for threads, rendezvous for the warp and
+// block collectives) and compares the tables they fill with a direct pass over the voxels.  Covered: the product kernel
+// scan_kernel<T, false, false> (march, worklists, per-voxel pair phases, flush), its one-hot instantiation, and the
+// experimental block kernels of ta_scan_block.cuh with and without warp merges -- on the scalar staging path (vec_ok = 0,
+// use_tma = 0: the only path without inline PTX).  Test infrastructure: g++ only, no GPU, no nvcc.
+// Usage: kernel_emu_check <seed> ; exit code 0 = every case equal.
+#include "emu/cuda_emu.h"
+
+#include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
+
+namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
+
+using namespace ta;
+
+struct LabelRow { u64 v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long bmin[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, bmax[3] = {-1, -1, -1};
+    bool operator==(const LabelRow& o) const { return std::equal(v, v + 10, o.v) && std::equal(bmin, bmin + 3, o.bmin) && std::equal(bmax, bmax + 3, o.bmax); } };
+typedef std::map<uint32_t, LabelRow> LabelTab;
+typedef std::map<std::pair<uint32_t, uint32_t>, std::array<u64, 7>> PairTab;
+
+struct Vol {
+    int nf, nm, ns; std::vector<uint32_t> d;
+    uint32_t at(int f, int m, int s) const {
+        f = std::min(std::max(f, 0), nf - 1); m = std::min(std::max(m, 0), nm - 1); s = std::min(std::max(s, 0), ns - 1);
+        return d[((size_t)s * nm + m) * nf + f];
+    }
+};
+
+static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, LabelTab& lt, PairTab& pt) {
+    const uint32_t a = V.at(f, m, s);
+    LabelRow& r = lt[a];
+    const u64 F = f, M = m, S = (u64)(s + slow_offset);
+    r.v[0] += 1; r.v[1] += F; r.v[2] += M; r.v[3] += S; r.v[4] += F * F; r.v[5] += F * M; r.v[6] += F * S; r.v[7] += M * M;
+    r.v[8] += M * S; r.v[9] += S * S;
+    const long c[3] = {(long)F, (long)M, (long)S};
+    for (int k = 0; k < 3; ++k) { r.bmin[k] = std::min(r.bmin[k], c[k]); r.bmax[k] = std::max(r.bmax[k], c[k]); }
+    std::map<uint32_t, int> seen;
+    for (int z = -1; z <= 1; ++z) for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) {
+        const int l1 = abs(z) + abs(y) + abs(x);
+        if (l1 < 1 || l1 > 2) continue;
+        const uint32_t b = V.at(f + x, m + y, s + z);
+        if (b != a) seen[b] = 1;
+    }
+    for (auto& kv : seen) pt[{std::min(a, kv.first), std::max(a, kv.first)}][6] += 1;
+    const uint32_t nb[3] = {V.at(f + 1, m, s), V.at(f, m + 1, s), V.at(f, m, s + 1)};
+    for (int k = 0; k < 3; ++k)
+        if (nb[k] != a) pt[{std::min(a, nb[k]), std::max(a, nb[k])}][2 * k + (a < nb[k] ? 0 : 1)] += 1;
+}
+
+enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE };
+static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<true>",
+                                   "scan_block_kernel<false>"};
+
+template <typename T>
+static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
+                    unsigned seed) {
+    std::mt19937 rng(seed);
+    Vol V{nf, nm, nbuf, std::vector<uint32_t>((size_t)nf * nm * nbuf)};
+    const uint32_t top = sizeof(T) == 2 ? 4000u : 9000u;            // dense label table: keep it small
+    std::vector<uint32_t> names(nlabels);
+    for (auto& n : names) n = 1 + rng() % top;
+    if (mode == 0) {
+        for (auto& v : V.d) v = names[rng() % nlabels];
+    } else {
+        std::vector<int> sx(nlabels), sy(nlabels), sz(nlabels);
+        for (int k = 0; k < nlabels; ++k) { sx[k] = rng() % nf; sy[k] = rng() % nm; sz[k] = rng() % nbuf; }
+        for (int s = 0; s < nbuf; ++s) for (int m = 0; m < nm; ++m) for (int f = 0; f < nf; ++f) {
+            long best = 1L << 60; int bk = 0;
+            for (int k = 0; k < nlabels; ++k) {
+                long d = (long)(f - sx[k]) * (f - sx[k]) + (long)(m - sy[k]) * (m - sy[k]) * 2 + (long)(s - sz[k]) * (s - sz[k]) * 3;
+                if (d < best) { best = d; bk = k; }
+            }
+            V.d[((size_t)s * nm + m) * nf + f] = names[bk];
+        }
+    }
+    LabelTab refL; PairTab refP;
+    for (int s = own_lo; s < own_hi; ++s) for (int m = 0; m < nm; ++m) for (int f = 0; f < nf; ++f)
+        add_voxel(V, f, m, s, slow_offset, refL, refP);
+
+    // device-side structures in host memory
+    std::vector<T> vol(V.d.size());
+    for (size_t i = 0; i < vol.size(); ++i) vol[i] = (T)V.d[i];
+    const uint32_t nrows = sizeof(T) == 2 ? 65536u : top + 2;
+    std::vector<u64> sums((size_t)nrows * 10, 0);
+    std::vector<int> boxes((size_t)nrows * 6);
+    for (size_t i = 0; i < (size_t)nrows * 3; ++i) { boxes[i] = 0x7FFFFFFF; boxes[(size_t)nrows * 3 + i] = -1; }
+    LabelTable lt;
+    lt.count = sums.data(); lt.s1 = lt.count + nrows; lt.s2 = lt.s1 + (size_t)nrows * 3;
+    lt.bmin = boxes.data(); lt.bmax = lt.bmin + (size_t)nrows * 3; lt.nrows = nrows;
+    const uint32_t cap = 1u << 14;
+    std::vector<u64> keys(cap, TA_EMPTY64);
+    std::vector<uint32_t> vals((size_t)cap * TA_PAIR_STRIDE, 0u), status(8, 0u);
+    PairTable pt;
+    pt.keys = keys.data(); pt.vals = vals.data(); pt.cap_mask = cap - 1; pt.status = status.data();
+    unsigned int brick_counter = 0;
+    ScanParams P{};
+    P.vol = vol.data(); P.nf = nf; P.nm = nm; P.ns = nbuf; P.own_lo = own_lo; P.own_hi = own_hi; P.slow_offset = slow_offset;
+    const int seg = 16 / (int)sizeof(T);
+    P.nbf = (nf + NFS * seg - 1) / (NFS * seg); P.nbm = (nm + BM - 1) / BM; P.nbs = (own_hi - own_lo + BS - 1) / BS;
+    P.flags = 7u; P.vec_ok = 0; P.use_tma = 0; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    bool ok = true;
+    for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
+        ok = emu::run_block(block, 2, NTHREADS, [&]() {
+            if (which == PRODUCT) scan_kernel<T, false, false>(P, lt, pt, tmap);
+            else if (which == ONEHOT) scan_kernel<T, true, false>(P, lt, pt, tmap);
+            else if (which == BLOCK_MERGE) scan_block_kernel<true>(P, lt, pt, tmap);
+            else scan_block_kernel<false>(P, lt, pt, tmap);
+        });
+    }
+    LabelTab gotL; PairTab gotP;
+    for (uint32_t L = 0; L < nrows; ++L) {
+        if (!lt.count[L]) continue;
+        LabelRow r;
+        r.v[0] = lt.count[L];
+        for (int k = 0; k < 3; ++k) { r.v[1 + k] = lt.s1[(size_t)L * 3 + k]; r.bmin[k] = lt.bmin[(size_t)L * 3 + k]; r.bmax[k] = lt.bmax[(size_t)L * 3 + k]; }
+        for (int k = 0; k < 6; ++k) r.v[4 + k] = lt.s2[(size_t)L * 6 + k];
+        gotL[L] = r;
+    }
+    for (uint32_t i = 0; i < cap; ++i) {
+        if (keys[i] == TA_EMPTY64) continue;
+        std::array<u64, 7> a;
+        u64 any = 0;
+        for (int k = 0; k < 7; ++k) { a[k] = vals[(size_t)i * TA_PAIR_STRIDE + k]; any |= a[k]; }
+        if (any) gotP[{(uint32_t)(keys[i] >> 32), (uint32_t)keys[i]}] = a;
+    }
+    if (!ok || status[0] || status[1] || gotL != refL || gotP != refP) {
+        fprintf(stderr, "MISMATCH %s T=%d nf=%d nm=%d nbuf=%d own=[%d,%d) labels=%d mode=%d seed=%u: run %s, status %u %u, labels %zu/%zu "
+                        "(equal %d), pairs %zu/%zu (equal %d)\n", which_name[which], (int)sizeof(T), nf, nm, nbuf, own_lo, own_hi, nlabels,
+                mode, seed, ok ? "ok" : "DEADLOCK", status[0], status[1], gotL.size(), refL.size(), (int)(gotL == refL), gotP.size(),
+                refP.size(), (int)(gotP == refP));
+        return 1;
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    std::mt19937 rng(argc > 1 ? (unsigned)atoi(argv[1]) : 1u);
+    const int ncases = argc > 2 ? atoi(argv[2]) : 24;
+    int bad = 0, ran = 0;
+    for (int c = 0; c < ncases; ++c) {
+        const Which which = (Which)(c % 4);
+        const bool wide = (c / 4) % 3 == 2 && which != BLOCK_MERGE && which != BLOCK_SIMPLE;      // block kernels: uint16 only
+        const int maxf = wide ? 150 : 300;
+        const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
+        int lo = 0, hi = nbuf; long off = 0;
+        if (c % 5 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }
+        const int nl = 1 + rng() % (c % 7 == 0 ? 40 : 12), mode = c % 3 == 0 ? 0 : 1;
+        const unsigned seed = rng();
+        bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed)
+                    : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed);
+        ++ran;
+    }
+    printf("kernel_emu_check: %d kernel runs on the CPU emulation, %d mismatches\n", ran, bad);
+    return bad ? 1 : 0;
+}

@@ -1,0 +1,29 @@
+"""The scan kernels themselves, run on the CPU (tests/host/emu/cuda_emu.h: every CUDA thread is a fiber, warp and block
+collectives are rendezvous points, atomics are plain) against a direct pass over the voxels.
+
+Covers the source of the product kernel scan_kernel<T, false, false> for uint16 and uint32 (march, worklists, per-voxel
+pair phases, flush, slab ownership, ragged bricks), its one-hot instantiation, and the experimental block kernels with and
+without warp merges -- on the scalar staging path (vec_ok = 0, use_tma = 0), the only one without inline PTX.  g++ only.
+The GPU parity tests stay the authority for the compiled kernels; this one finds logic errors without a GPU.
+"""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_scan_kernels_on_the_cpu_emulation(tmp_path):
+    gxx = shutil.which("g++")
+    inc = "/usr/local/cuda/include"
+    if not gxx or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    exe = str(tmp_path / "kernel_emu_check")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-w", "-I" + inc, "-o", exe, os.path.join(HERE, "host", "kernel_emu_check.cpp")],
+                   check=True, capture_output=True, timeout=900)
+    for seed in (1, 2):
+        r = subprocess.run([exe, str(seed), "24"], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert " 0 mismatches" in r.stdout

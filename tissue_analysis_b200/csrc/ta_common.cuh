@@ -10,6 +10,11 @@
 
 typedef unsigned long long u64;
 
+// inline PTX goes through this macro so that the CPU emulation of the kernels (tests/host/emu) can compile them with g++
+#ifndef TA_PTX
+#define TA_PTX(...) asm volatile(__VA_ARGS__)
+#endif
+
 // Dense per-label table (row index = label value).  Sums are exact u64 integers so the result does not
 // depend on accumulation order (bit-reproducible, mergeable across ranks by plain addition).
 struct LabelTable {

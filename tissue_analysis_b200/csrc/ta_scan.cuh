@@ -90,37 +90,37 @@ template <typename T> constexpr size_t scan_smem_bytes() {
 
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    TA_PTX("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+    TA_PTX("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    TA_PTX("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- TMA staging: one 3-D box copy (brick + halo) per tile, completion on an mbarrier ------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    TA_PTX("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+    TA_PTX("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                  :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\t"
+    TA_PTX("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
     return done != 0u;
 }
 __device__ __forceinline__ void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+    TA_PTX("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
                     "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
@@ -810,7 +810,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     const bool use_tma = P.use_tma && ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u) == 0u;
     if (use_tma && tid == 0) {
         mbar_init(tma_bar, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        TA_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
     // Phase clocks (TIMING only): thread 0 keeps per-phase cycle totals and the last time stamp in shared memory -- no
@@ -843,7 +843,7 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         if (use_tma) {
             // the callers' barrier ordered every earlier generic-proxy access of the tile before this point
             if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
                 tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
             }

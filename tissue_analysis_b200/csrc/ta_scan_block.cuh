@@ -4,7 +4,9 @@
 // ownership rules are validated on the CPU (tests/host/block_host_check.cu, block_volume_check.cu).  This kernel wires
 // them to the staging, the per-brick tables and the flush of the product kernel: one 8 x 4 x 2 block per thread; the
 // results go to the per-brick shared tables through slot-wise warp merges (MERGE = true) or, in the simpler form kept
-// to bisect against, with plain atomics per block (MERGE = false).  It
+// to bisect against, with plain atomics per block (MERGE = false).  Both forms fill exact tables on the CPU emulation
+// of the CUDA execution model (tests/host/kernel_emu_check.cpp: fibers for threads, rendezvous for the collectives;
+// scalar staging path).  It
 // compiles for sm_100a but was written after the round's GPU budget was spent: it has NOT run on a GPU, and it is NOT
 // part of the product build (ta_api.cu includes it only under -DTA_WITH_BLOCK_KERNEL; a product library answers flag
 // 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: the per-voxel fallback and the plain-atomics updates are
@@ -181,7 +183,7 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     const bool use_tma = P.use_tma && ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u) == 0u;
     if (use_tma && tid == 0) {
         mbar_init(tma_bar, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        TA_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid == 0) sh.ctr[6] = atomicAdd(P.brick_counter, 1u);
     __syncthreads();
@@ -197,7 +199,7 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         // ---- phase A: the tile, as in the product kernel (TODO: share the code once this kernel has run) ---------------
         if (use_tma) {
             if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
                 tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
             }
