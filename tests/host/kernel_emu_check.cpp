@@ -59,6 +59,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     const uint32_t top = sizeof(T) == 2 ? 4000u : 9000u;            // dense label table: keep it small
     std::vector<uint32_t> names(nlabels);
     for (auto& n : names) n = 1 + rng() % top;
+    if (sizeof(T) == 2 && nlabels >= 3 && (seed & 1u)) names[1] = 0xFFFFu;      // the uint16 value that doubles as the MIXED code
     if (mode == 0) {
         for (auto& v : V.d) v = names[rng() % nlabels];
     } else {
@@ -87,7 +88,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     LabelTable lt;
     lt.count = sums.data(); lt.s1 = lt.count + nrows; lt.s2 = lt.s1 + (size_t)nrows * 3;
     lt.bmin = boxes.data(); lt.bmax = lt.bmin + (size_t)nrows * 3; lt.nrows = nrows;
-    const uint32_t cap = 1u << 14;
+    const uint32_t cap = 1u << 17;                    // room for the noise cases (tens of thousands of pairs)
     std::vector<u64> keys(cap, TA_EMPTY64);
     std::vector<uint32_t> vals((size_t)cap * TA_PAIR_STRIDE, 0u), status(8, 0u);
     PairTable pt;
@@ -146,7 +147,8 @@ int main(int argc, char** argv) {
         const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
         int lo = 0, hi = nbuf; long off = 0;
         if (c % 5 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }
-        const int nl = 1 + rng() % (c % 7 == 0 ? 40 : 12), mode = c % 3 == 0 ? 0 : 1;
+        // c % 11 == 3: hundreds of labels in noise -- the per-brick label and pair tables fill up and spill to the global ones
+        const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = (c % 3 == 0 || c % 11 == 3) ? 0 : 1;
         const unsigned seed = rng();
         bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed)
                     : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed);
