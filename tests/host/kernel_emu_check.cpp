@@ -48,8 +48,8 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE };
-static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<true>",
-                                   "scan_block_kernel<false>"};
+static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
+                                   "scan_block_kernel<T,false>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -106,8 +106,8 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
         ok = emu::run_block(block, 2, NTHREADS, [&]() {
             if (which == PRODUCT) scan_kernel<T, false, false>(P, lt, pt, tmap);
             else if (which == ONEHOT) scan_kernel<T, true, false>(P, lt, pt, tmap);
-            else if (which == BLOCK_MERGE) scan_block_kernel<true>(P, lt, pt, tmap);
-            else scan_block_kernel<false>(P, lt, pt, tmap);
+            else if (which == BLOCK_MERGE) scan_block_kernel<T, true>(P, lt, pt, tmap);
+            else scan_block_kernel<T, false>(P, lt, pt, tmap);
         });
     }
     LabelTab gotL; PairTab gotP;
@@ -142,7 +142,7 @@ int main(int argc, char** argv) {
     int bad = 0, ran = 0;
     for (int c = 0; c < ncases; ++c) {
         const Which which = (Which)(c % 4);
-        const bool wide = (c / 4) % 3 == 2 && which != BLOCK_MERGE && which != BLOCK_SIMPLE;      // block kernels: uint16 only
+        const bool wide = (c / 4) % 3 == 2;                                   // every third round: uint32 labels
         const int maxf = wide ? 150 : 300;
         const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
         int lo = 0, hi = nbuf; long off = 0;

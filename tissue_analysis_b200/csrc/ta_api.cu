@@ -352,21 +352,16 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
 #ifdef TA_WITH_BLOCK_KERNEL
-    if ((P.flags & 0x4000u) && ctx->elem == 2) {
+    if (P.flags & 0x4000u) {
         // experimental block-bitmask kernel (ta_scan_block.cuh): only on request, configured on first use so that the
         // product path never depends on it
-        static bool configured = false;
-        if (!configured) {
-            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ta::scan_block_smem_bytes()));
-            TA_CUDA(cudaFuncSetAttribute((const void*)ta::scan_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ta::scan_block_smem_bytes()));
-            configured = true;
-        }
-        if (P.flags & 0x8000u)
-            ta::scan_block_kernel<false><<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
-        else
-            ta::scan_block_kernel<true><<<grid, ta::NTHREADS, ta::scan_block_smem_bytes(), st>>>(P, ctx->lt, ctx->pt, tmap);
+        typedef void (*block_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
+        const bool merge = !(P.flags & 0x8000u);
+        const block_fn fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_block_kernel<uint16_t, true> : (block_fn)ta::scan_block_kernel<uint16_t, false>)
+                                           : (merge ? (block_fn)ta::scan_block_kernel<uint32_t, true> : (block_fn)ta::scan_block_kernel<uint32_t, false>);
+        const size_t bsmem = ctx->elem == 2 ? ta::scan_block_smem_bytes<uint16_t>() : ta::scan_block_smem_bytes<uint32_t>();
+        TA_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        fn<<<grid, ta::NTHREADS, bsmem, st>>>(P, ctx->lt, ctx->pt, tmap);
         ctx->launches++;
         TA_CUDA(cudaGetLastError());
         return TA_OK;

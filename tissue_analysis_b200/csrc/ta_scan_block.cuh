@@ -1,4 +1,4 @@
-// EXPERIMENTAL scan kernel on the block-bitmask formulation (csrc/ta_block.cuh): uint16 volumes, flag 0x4000.
+// EXPERIMENTAL scan kernel on the block-bitmask formulation (csrc/ta_block.cuh): both label widths, flag 0x4000.
 //
 // STATUS: the block arithmetic, the block -> brick -> global transforms, the pair slot conventions and the slab
 // ownership rules are validated on the CPU (tests/host/block_host_check.cu, block_volume_check.cu).  This kernel wires
@@ -18,29 +18,30 @@
 //   TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$PWD/build/libtissue_b200_block.so bash tissue_analysis_b200/csrc/build.sh
 //   TA_LIB_PATH=$PWD/build/libtissue_b200_block.so TA_PAIR_PATH=block python -m pytest tests/test_gpu_parity.py -x -q
 //   TA_LIB_PATH=$PWD/build/libtissue_b200_block.so TA_PAIR_PATH=block python tools/profile_scan.py --config C3
-// (TA_PAIR_PATH=block sets flag 0x4000 for every pass of uint16 volumes, so the whole parity suite runs on this kernel;
+// (TA_PAIR_PATH=block sets flag 0x4000 for every pass, so the whole parity suite runs on this kernel;
 //  TA_PAIR_PATH=block_simple selects the form without warp merges.)
 #pragma once
 #include "ta_block.cuh"
 
 namespace ta {
 
-constexpr size_t scan_block_smem_bytes() {
-    return (size_t)TILE_SEGS * 16 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * 4 + PT_SLOTS * PT_WORDS * 4 + 64 +
+template <typename T> constexpr size_t scan_block_smem_bytes() {
+    return (size_t)TILE_SEGS * 16 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) +
+           PT_SLOTS * PT_WORDS * 4 + 64 +
            NTHREADS * 2;                        // + the list of blocks that take the per-voxel path
 }
 
 // per-voxel fallback for one voxel of a block whose window holds more labels than slots: moments of the voxel and its
-// pairs by a register de-duplication of the 18 neighbours (the logic of phase D2 of the product kernel)
-__device__ __noinline__ void block_fallback_voxel(const BrickShared<uint16_t>& sh, const LabelTable& lt,
-                                                     const PairTable& pt, const unsigned short* p, uint32_t f, uint32_t m,
-                                                     uint32_t s, u64 gF0, u64 gM0, u64 gS0, bool do_mom, bool do_p6,
-                                                     bool do_w18) {
-    constexpr int ROWE = ROWV * 8, PLANEE = (BM + 2) * ROWE;
+// pairs by a first-occurrence scan of the 18 neighbours (the rare path of phase D2 of the product kernel)
+template <typename T>
+__device__ __noinline__ void block_fallback_voxel(const BrickShared<T>& sh, const LabelTable& lt, const PairTable& pt,
+                                                  const T* p, uint32_t f, uint32_t m, uint32_t s, u64 gF0, u64 gM0, u64 gS0,
+                                                  bool do_mom, bool do_p6, bool do_w18) {
+    constexpr int ROWE = ROWV * Vox<T>::SEG, PLANEE = (BM + 2) * ROWE;
     const uint32_t a = p[0];
     if (do_mom) {
         uint32_t v[LT_FIELDS] = {1u, f, m, s, f * f, f * m, f * s, m * m, m * s, s * s, f, m, s, f, m, s};
-        label_add<uint16_t>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
+        label_add<T>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
     }
     if (!(do_p6 || do_w18)) return;
     constexpr int offs[18] = {1, ROWE, PLANEE, -1, -ROWE, -PLANEE, -ROWE - 1, -ROWE + 1, ROWE - 1, ROWE + 1,
@@ -50,7 +51,7 @@ __device__ __noinline__ void block_fallback_voxel(const BrickShared<uint16_t>& s
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const uint32_t b = p[offs[k]];
-            if (b != a) pair_add<uint16_t>(sh, pt, a, b, 2 * k + (a < b ? 0 : 1), 1u);
+            if (b != a) pair_add<T>(sh, pt, a, b, 2 * k + (a < b ? 0 : 1), 1u);
         }
     }
     if (do_w18) {
@@ -60,23 +61,25 @@ __device__ __noinline__ void block_fallback_voxel(const BrickShared<uint16_t>& s
             if (b == a) continue;
             bool seen = false;
             for (int q = 0; q < k; ++q) seen |= ((uint32_t)p[offs[q]] == b);
-            if (!seen) pair_add<uint16_t>(sh, pt, a, b, 6, 1u);
+            if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
         }
     }
 }
 
 // Out-of-line table updates: the block code calls them from up to 4 label slots and 12 ordered slot pairs; inlining
 // every copy multiplies the compile time of this kernel by five for nothing.
-__device__ __noinline__ void block_emit_label(const BrickShared<uint16_t>& sh, const LabelTable& lt, uint32_t* status,
+template <typename T>
+__device__ __noinline__ void block_emit_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
                                               uint32_t L, const uint32_t* vin, uint32_t bF, uint32_t bM, uint32_t bS, u64 gF0,
                                               u64 gM0, u64 gS0) {
     uint32_t v[LT_FIELDS];
 #pragma unroll
     for (int i = 0; i < LT_FIELDS; ++i) v[i] = vin[i];
     block_shift_moments(v, bF, bM, bS);                           // block -> brick coordinates
-    label_add<uint16_t>(sh, lt, status, L, v, gF0, gM0, gS0);
+    label_add<T>(sh, lt, status, L, v, gF0, gM0, gS0);
 }
-__device__ __noinline__ void block_emit_pair(const BrickShared<uint16_t>& sh, const PairTable& pt, uint32_t a, uint32_t b,
+template <typename T>
+__device__ __noinline__ void block_emit_pair(const BrickShared<T>& sh, const PairTable& pt, uint32_t a, uint32_t b,
                                              uint32_t w18, uint32_t ff, uint32_t fm, uint32_t fsl) {
     // seen from label a at the lower-index voxel: slot 2k when a is the smaller label, else 2k + 1
     const bool lo = a < b;
@@ -85,13 +88,14 @@ __device__ __noinline__ void block_emit_pair(const BrickShared<uint16_t>& sh, co
     inc[1] = (lo ? 0u : ff) | ((lo ? fm : 0u) << 16);
     inc[2] = (lo ? 0u : fm) | ((lo ? fsl : 0u) << 16);
     inc[3] = lo ? 0u : fsl;
-    if (inc[0] | inc[1] | inc[2] | inc[3]) pair_add_packed<uint16_t>(sh, pt, Vox<uint16_t>::key(a, b), inc);
+    if (inc[0] | inc[1] | inc[2] | inc[3]) pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
 }
 
 // Warp merges (all 32 lanes call; lanes without a contribution pass has = false).  One shared-table update per
 // distinct label / pair of the warp: uniform loop over the distinct keys, full-mask redux, the group leaders add.  Same
 // pattern as the column flush and phase D of the product kernel.
-__device__ __forceinline__ void block_merge_label(const BrickShared<uint16_t>& sh, const LabelTable& lt, uint32_t* status,
+template <typename T>
+__device__ __forceinline__ void block_merge_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
                                                   bool has, uint32_t L, const uint32_t v[LT_FIELDS], u64 gF0, u64 gM0,
                                                   u64 gS0, int lane) {
     unsigned pending = __ballot_sync(0xffffffffu, has);
@@ -120,16 +124,17 @@ __device__ __forceinline__ void block_merge_label(const BrickShared<uint16_t>& s
         am_leader = am_leader || lead;
         pending &= ~__ballot_sync(0xffffffffu, mine);
     }
-    if (am_leader) label_add<uint16_t>(sh, lt, status, L, tot, gF0, gM0, gS0);
+    if (am_leader) label_add<T>(sh, lt, status, L, tot, gF0, gM0, gS0);
 }
-__device__ __forceinline__ void block_merge_pair(const BrickShared<uint16_t>& sh, const PairTable& pt, uint32_t key,
+template <typename T>
+__device__ __forceinline__ void block_merge_pair(const BrickShared<T>& sh, const PairTable& pt, typename Vox<T>::PKey key,
                                                  const uint32_t inc[PT_WORDS], int lane) {
-    unsigned pending = __ballot_sync(0xffffffffu, key != Vox<uint16_t>::PEMPTY);
+    unsigned pending = __ballot_sync(0xffffffffu, key != Vox<T>::PEMPTY);
     uint32_t tot[PT_WORDS] = {0u, 0u, 0u, 0u};
     bool am_leader = false;
     while (pending) {
         const int leader = __ffs(pending) - 1;
-        const uint32_t kk = __shfl_sync(0xffffffffu, key, leader);
+        const typename Vox<T>::PKey kk = __shfl_sync(0xffffffffu, key, leader);
         const bool mine = (key == kk);
 #pragma unroll
         for (int w = 0; w < PT_WORDS; ++w) {
@@ -139,17 +144,16 @@ __device__ __forceinline__ void block_merge_pair(const BrickShared<uint16_t>& sh
         am_leader = am_leader || (lane == leader);
         pending &= ~__ballot_sync(0xffffffffu, mine);
     }
-    if (am_leader) pair_add_packed<uint16_t>(sh, pt, key, tot);
+    if (am_leader) pair_add_packed<T>(sh, pt, key, tot);
 }
 
 // MERGE = true: slot-wise uniform loops with warp merges (flag 0x4000); false: plain atomics per block (0x4000 | 0x8000),
 // kept as the simpler form to bisect against.
-template <bool MERGE>
+template <typename T, bool MERGE>
 __global__ void __launch_bounds__(NTHREADS, 3)
 scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
-    typedef uint16_t T;
-    typedef Vox<T>::PKey PKey;
-    constexpr int SEG = 8, ROWE = ROWV * SEG, BF = NFS * SEG;
+    typedef typename Vox<T>::PKey PKey;
+    constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG, BF = NFS * SEG;
     static_assert(NTHREADS == NFS * (BM / BLK_M) * (BS / BLK_S), "one block per thread");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -252,8 +256,13 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < SEG; ++j) tmp[j] = row[min(max(gf + j, 0), nf - 1)];
                 uint4 v;
-                v.x = (uint32_t)tmp[0] | ((uint32_t)tmp[1] << 16); v.y = (uint32_t)tmp[2] | ((uint32_t)tmp[3] << 16);
-                v.z = (uint32_t)tmp[4] | ((uint32_t)tmp[5] << 16); v.w = (uint32_t)tmp[6] | ((uint32_t)tmp[7] << 16);
+                if (SEG == 8) {
+                    v.x = (uint32_t)tmp[0] | ((uint32_t)tmp[1] << 16); v.y = (uint32_t)tmp[2] | ((uint32_t)tmp[3] << 16);
+                    v.z = (uint32_t)tmp[4 % SEG] | ((uint32_t)tmp[5 % SEG] << 16);
+                    v.w = (uint32_t)tmp[6 % SEG] | ((uint32_t)tmp[7 % SEG] << 16);
+                } else {
+                    v.x = tmp[0]; v.y = tmp[1]; v.z = tmp[2 % SEG]; v.w = tmp[3 % SEG];
+                }
                 sh.tile[i] = v;
             }
         }
@@ -263,12 +272,13 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         const uint32_t ref_label = tileT[SEG];
         bool all_ref = true;
         {
-            const uint32_t pat = ref_label * 0x00010001u;
+            const uint32_t pat = (SEG == 8) ? ref_label * 0x00010001u : ref_label;
             for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
                 const int fsv = i % ROWV;
                 const uint4 v = sh.tile[i];
-                if (fsv == 0) all_ref = all_ref && ((v.w >> 16) == ref_label);               // only the lane beside the brick
-                else if (fsv == ROWV - 1) all_ref = all_ref && ((v.x & 0xFFFFu) == ref_label);
+                // halo segments: only the lane beside the brick
+                if (fsv == 0) all_ref = all_ref && (((SEG == 8) ? (v.w >> 16) : v.w) == ref_label);
+                else if (fsv == ROWV - 1) all_ref = all_ref && (((SEG == 8) ? (v.x & 0xFFFFu) : v.x) == ref_label);
                 else all_ref = all_ref && (v.x == pat) && (v.y == pat) && (v.z == pat) && (v.w == pat);
             }
         }
