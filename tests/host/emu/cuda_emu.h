@@ -65,13 +65,29 @@ inline std::function<void()> g_kernel;
 
 inline void yield() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
 
+// Operation counts of the emulated launches (cost indicators, not instruction counts): collectives are counted once per
+// warp / block, atomics once per calling thread and by address space.
+struct Stats {
+    unsigned long long syncthreads = 0, ballot = 0, shfl = 0, redux = 0, syncwarp = 0, atom_shared = 0, atom_global = 0;
+    void clear() { *this = Stats(); }
+};
+inline Stats g_stats;
+inline const unsigned char* g_smem_lo = nullptr;
+inline const unsigned char* g_smem_hi = nullptr;      // set by the harness: [lo, hi) is the block's shared memory
+inline void count_atomic(const void* p) {
+    const unsigned char* q = (const unsigned char*)p;
+    if (q >= g_smem_lo && q < g_smem_hi) ++g_stats.atom_shared; else ++g_stats.atom_global;
+}
+
 // Every participant calls with its value; `compute(vals, results, n)` runs once, in the last arriver.
 template <typename F>
-inline unsigned long long rendezvous(Rendezvous& r, int slot, int n, unsigned long long v, F compute) {
+inline unsigned long long rendezvous(Rendezvous& r, int slot, int n, unsigned long long v, F compute,
+                                     unsigned long long* counter = nullptr) {
     const unsigned my_gen = r.gen;
     r.val[slot] = v;
     g_progress = true;
     if (++r.arrived == n) {
+        if (counter) ++*counter;
         compute(r.val, r.res[my_gen & 1u], n);
         r.arrived = 0;
         ++r.gen;
@@ -138,7 +154,8 @@ inline bool run_block(unsigned block, unsigned grid, int nthreads, std::function
 #define TA_PTX(...) ((void)0)                      /* inline PTX: only on paths the emulation does not take */
 
 inline void __syncthreads() {
-    emu::rendezvous(emu::g_block, emu::g_cur, emu::g_nthreads, 0ull, [](unsigned long long*, unsigned long long*, int) {});
+    emu::rendezvous(emu::g_block, emu::g_cur, emu::g_nthreads, 0ull, [](unsigned long long*, unsigned long long*, int) {},
+                    &emu::g_stats.syncthreads);
 }
 inline int __syncthreads_and(int pred) {
     return (int)emu::rendezvous(emu::g_block, emu::g_cur, emu::g_nthreads, pred ? 1ull : 0ull,
@@ -146,14 +163,15 @@ inline int __syncthreads_and(int pred) {
                                     unsigned long long all = 1ull;
                                     for (int i = 0; i < n; ++i) all &= v[i];
                                     for (int i = 0; i < n; ++i) r[i] = all;
-                                });
+                                }, &emu::g_stats.syncthreads);
 }
 inline void emu_check_mask(unsigned mask) {
     if (mask != 0xffffffffu) { fprintf(stderr, "emu: only full-mask warp collectives are emulated\n"); abort(); }
 }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
     emu_check_mask(mask);
-    emu::rendezvous(emu::my_warp(), emu::lane(), emu::warp_size_here(), 0ull, [](unsigned long long*, unsigned long long*, int) {});
+    emu::rendezvous(emu::my_warp(), emu::lane(), emu::warp_size_here(), 0ull, [](unsigned long long*, unsigned long long*, int) {},
+                    &emu::g_stats.syncwarp);
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu_check_mask(mask);
@@ -162,7 +180,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
                                          unsigned long long b = 0;
                                          for (int i = 0; i < n; ++i) b |= (v[i] & 1ull) << i;
                                          for (int i = 0; i < n; ++i) r[i] = b;
-                                     });
+                                     }, &emu::g_stats.ballot);
 }
 template <typename V> inline V __shfl_sync(unsigned mask, V var, int src, int width = 32) {
     emu_check_mask(mask);
@@ -175,7 +193,7 @@ template <typename V> inline V __shfl_sync(unsigned mask, V var, int src, int wi
     const int ln = emu::lane();
     emu::rendezvous(w, ln, emu::warp_size_here(), bits, [](unsigned long long* v, unsigned long long* r, int n) {
         for (int i = 0; i < n; ++i) r[i] = v[i];          // results = a snapshot of all values; picked below per lane
-    });
+    }, &emu::g_stats.shfl);
     // the snapshot of generation g lives in res[g & 1]; read the source lane's entry of the generation just completed
     const unsigned done_gen = w.gen - 1u;
     unsigned long long out = w.res[done_gen & 1u][src & 31];
@@ -198,7 +216,7 @@ template <typename V> inline V __shfl_up_sync(unsigned mask, V var, unsigned del
                                              unsigned a = (init);                                                     \
                                              for (int i = 0; i < n; ++i) { const unsigned b = (unsigned)x[i]; a = (op); } \
                                              for (int i = 0; i < n; ++i) r[i] = a;                                    \
-                                         });                                                                          \
+                                         }, &emu::g_stats.redux);                                                     \
     }
 EMU_REDUX(__reduce_add_sync, 0u, a + b)
 EMU_REDUX(__reduce_min_sync, 0xFFFFFFFFu, (a < b ? a : b))
@@ -206,13 +224,13 @@ EMU_REDUX(__reduce_max_sync, 0u, (a > b ? a : b))
 EMU_REDUX(__reduce_or_sync, 0u, a | b)
 EMU_REDUX(__reduce_and_sync, 0xFFFFFFFFu, a & b)
 
-template <typename V> inline V atomicAdd(V* p, V v) { V o = *p; *p = (V)(o + v); return o; }
-inline unsigned atomicAdd(unsigned* p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
-template <typename V> inline V atomicMin(V* p, V v) { V o = *p; if (v < o) *p = v; return o; }
-template <typename V> inline V atomicMax(V* p, V v) { V o = *p; if (v > o) *p = v; return o; }
-template <typename V> inline V atomicExch(V* p, V v) { V o = *p; *p = v; return o; }
-template <typename V> inline V atomicCAS(V* p, V cmp, V v) { V o = *p; if (o == cmp) *p = v; return o; }
-template <typename V> inline V atomicOr(V* p, V v) { V o = *p; *p = o | v; return o; }
+template <typename V> inline V atomicAdd(V* p, V v) { emu::count_atomic(p); V o = *p; *p = (V)(o + v); return o; }
+inline unsigned atomicAdd(unsigned* p, int v) { emu::count_atomic(p); unsigned o = *p; *p = o + (unsigned)v; return o; }
+template <typename V> inline V atomicMin(V* p, V v) { emu::count_atomic(p); V o = *p; if (v < o) *p = v; return o; }
+template <typename V> inline V atomicMax(V* p, V v) { emu::count_atomic(p); V o = *p; if (v > o) *p = v; return o; }
+template <typename V> inline V atomicExch(V* p, V v) { emu::count_atomic(p); V o = *p; *p = v; return o; }
+template <typename V> inline V atomicCAS(V* p, V cmp, V v) { emu::count_atomic(p); V o = *p; if (o == cmp) *p = v; return o; }
+template <typename V> inline V atomicOr(V* p, V v) { emu::count_atomic(p); V o = *p; *p = o | v; return o; }
 
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }

@@ -136,7 +136,27 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     return 0;
 }
 
+// Operation counts per voxel of the four kernels on a tissue-like volume (cells of ~21 500 voxels as in C3): what the
+// table updates cost in shared-memory atomics and warp collectives.  Not a time; a GPU decides that.
+static void print_stats() {
+    const int nf = 256, nm = 64, nbuf = 32;
+    const int ncell = (int)((double)nf * nm * nbuf / 21500.0 + 0.5);
+    printf("tissue-like volume %d x %d x %d, %d cells; operations per voxel\n", nf, nm, nbuf, ncell);
+    printf("%-28s %9s %9s %9s %9s %9s %9s\n", "kernel", "atom.smem", "atom.glob", "redux/w", "ballot/w", "shfl/w", "bar/blk");
+    for (int w = 0; w < 4; ++w) {
+        emu::g_stats.clear();
+        const int bad = run_case<uint16_t>((Which)w, nf, nm, nbuf, 0, nbuf, 0, ncell, 1, 12345u);
+        const double nv = (double)nf * nm * nbuf;
+        const emu::Stats& s = emu::g_stats;
+        printf("%-28s %9.4f %9.4f %9.4f %9.4f %9.4f %9.5f%s\n", which_name[w], s.atom_shared / nv, s.atom_global / nv, s.redux / nv,
+               s.ballot / nv, s.shfl / nv, s.syncthreads / nv, bad ? "  (MISMATCH)" : "");
+    }
+}
+
 int main(int argc, char** argv) {
+    emu::g_smem_lo = ta::smem_raw;
+    emu::g_smem_hi = ta::smem_raw + sizeof ta::smem_raw;
+    if (argc > 1 && !strcmp(argv[1], "--stats")) { print_stats(); return 0; }
     std::mt19937 rng(argc > 1 ? (unsigned)atoi(argv[1]) : 1u);
     const int ncases = argc > 2 ? atoi(argv[2]) : 24;
     int bad = 0, ran = 0;
