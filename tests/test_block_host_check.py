@@ -36,3 +36,18 @@ def test_block_pass_over_whole_volumes_on_the_host(tmp_path):
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 mismatching volumes" in r.stdout
+
+
+def test_level_formulation_over_whole_volumes_on_the_host(tmp_path):
+    """The level formulation (window min / max, fused masks of the known labels, what each level adds, restricted
+    per-voxel fallback) for both label widths and 2 .. 5 levels == a direct pass."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "block_level_check")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", exe,
+                    os.path.join(HERE, "host", "block_level_check.cu")], check=True, capture_output=True, timeout=600)
+    for seed in (1, 2):
+        r = subprocess.run([exe, str(seed)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert " 0 mismatching volumes" in r.stdout

@@ -296,6 +296,248 @@ template <typename T, int MAXLAB> struct BlockSlots {
     }
 };
 
+// ---- level formulation ----------------------------------------------------------------------------------------------
+// The discovery loop of BlockSlots costs every lane of a warp as many mask builds as the most crowded block of the warp
+// holds labels (measured warp maximum 3.98 against a lane mean of 1.85, tools/simt_stats.py).  The level formulation
+// makes the label count a property of a LIST instead of a lane:
+//
+//   level 1   min / max label over the window (one pass over its 24 rows).  min == max: the window is one label, the
+//             block contributes closed-form moments and nothing else.  Otherwise the block goes to list 2 with the two
+//             labels (both ARE labels of the window).
+//   level N   (N = 2, 3, ...) for the blocks of list N, N labels known: ONE fused pass over the rows builds the N masks
+//             (row loads shared between the labels).  Emitted: for N = 2 the moments of both labels and their pair; for
+//             N > 2 the moments of the newest label and its pairs with the N - 1 older ones -- exactly what the earlier
+//             levels could not know.  Window positions covered by none of the N labels name label N + 1: list N + 1.
+//   fallback  blocks still uncovered after the last level take the per-voxel path for everything that involves a label
+//             outside their known set S (moments of voxels not in S, pairs with at least one side not in S); all
+//             S-internal contributions were emitted by the levels.
+//
+// Every list is processed by full warps of blocks with the same label count, so the cost follows the mean of the label
+// count distribution, not the warp maximum.  tests/host/block_level_check.cu runs this on the CPU against a direct pass.
+TA_HD uint32_t ta_vmaxu2(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __vmaxu2(a, b);
+#else
+    const uint32_t l = (a & 0xFFFFu) > (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
+    const uint32_t h = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+    return l | (h << 16);
+#endif
+}
+// keeps the row loads of one half plane from being hoisted above the arithmetic of the previous one (register pressure)
+TA_HD void block_sched_fence() {
+#ifdef __CUDA_ARCH__
+    TA_PTX("" ::: "memory");
+#endif
+}
+
+// Smallest and largest label of the window whose first row (m0 - 1, s0 - 1) is vector t0.
+template <typename T> TA_HD void block_window_minmax(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi);
+template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int p = 0; p < BLK_S + 2; ++p) {
+#pragma unroll
+        for (int r = 0; r < BLK_M + 2; ++r) {
+            const int t = t0 + p * PLANEV + r * ROWV;
+            const uint4 c = tile[t];
+            const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
+            const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16);
+            mn = ta_vminu2(ta_vminu2(ta_vminu2(mn, c.x), ta_vminu2(c.y, c.z)), ta_vminu2(c.w, ew));
+            mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(mx, c.x), ta_vmaxu2(c.y, c.z)), ta_vmaxu2(c.w, ew));
+        }
+        block_sched_fence();
+    }
+    lo = (mn & 0xFFFFu) < (mn >> 16) ? (mn & 0xFFFFu) : (mn >> 16);
+    hi = (mx & 0xFFFFu) > (mx >> 16) ? (mx & 0xFFFFu) : (mx >> 16);
+}
+template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int p = 0; p < BLK_S + 2; ++p) {
+#pragma unroll
+        for (int r = 0; r < BLK_M + 2; ++r) {
+            const int t = t0 + p * PLANEV + r * ROWV;
+            const uint4 c = tile[t];
+            const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
+            const uint32_t a = e[-1], b = e[4];
+            const uint32_t n1 = c.x < c.y ? c.x : c.y, n2 = c.z < c.w ? c.z : c.w, n3 = a < b ? a : b;
+            const uint32_t x1 = c.x > c.y ? c.x : c.y, x2 = c.z > c.w ? c.z : c.w, x3 = a > b ? a : b;
+            const uint32_t n12 = n1 < n2 ? n1 : n2, x12 = x1 > x2 ? x1 : x2;
+            const uint32_t n = n12 < n3 ? n12 : n3, x = x12 > x3 ? x12 : x3;
+            mn = mn < n ? mn : n;
+            mx = mx > x ? mx : x;
+        }
+        block_sched_fence();
+    }
+    lo = mn; hi = mx;
+}
+
+// NOT-equal bits of one window row (vector index t of its segment) against N labels at once: out[i] bit x (0 .. SEG + 1,
+// the positions of block_row_mask) is set where the voxel differs from label i.  The row is loaded once for all labels.
+template <typename T, int N> struct BlockRowNeq;
+template <int N> struct BlockRowNeq<uint16_t, N> {
+    static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
+        const uint4 c = tile[t];
+        const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
+        const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16), one = 0x00010001u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t pat = L[i] * 0x00010001u;
+            const uint32_t tt = ta_vminu2(c.x ^ pat, one) | (ta_vminu2(c.y ^ pat, one) << 2) | (ta_vminu2(c.z ^ pat, one) << 4) |
+                                (ta_vminu2(c.w ^ pat, one) << 6);
+            const uint32_t te = ta_vminu2(ew ^ pat, one);              // bit 0: lane left of the segment, bit 16: right of it
+            out[i] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
+        }
+    }
+};
+template <int N> struct BlockRowNeq<uint32_t, N> {
+    static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
+        const uint4 c = tile[t];
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
+        const uint32_t a = e[-1], b = e[4];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t l = L[i];
+            out[i] = (a != l ? 1u : 0u) | (c.x != l ? 2u : 0u) | (c.y != l ? 4u : 0u) | (c.z != l ? 8u : 0u) |
+                     (c.w != l ? 16u : 0u) | (b != l ? 32u : 0u);
+        }
+    }
+};
+
+// Packed row moments for the table form of the moments: n [0..9] | sum x [10..20] | sum x^2 [21..31] of the set bits of
+// a byte.  The field widths hold every weighted sum over the 8 rows of a block (weights r <= 3, r^2 <= 9).
+TA_HD uint32_t block_byte_moments_packed(uint32_t b) {
+    const uint32_t t = block_byte_moments(b);
+    return (t & 0xFFu) | (((t >> 8) & 0xFFu) << 10) | ((t >> 16) << 21);
+}
+
+// Closed-form sums and box of a one-label block with a x b x c voxels inside the volume (block-local coordinates).
+TA_HD void block_uniform_moments(uint32_t a, uint32_t b, uint32_t c, uint32_t v[16]) {
+    const uint32_t ta_ = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
+    const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6, qc = (c - 1) * c * (2 * c - 1) / 6;
+    v[0] = a * b * c; v[1] = b * c * ta_; v[2] = a * c * tb; v[3] = a * b * tc;
+    v[4] = b * c * qa; v[5] = c * ta_ * tb; v[6] = b * ta_ * tc; v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
+    v[10] = 0u; v[11] = 0u; v[12] = 0u; v[13] = a - 1u; v[14] = b - 1u; v[15] = c - 1u;
+}
+
+// N known labels of one block: window masks, dilations, coverage.
+template <typename T, int N> struct BlockLevel {
+    uint32_t lab[N];
+    u64 M1[N], M2[N], M3[N], D0[N], D1[N];
+    u64 cv0, cv1;             // centre voxels inside the volume, planes 1 and 2 of the window
+
+    TA_HD void clear() {
+        cv0 = cv1 = 0ull;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { lab[i] = 0u; M1[i] = M2[i] = M3[i] = D0[i] = D1[i] = 0ull; }
+    }
+
+    // L[0 .. N - 1]: distinct labels.  true: they cover the window; false: `next` = a label of the window that is none
+    // of them (the label at the first uncovered position).
+    TA_HD bool build(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, const uint32_t* L, uint32_t& next) {
+        constexpr int SEG = Blk<T>::SEG, ROWBITS = Blk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
+        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
+        u64 neq[N][BLK_S + 2];
+#pragma unroll
+        for (int p = 0; p < BLK_S + 2; ++p) {
+            uint32_t half[N][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) half[i][h] = 0u;
+#pragma unroll
+                for (int r = HALF - 1; r >= 0; --r) {                  // descending: acc = (acc << ROWBITS) + row
+                    uint32_t row[N];
+                    BlockRowNeq<T, N>::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) half[i][h] = (half[i][h] << ROWBITS) + row[i];
+                }
+                block_sched_fence();
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) neq[i][p] = (u64)half[i][0] | ((u64)half[i][1] << (ROWBITS * HALF));
+        }
+        u64 r0 = ALL, r1 = ALL, r2 = ALL, r3 = ALL;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            r0 &= neq[i][0]; r1 &= neq[i][1]; r2 &= neq[i][2]; r3 &= neq[i][3];
+            u64 m[4], d[2];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) m[p] = ~neq[i][p] & ALL;
+            block_dilate18<T>(m, d);
+            lab[i] = L[i]; M1[i] = m[1]; M2[i] = m[2]; M3[i] = m[3]; D0[i] = d[0]; D1[i] = d[1];
+        }
+        u64 cv = 0ull;
+#pragma unroll
+        for (int r = 1; r <= BLK_M; ++r)
+            if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (ROWBITS * r);
+        cv0 = nvs >= 1 ? cv : 0ull;
+        cv1 = nvs >= 2 ? cv : 0ull;
+        if (!(r0 | r1 | r2 | r3)) return true;
+        const int p = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
+        const u64 rp = r0 ? r0 : r1 ? r1 : r2 ? r2 : r3;
+        const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
+        next = reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
+        return false;
+    }
+
+    // moments and box of label i over its centre voxels, block-local coordinates; `tab` = block_byte_moments_packed of
+    // every byte (256 entries, shared memory in the kernel).  false: no centre voxel.
+    TA_HD bool label_moments(int i, const uint32_t* tab, uint32_t v[16]) const {
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        const u64 c0 = M1[i] & cv0, c1 = M2[i] & cv1;
+        if (!(c0 | c1)) return false;
+        uint32_t a0 = 0u, a1 = 0u, a2 = 0u, ap = 0u, apm = 0u, colmask = 0u, rows = 0u;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int r = 0; r < BLK_M; ++r) {
+                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
+                const uint32_t t = tab[b];
+                a0 += t; a1 += (uint32_t)r * t; a2 += (uint32_t)(r * r) * t;
+                if (p) { ap += t; apm += (uint32_t)r * t; }
+                colmask |= b;
+                rows |= b ? (1u << (p * BLK_M + r)) : 0u;
+            }
+        const uint32_t mrows = (rows | (rows >> BLK_M)) & ((1u << BLK_M) - 1u);
+        v[0] = a0 & 0x3FFu; v[1] = (a0 >> 10) & 0x7FFu; v[2] = a1 & 0x3FFu; v[3] = ap & 0x3FFu;
+        v[4] = a0 >> 21; v[5] = (a1 >> 10) & 0x7FFu; v[6] = (ap >> 10) & 0x7FFu; v[7] = a2 & 0x3FFu;
+        v[8] = apm & 0x3FFu; v[9] = v[3];
+        v[10] = (uint32_t)ta_ffs(colmask) - 1u; v[11] = (uint32_t)ta_ffs(mrows) - 1u;
+        v[12] = (rows & ((1u << BLK_M) - 1u)) ? 0u : 1u;
+        uint32_t ftop = Blk<T>::SEG - 1, mtop = BLK_M - 1;
+        while (!((colmask >> ftop) & 1u)) --ftop;
+        while (!((mrows >> mtop) & 1u)) --mtop;
+        v[13] = ftop; v[14] = mtop; v[15] = (rows >> BLK_M) ? 1u : 0u;
+        return true;
+    }
+
+    // both directions of the unordered pair (i, j) as packed increments of the per-brick pair table
+    // ([w18|f0] [f1|f2] [f3|f4] [f5|-]: a face goes to slot 2k when its lower-index voxel carries the smaller label)
+    TA_HD bool pair_increments(int i, int j, bool do_p6, bool do_w18, uint32_t inc[4]) const {
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        const u64 ci0 = M1[i] & cv0, ci1 = M2[i] & cv1, cj0 = M1[j] & cv0, cj1 = M2[j] & cv1;
+        uint32_t w18 = 0u, fi[3] = {0u, 0u, 0u}, fj[3] = {0u, 0u, 0u};
+        if (do_w18)
+            w18 = ta_popc64(ci0 & D0[j]) + ta_popc64(ci1 & D1[j]) + ta_popc64(cj0 & D0[i]) + ta_popc64(cj1 & D1[i]);
+        if (do_p6) {
+            fi[0] = ta_popc64(ci0 & (M1[j] >> 1)) + ta_popc64(ci1 & (M2[j] >> 1));
+            fi[1] = ta_popc64(ci0 & (M1[j] >> ROWBITS)) + ta_popc64(ci1 & (M2[j] >> ROWBITS));
+            fi[2] = ta_popc64(ci0 & M2[j]) + ta_popc64(ci1 & M3[j]);
+            fj[0] = ta_popc64(cj0 & (M1[i] >> 1)) + ta_popc64(cj1 & (M2[i] >> 1));
+            fj[1] = ta_popc64(cj0 & (M1[i] >> ROWBITS)) + ta_popc64(cj1 & (M2[i] >> ROWBITS));
+            fj[2] = ta_popc64(cj0 & M2[i]) + ta_popc64(cj1 & M3[i]);
+        }
+        const bool ilo = lab[i] < lab[j];            // faces seen from the smaller label go to the even slots
+        const uint32_t e0 = ilo ? fi[0] : fj[0], o0 = ilo ? fj[0] : fi[0];
+        const uint32_t e1 = ilo ? fi[1] : fj[1], o1 = ilo ? fj[1] : fi[1];
+        const uint32_t e2 = ilo ? fi[2] : fj[2], o2 = ilo ? fj[2] : fi[2];
+        inc[0] = w18 | (e0 << 16); inc[1] = o0 | (e1 << 16); inc[2] = o1 | (e2 << 16); inc[3] = o2;
+        return (inc[0] | inc[1] | inc[2] | inc[3]) != 0u;
+    }
+};
+
 // block_features on top of BlockSlots: same callbacks and results as the reference form above.
 template <typename T, int MAXLAB, typename OnLabel, typename OnPair>
 TA_HD bool block_features_reg(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, OnLabel&& on_label,
