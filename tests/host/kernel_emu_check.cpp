@@ -1,13 +1,14 @@
 // Runs the scan kernels THEMSELVES on the CPU (tests/host/emu/cuda_emu.h: fibers for threads, rendezvous for the warp and
 // block collectives) and compares the tables they fill with a direct pass over the voxels.  Covered: the product kernel
-// scan_kernel<T, false, false> (march, worklists, per-voxel pair phases, flush), its one-hot instantiation, and the
-// experimental block kernels of ta_scan_block.cuh with and without warp merges -- on the scalar staging path (vec_ok = 0,
-// use_tma = 0: the only path without inline PTX).  Test infrastructure: g++ only, no GPU, no nvcc.
+// scan_kernel<T, false, false> (march, worklists, per-voxel pair phases, flush), its one-hot instantiation, the
+// experimental block kernels of ta_scan_block.cuh and the level kernels of ta_scan_level.cuh, each with and without warp
+// merges -- on the scalar staging path (vec_ok = 0, use_tma = 0: the only path without inline PTX).  Test infrastructure: g++ only, no GPU, no nvcc.
 // Usage: kernel_emu_check <seed> ; exit code 0 = every case equal.
 #include "emu/cuda_emu.h"
 
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
 
@@ -47,9 +48,9 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
         if (nb[k] != a) pt[{std::min(a, nb[k]), std::max(a, nb[k])}][2 * k + (a < nb[k] ? 0 : 1)] += 1;
 }
 
-enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE };
+enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, NWHICH };
 static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
-                                   "scan_block_kernel<T,false>"};
+                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -107,7 +108,9 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
             if (which == PRODUCT) scan_kernel<T, false, false>(P, lt, pt, tmap);
             else if (which == ONEHOT) scan_kernel<T, true, false>(P, lt, pt, tmap);
             else if (which == BLOCK_MERGE) scan_block_kernel<T, true>(P, lt, pt, tmap);
-            else scan_block_kernel<T, false>(P, lt, pt, tmap);
+            else if (which == BLOCK_SIMPLE) scan_block_kernel<T, false>(P, lt, pt, tmap);
+            else if (which == LEVEL_MERGE) scan_level_kernel<T, true>(P, lt, pt, tmap);
+            else scan_level_kernel<T, false>(P, lt, pt, tmap);
         });
     }
     LabelTab gotL; PairTab gotP;
@@ -136,14 +139,14 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     return 0;
 }
 
-// Operation counts per voxel of the four kernels on a tissue-like volume (cells of ~21 500 voxels as in C3): what the
+// Operation counts per voxel of the six kernels on a tissue-like volume (cells of ~21 500 voxels as in C3): what the
 // table updates cost in shared-memory atomics and warp collectives.  Not a time; a GPU decides that.
 static void print_stats() {
     const int nf = 256, nm = 64, nbuf = 32;
     const int ncell = (int)((double)nf * nm * nbuf / 21500.0 + 0.5);
     printf("tissue-like volume %d x %d x %d, %d cells; operations per voxel\n", nf, nm, nbuf, ncell);
     printf("%-28s %9s %9s %9s %9s %9s %9s\n", "kernel", "atom.smem", "atom.glob", "redux/w", "ballot/w", "shfl/w", "bar/blk");
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < NWHICH; ++w) {
         emu::g_stats.clear();
         const int bad = run_case<uint16_t>((Which)w, nf, nm, nbuf, 0, nbuf, 0, ncell, 1, 12345u);
         const double nv = (double)nf * nm * nbuf;
@@ -158,17 +161,17 @@ int main(int argc, char** argv) {
     emu::g_smem_hi = ta::smem_raw + sizeof ta::smem_raw;
     if (argc > 1 && !strcmp(argv[1], "--stats")) { print_stats(); return 0; }
     std::mt19937 rng(argc > 1 ? (unsigned)atoi(argv[1]) : 1u);
-    const int ncases = argc > 2 ? atoi(argv[2]) : 24;
+    const int ncases = argc > 2 ? atoi(argv[2]) : 36;
     int bad = 0, ran = 0;
     for (int c = 0; c < ncases; ++c) {
-        const Which which = (Which)(c % 4);
-        const bool wide = (c / 4) % 3 == 2;                                   // every third round: uint32 labels
+        const Which which = (Which)(c % NWHICH);
+        const bool wide = (c / NWHICH) % 3 == 2;                                   // every third round: uint32 labels
         const int maxf = wide ? 150 : 300;
         const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
         int lo = 0, hi = nbuf; long off = 0;
         if (c % 5 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }
         // c % 11 == 3: hundreds of labels in noise -- the per-brick label and pair tables fill up and spill to the global ones
-        const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = (c % 3 == 0 || c % 11 == 3) ? 0 : 1;
+        const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = ((c / NWHICH) % 2 == 0 || c % 11 == 3) ? 0 : 1;
         const unsigned seed = rng();
         bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed)
                     : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed);

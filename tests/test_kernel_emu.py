@@ -2,8 +2,8 @@
 collectives are rendezvous points, atomics are plain) against a direct pass over the voxels.
 
 Covers the source of the product kernel scan_kernel<T, false, false> for uint16 and uint32 (march, worklists, per-voxel
-pair phases, flush, slab ownership, ragged bricks), its one-hot instantiation, and the experimental block kernels with and
-without warp merges -- on the scalar staging path (vec_ok = 0, use_tma = 0), the only one without inline PTX.  g++ only.
+pair phases, flush, slab ownership, ragged bricks), its one-hot instantiation, the experimental block kernels and the
+level kernels (ta_scan_level.cuh), each with and without warp merges -- on the scalar staging path (vec_ok = 0, use_tma = 0), the only one without inline PTX.  g++ only.
 The GPU parity tests stay the authority for the compiled kernels; this one finds logic errors without a GPU.
 """
 import os
@@ -24,6 +24,6 @@ def test_scan_kernels_on_the_cpu_emulation(tmp_path):
     subprocess.run([gxx, "-std=c++17", "-O1", "-w", "-I" + inc, "-o", exe, os.path.join(HERE, "host", "kernel_emu_check.cpp")],
                    check=True, capture_output=True, timeout=900)
     for seed in (1, 2):
-        r = subprocess.run([exe, str(seed), "24"], capture_output=True, text=True, timeout=900)
+        r = subprocess.run([exe, str(seed), "36"], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout + r.stderr
         assert " 0 mismatches" in r.stdout

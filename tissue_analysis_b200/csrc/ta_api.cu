@@ -15,6 +15,7 @@
 #include "ta_scan.cuh"
 #ifdef TA_WITH_BLOCK_KERNEL           // experimental, not part of the product build: TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL
 #include "ta_scan_block.cuh"
+#include "ta_scan_level.cuh"
 #endif
 #include "ta_second_pass.cuh"
 
@@ -357,9 +358,14 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
         // product path never depends on it
         typedef void (*block_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
         const bool merge = !(P.flags & 0x8000u);
-        const block_fn fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_block_kernel<uint16_t, true> : (block_fn)ta::scan_block_kernel<uint16_t, false>)
+        block_fn fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_block_kernel<uint16_t, true> : (block_fn)ta::scan_block_kernel<uint16_t, false>)
                                            : (merge ? (block_fn)ta::scan_block_kernel<uint32_t, true> : (block_fn)ta::scan_block_kernel<uint32_t, false>);
-        const size_t bsmem = ctx->elem == 2 ? ta::scan_block_smem_bytes<uint16_t>() : ta::scan_block_smem_bytes<uint32_t>();
+        size_t bsmem = ctx->elem == 2 ? ta::scan_block_smem_bytes<uint16_t>() : ta::scan_block_smem_bytes<uint32_t>();
+        if (P.flags & 0x10000u) {          // level formulation (ta_scan_level.cuh)
+            fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_level_kernel<uint16_t, true> : (block_fn)ta::scan_level_kernel<uint16_t, false>)
+                                : (merge ? (block_fn)ta::scan_level_kernel<uint32_t, true> : (block_fn)ta::scan_level_kernel<uint32_t, false>);
+            bsmem = ctx->elem == 2 ? ta::scan_level_smem_bytes<uint16_t>() : ta::scan_level_smem_bytes<uint32_t>();
+        }
         TA_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
         fn<<<grid, ta::NTHREADS, bsmem, st>>>(P, ctx->lt, ctx->pt, tmap);
         ctx->launches++;
@@ -476,6 +482,8 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
         else if (!strcmp(pp, "block")) P.flags |= 0x4000u;
         else if (!strcmp(pp, "block_simple")) P.flags |= 0x4000u | 0x8000u;
+        else if (!strcmp(pp, "level")) P.flags |= 0x4000u | 0x10000u;
+        else if (!strcmp(pp, "level_simple")) P.flags |= 0x4000u | 0x8000u | 0x10000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {

@@ -31,6 +31,13 @@ template <typename T> struct Blk {
     static constexpr uint32_t LANES = (1u << SEG) - 1u;
 };
 
+TA_HD int ta_fls(uint32_t x) {                  // index of the highest set bit (x != 0)
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
 TA_HD int ta_popc64(u64 x) { return ta_popc((uint32_t)x) + ta_popc((uint32_t)(x >> 32)); }
 TA_HD int ta_ffs64(u64 x) {                    // 1-based index of the lowest set bit, 0 if none
     const uint32_t lo = (uint32_t)x;
@@ -274,10 +281,7 @@ template <typename T, int MAXLAB> struct BlockSlots {
         v[8] = sm1;                  // sum m * s: s is 0 or 1
         v[9] = ss;                   // sum s * s = sum s
         v[10] = (uint32_t)ta_ffs(colmask) - 1u; v[11] = (uint32_t)ta_ffs(mrows) - 1u; v[12] = (rows & ((1u << BLK_M) - 1u)) ? 0u : 1u;
-        uint32_t ftop = Blk<T>::SEG - 1, mtop = BLK_M - 1;
-        while (!((colmask >> ftop) & 1u)) --ftop;
-        while (!((mrows >> mtop) & 1u)) --mtop;
-        v[13] = ftop; v[14] = mtop; v[15] = (rows >> BLK_M) ? 1u : 0u;
+        v[13] = (uint32_t)ta_fls(colmask); v[14] = (uint32_t)ta_fls(mrows); v[15] = (rows >> BLK_M) ? 1u : 0u;
         return true;
     }
 
@@ -506,10 +510,7 @@ template <typename T, int N> struct BlockLevel {
         v[8] = apm & 0x3FFu; v[9] = v[3];
         v[10] = (uint32_t)ta_ffs(colmask) - 1u; v[11] = (uint32_t)ta_ffs(mrows) - 1u;
         v[12] = (rows & ((1u << BLK_M) - 1u)) ? 0u : 1u;
-        uint32_t ftop = Blk<T>::SEG - 1, mtop = BLK_M - 1;
-        while (!((colmask >> ftop) & 1u)) --ftop;
-        while (!((mrows >> mtop) & 1u)) --mtop;
-        v[13] = ftop; v[14] = mtop; v[15] = (rows >> BLK_M) ? 1u : 0u;
+        v[13] = (uint32_t)ta_fls(colmask); v[14] = (uint32_t)ta_fls(mrows); v[15] = (rows >> BLK_M) ? 1u : 0u;
         return true;
     }
 

@@ -31,10 +31,12 @@ template <typename T> constexpr size_t scan_block_smem_bytes() {
            NTHREADS * 2;                        // + the list of blocks that take the per-voxel path
 }
 
+// (The out-of-line functions below take the shared-memory descriptor BY VALUE: a reference would force the kernel's copy
+// into local memory, and every tile access of the kernel would become a generic load instead of LDS.)
 // per-voxel fallback for one voxel of a block whose window holds more labels than slots: moments of the voxel and its
 // pairs by a first-occurrence scan of the 18 neighbours (the rare path of phase D2 of the product kernel)
 template <typename T>
-__device__ __noinline__ void block_fallback_voxel(const BrickShared<T>& sh, const LabelTable& lt, const PairTable& pt,
+__device__ __noinline__ void block_fallback_voxel(const BrickShared<T> sh, const LabelTable lt, const PairTable pt,
                                                   const T* p, uint32_t f, uint32_t m, uint32_t s, u64 gF0, u64 gM0, u64 gS0,
                                                   bool do_mom, bool do_p6, bool do_w18) {
     constexpr int ROWE = ROWV * Vox<T>::SEG, PLANEE = (BM + 2) * ROWE;
@@ -69,7 +71,7 @@ __device__ __noinline__ void block_fallback_voxel(const BrickShared<T>& sh, cons
 // Out-of-line table updates: the block code calls them from up to 4 label slots and 12 ordered slot pairs; inlining
 // every copy multiplies the compile time of this kernel by five for nothing.
 template <typename T>
-__device__ __noinline__ void block_emit_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status,
+__device__ __noinline__ void block_emit_label(const BrickShared<T> sh, const LabelTable lt, uint32_t* status,
                                               uint32_t L, const uint32_t* vin, uint32_t bF, uint32_t bM, uint32_t bS, u64 gF0,
                                               u64 gM0, u64 gS0) {
     uint32_t v[LT_FIELDS];
@@ -79,7 +81,7 @@ __device__ __noinline__ void block_emit_label(const BrickShared<T>& sh, const La
     label_add<T>(sh, lt, status, L, v, gF0, gM0, gS0);
 }
 template <typename T>
-__device__ __noinline__ void block_emit_pair(const BrickShared<T>& sh, const PairTable& pt, uint32_t a, uint32_t b,
+__device__ __noinline__ void block_emit_pair(const BrickShared<T> sh, const PairTable pt, uint32_t a, uint32_t b,
                                              uint32_t w18, uint32_t ff, uint32_t fm, uint32_t fsl) {
     // seen from label a at the lower-index voxel: slot 2k when a is the smaller label, else 2k + 1
     const bool lo = a < b;
@@ -147,6 +149,153 @@ __device__ __forceinline__ void block_merge_pair(const BrickShared<T>& sh, const
     if (am_leader) pair_add_packed<T>(sh, pt, key, tot);
 }
 
+// ---- pieces shared by the block kernels (this file and ta_scan_level.cuh) ----------------------------------------------
+// phase A: the tile (brick + one-voxel halo), as in the product kernel: one TMA box copy, or the scalar path
+template <typename T>
+__device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const ScanParams& P, const CUtensorMap& tmap, uint64_t* tma_bar,
+                                                 uint32_t& tma_parity, bool use_tma, int F0, int M0, int S0, unsigned iter,
+                                                 unsigned int brick, int tid) {
+    constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG, BF = NFS * SEG;
+    const T* vol = reinterpret_cast<const T*>(P.vol);
+    const int nf = (int)P.nf, nm = (int)P.nm, ns = (int)P.ns;
+    if (use_tma) {
+        if (tid == 0) {
+            TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
+            tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
+        }
+        __syncwarp();
+        unsigned spins = 0;
+        while (!mbar_try_wait(tma_bar, tma_parity)) {
+            if (++spins > (1u << 18)) {
+                if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
+                    P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
+                    P.diag[2] = ((u64)iter << 32) | (u64)brick;
+                    __threadfence_system();
+                }
+                __trap();
+            }
+        }
+        tma_parity ^= 1u;
+        const bool edge = (F0 == 0) | (F0 + BF + 1 > nf) | (M0 == 0) | (M0 + BM + 1 > nm) | (S0 < 1) | (S0 + BS + 1 > ns);
+        if (edge) {
+            T* tw = reinterpret_cast<T*>(sh.tile);
+            const int xl = (F0 == 0) ? SEG : 0;
+            const int xr = min(ROWE, nf - F0 + SEG);
+            for (int r = tid; r < TILE_ROWS; r += NTHREADS) {
+                T* row = tw + r * ROWE;
+                if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
+                if (xr < ROWE) { const T v = row[xr - 1]; for (int x = xr; x < ROWE; ++x) row[x] = v; }
+            }
+            __syncthreads();
+            for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+                const int r = i / ROWV, m = r % (BM + 2) - 1;
+                const int mc = min(max(M0 + m, 0), nm - 1) - M0;
+                if (mc != m) sh.tile[i] = sh.tile[i + (mc - m) * ROWV];
+            }
+            __syncthreads();
+            for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+                const int s = i / PLANEV - 1;
+                const int sc = min(max(S0 + s, 0), ns - 1) - S0;
+                if (sc != s) sh.tile[i] = sh.tile[i + (sc - s) * PLANEV];
+            }
+        }
+    } else {
+        for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+            const int fsv = i % ROWV - 1;
+            const int r = i / ROWV;
+            const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
+            const int gs = min(max(S0 + s, 0), ns - 1);
+            const int gm = min(max(M0 + m, 0), nm - 1);
+            const int gf = F0 + fsv * SEG;
+            const T* row = vol + ((size_t)gs * nm + gm) * (size_t)nf;
+            T tmp[SEG];
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) tmp[j] = row[min(max(gf + j, 0), nf - 1)];
+            uint4 v;
+            if (SEG == 8) {
+                v.x = (uint32_t)tmp[0] | ((uint32_t)tmp[1] << 16); v.y = (uint32_t)tmp[2] | ((uint32_t)tmp[3] << 16);
+                v.z = (uint32_t)tmp[4 % SEG] | ((uint32_t)tmp[5 % SEG] << 16);
+                v.w = (uint32_t)tmp[6 % SEG] | ((uint32_t)tmp[7 % SEG] << 16);
+            } else {
+                v.x = tmp[0]; v.y = tmp[1]; v.z = tmp[2 % SEG]; v.w = tmp[3 % SEG];
+            }
+            sh.tile[i] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// one-label tile: closed-form moments, no pairs.  true: the brick is done (all threads agree).
+template <typename T>
+__device__ __forceinline__ bool block_uniform_tile(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
+                                                   int F0, int M0, int S0, u64 gF0, u64 gM0, u64 gS0, int tid) {
+    constexpr int SEG = Vox<T>::SEG, BF = NFS * SEG;
+    const T* tileT = reinterpret_cast<const T*>(sh.tile);
+    const int nf = (int)P.nf, nm = (int)P.nm;
+    const bool do_mom = P.flags & 1u;
+    const uint32_t ref_label = tileT[SEG];
+    bool all_ref = true;
+    {
+        const uint32_t pat = (SEG == 8) ? ref_label * 0x00010001u : ref_label;
+        for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
+            const int fsv = i % ROWV;
+            const uint4 v = sh.tile[i];
+            // halo segments: only the lane beside the brick
+            if (fsv == 0) all_ref = all_ref && (((SEG == 8) ? (v.w >> 16) : v.w) == ref_label);
+            else if (fsv == ROWV - 1) all_ref = all_ref && (((SEG == 8) ? (v.x & 0xFFFFu) : v.x) == ref_label);
+            else all_ref = all_ref && (v.x == pat) && (v.y == pat) && (v.z == pat) && (v.w == pat);
+        }
+    }
+    if (__syncthreads_and(all_ref)) {
+        if (tid == 0 && do_mom) {
+            const uint32_t a = (uint32_t)min(BF, nf - F0), b = (uint32_t)min(BM, nm - M0),
+                           c = (uint32_t)min(BS, (int)P.own_hi - S0);
+            const uint32_t ta = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
+            const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6,
+                           qc = (c - 1) * c * (2 * c - 1) / 6;
+            uint32_t v[LT_FIELDS];
+            v[0] = a * b * c; v[1] = b * c * ta; v[2] = a * c * tb; v[3] = a * b * tc;
+            v[4] = b * c * qa; v[5] = c * ta * tb; v[6] = b * ta * tc;
+            v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
+            v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
+            label_to_global(lt, pt.status, ref_label, v, gF0, gM0, gS0);
+        }
+        return true;
+    }
+    return false;
+}
+
+// flush the per-brick tables to the global ones and clear them (as phase F of the product kernel)
+template <typename T>
+__device__ __forceinline__ void block_flush_tables(const BrickShared<T>& sh, const LabelTable& lt, const PairTable& pt, u64 gF0, u64 gM0,
+                                                   u64 gS0, int tid) {
+    typedef typename Vox<T>::PKey PKey;
+    for (int i = tid; i < LT_SLOTS; i += NTHREADS) {
+        const uint32_t L = sh.lt_key[i];
+        if (L == TA_EMPTY32) continue;
+        uint32_t* d = &sh.lt_val[i * LT_FIELDS];
+        label_to_global(lt, pt.status, L, d, gF0, gM0, gS0);
+#pragma unroll
+        for (int f = 0; f < LT_FIELDS; ++f) d[f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+        sh.lt_key[i] = TA_EMPTY32;
+    }
+    for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
+        const PKey key = sh.pt_key[i];
+        if (key == Vox<T>::PEMPTY) continue;
+        uint32_t* d = &sh.pt_val[i * PT_WORDS];
+        const int slot = ta_pair_slot(pt, Vox<T>::key64(key));
+#pragma unroll
+        for (int idx = 0; idx < 7; ++idx) {
+            const uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+            if (n && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + (idx == 0 ? 6 : idx - 1)], n);
+        }
+#pragma unroll
+        for (int w = 0; w < PT_WORDS; ++w) d[w] = 0u;
+        sh.pt_key[i] = Vox<T>::PEMPTY;
+    }
+}
+
 // MERGE = true: slot-wise uniform loops with warp merges (flag 0x4000); false: plain atomics per block (0x4000 | 0x8000),
 // kept as the simpler form to bisect against.
 template <typename T, bool MERGE>
@@ -200,104 +349,11 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
 
-        // ---- phase A: the tile, as in the product kernel (TODO: share the code once this kernel has run) ---------------
-        if (use_tma) {
-            if (tid == 0) {
-                TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
-                tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
-            }
-            __syncwarp();
-            unsigned spins = 0;
-            while (!mbar_try_wait(tma_bar, tma_parity)) {
-                if (++spins > (1u << 18)) {
-                    if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
-                        P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
-                        P.diag[2] = ((u64)iter << 32) | (u64)brick;
-                        __threadfence_system();
-                    }
-                    __trap();
-                }
-            }
-            tma_parity ^= 1u;
-            const bool edge = (F0 == 0) | (F0 + BF + 1 > nf) | (M0 == 0) | (M0 + BM + 1 > nm) | (S0 < 1) | (S0 + BS + 1 > ns);
-            if (edge) {
-                T* tw = reinterpret_cast<T*>(sh.tile);
-                const int xl = (F0 == 0) ? SEG : 0;
-                const int xr = min(ROWE, nf - F0 + SEG);
-                for (int r = tid; r < TILE_ROWS; r += NTHREADS) {
-                    T* row = tw + r * ROWE;
-                    if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
-                    if (xr < ROWE) { const T v = row[xr - 1]; for (int x = xr; x < ROWE; ++x) row[x] = v; }
-                }
-                __syncthreads();
-                for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-                    const int r = i / ROWV, m = r % (BM + 2) - 1;
-                    const int mc = min(max(M0 + m, 0), nm - 1) - M0;
-                    if (mc != m) sh.tile[i] = sh.tile[i + (mc - m) * ROWV];
-                }
-                __syncthreads();
-                for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-                    const int s = i / PLANEV - 1;
-                    const int sc = min(max(S0 + s, 0), ns - 1) - S0;
-                    if (sc != s) sh.tile[i] = sh.tile[i + (sc - s) * PLANEV];
-                }
-            }
-        } else {
-            for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-                const int fsv = i % ROWV - 1;
-                const int r = i / ROWV;
-                const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
-                const int gs = min(max(S0 + s, 0), ns - 1);
-                const int gm = min(max(M0 + m, 0), nm - 1);
-                const int gf = F0 + fsv * SEG;
-                const T* row = vol + ((size_t)gs * nm + gm) * (size_t)nf;
-                T tmp[SEG];
-#pragma unroll
-                for (int j = 0; j < SEG; ++j) tmp[j] = row[min(max(gf + j, 0), nf - 1)];
-                uint4 v;
-                if (SEG == 8) {
-                    v.x = (uint32_t)tmp[0] | ((uint32_t)tmp[1] << 16); v.y = (uint32_t)tmp[2] | ((uint32_t)tmp[3] << 16);
-                    v.z = (uint32_t)tmp[4 % SEG] | ((uint32_t)tmp[5 % SEG] << 16);
-                    v.w = (uint32_t)tmp[6 % SEG] | ((uint32_t)tmp[7 % SEG] << 16);
-                } else {
-                    v.x = tmp[0]; v.y = tmp[1]; v.z = tmp[2 % SEG]; v.w = tmp[3 % SEG];
-                }
-                sh.tile[i] = v;
-            }
-        }
-        __syncthreads();
+        // ---- phase A: the tile (ends with a block barrier) -------------------------------------------------------------
+        block_stage_tile<T>(sh, P, tmap, tma_bar, tma_parity, use_tma, F0, M0, S0, iter, brick, tid);
 
         // ---- one-label tile: closed-form moments, no pairs ------------------------------------------------------------
-        const uint32_t ref_label = tileT[SEG];
-        bool all_ref = true;
-        {
-            const uint32_t pat = (SEG == 8) ? ref_label * 0x00010001u : ref_label;
-            for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-                const int fsv = i % ROWV;
-                const uint4 v = sh.tile[i];
-                // halo segments: only the lane beside the brick
-                if (fsv == 0) all_ref = all_ref && (((SEG == 8) ? (v.w >> 16) : v.w) == ref_label);
-                else if (fsv == ROWV - 1) all_ref = all_ref && (((SEG == 8) ? (v.x & 0xFFFFu) : v.x) == ref_label);
-                else all_ref = all_ref && (v.x == pat) && (v.y == pat) && (v.z == pat) && (v.w == pat);
-            }
-        }
-        if (__syncthreads_and(all_ref)) {
-            if (tid == 0 && do_mom) {
-                const uint32_t a = (uint32_t)min(BF, nf - F0), b = (uint32_t)min(BM, nm - M0),
-                               c = (uint32_t)min(BS, (int)P.own_hi - S0);
-                const uint32_t ta = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
-                const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6,
-                               qc = (c - 1) * c * (2 * c - 1) / 6;
-                uint32_t v[LT_FIELDS];
-                v[0] = a * b * c; v[1] = b * c * ta; v[2] = a * c * tb; v[3] = a * b * tc;
-                v[4] = b * c * qa; v[5] = c * ta * tb; v[6] = b * ta * tc;
-                v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
-                v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
-                label_to_global(lt, pt.status, ref_label, v, gF0, gM0, gS0);
-            }
-            continue;
-        }
+        if (block_uniform_tile<T>(sh, P, lt, pt, F0, M0, S0, gF0, gM0, gS0, tid)) continue;
 
         // ---- one block per thread ------------------------------------------------------------------------------------------
         if (MERGE) {
@@ -384,29 +440,7 @@ scan_block_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         __syncthreads();
 
         // ---- flush the per-brick tables (as phase F of the product kernel) ---------------------------------------------
-        for (int i = tid; i < LT_SLOTS; i += NTHREADS) {
-            const uint32_t L = sh.lt_key[i];
-            if (L == TA_EMPTY32) continue;
-            uint32_t* d = &sh.lt_val[i * LT_FIELDS];
-            label_to_global(lt, pt.status, L, d, gF0, gM0, gS0);
-#pragma unroll
-            for (int f = 0; f < LT_FIELDS; ++f) d[f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
-            sh.lt_key[i] = TA_EMPTY32;
-        }
-        for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
-            const PKey key = sh.pt_key[i];
-            if (key == Vox<T>::PEMPTY) continue;
-            uint32_t* d = &sh.pt_val[i * PT_WORDS];
-            const int slot = ta_pair_slot(pt, Vox<T>::key64(key));
-#pragma unroll
-            for (int idx = 0; idx < 7; ++idx) {
-                const uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
-                if (n && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + (idx == 0 ? 6 : idx - 1)], n);
-            }
-#pragma unroll
-            for (int w = 0; w < PT_WORDS; ++w) d[w] = 0u;
-            sh.pt_key[i] = Vox<T>::PEMPTY;
-        }
+        block_flush_tables<T>(sh, lt, pt, gF0, gM0, gS0, tid);
         __syncthreads();
     }
 }
