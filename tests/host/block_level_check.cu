@@ -1,8 +1,9 @@
 // CPU check of the LEVEL formulation of the block pass (csrc/ta_block.cuh: block_window_minmax, BlockLevel<T, N>; test
 // infrastructure, no GPU needed).  A volume of several bricks is tiled as the scan kernel tiles it; every 8 x 4 x 2 (uint32:
-// 4 x 4 x 2) block goes through level 1 (window min / max, closed-form moments when they agree), levels 2 .. MAXL (fused
-// masks of the known labels; emitted: what the level adds) and, when labels are still uncovered, the per-voxel fallback
-// restricted to contributions with a label outside the known set.  The global tables must equal a direct pass.
+// 4 x 4 x 2) block goes through level 1 (window min / max, closed-form moments when they agree), level 2 (fused masks of both
+// labels), level 3 (fused masks of three labels) with its extension steps up to MAXL labels (one more mask per step;
+// emitted: what the step adds) and, when labels are still uncovered, the per-voxel fallback restricted to contributions
+// with a label outside the known set.  The global tables must equal a direct pass.
 // Usage: block_level_check <seed> [maxl] ; exit code 0 = every case equal.
 #include <algorithm>
 #include <array>
@@ -84,26 +85,48 @@ struct Sink {
     }
 };
 
-// Levels N .. MAXL of one block.  Returns the number of known labels when the window is covered, -(number known) when
-// labels are still uncovered after the last level.
-template <typename T, int N, int MAXL>
+// Extension steps I .. MAXL - 1 of the level-3 pass: one more label per step (slot I), its moments and its pairs with
+// every older slot.  Returns the number of known labels when the window is covered, -MAXL when it is still not.
+template <typename T, int I, int MAXL>
+static int run_extend(BlockLevel<T, (MAXL > 3 ? MAXL : 3)>& b, const uint4* tile, int fs, int m0, int s0, uint32_t* L, const uint32_t* tab,
+                      const Sink& sink) {
+    if constexpr (I < MAXL) {
+        uint32_t next = 0u, v[16], inc[4];
+        const bool covered = b.template extend<I>(tile, fs, m0, s0, L[I], next);
+        if (b.label_moments(I, tab, v)) sink.label(b.lab[I], v);
+        for (int j = 0; j < I; ++j) if (b.pair_increments(I, j, true, true, inc)) sink.pair(b.lab[I], b.lab[j], inc);
+        if (covered) return I + 1;
+        L[I + 1] = next;
+        return run_extend<T, I + 1, MAXL>(b, tile, fs, m0, s0, L, tab, sink);
+    } else {
+        return -MAXL;
+    }
+}
+
+// Level 2, then (labels left) level 3 with its extension steps, as the kernel runs them.  Returns the number of known
+// labels when the window is covered, -(number known) when labels are still uncovered after the last step.
+template <typename T, int MAXL>
 static int run_levels(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, uint32_t* L, const uint32_t* tab,
                       const Sink& sink) {
-    BlockLevel<T, N> b;
-    uint32_t next = 0u;
-    const bool covered = b.build(tile, fs, m0, s0, nvf, nvm, nvs, L, next);
-    uint32_t v[16], inc[4];
-    if (N == 2) {
+    uint32_t next = 0u, v[16], inc[4];
+    {
+        BlockLevel<T, 2> b;
+        const bool covered = b.template build<2>(tile, fs, m0, s0, nvf, nvm, nvs, L, next);
         for (int i = 0; i < 2; ++i) if (b.label_moments(i, tab, v)) sink.label(b.lab[i], v);
         if (b.pair_increments(0, 1, true, true, inc)) sink.pair(b.lab[0], b.lab[1], inc);
-    } else {
-        if (b.label_moments(N - 1, tab, v)) sink.label(b.lab[N - 1], v);
-        for (int j = 0; j < N - 1; ++j) if (b.pair_increments(N - 1, j, true, true, inc)) sink.pair(b.lab[N - 1], b.lab[j], inc);
+        if (covered) return 2;
+        L[2] = next;
     }
-    if (covered) return N;
-    L[N] = next;
-    if constexpr (N < MAXL) return run_levels<T, N + 1, MAXL>(tile, fs, m0, s0, nvf, nvm, nvs, L, tab, sink);
-    else return -N;
+    if constexpr (MAXL < 3) return -2;
+    else {
+        BlockLevel<T, (MAXL > 3 ? MAXL : 3)> b;
+        const bool covered = b.template build<3>(tile, fs, m0, s0, nvf, nvm, nvs, L, next);
+        if (b.label_moments(2, tab, v)) sink.label(b.lab[2], v);
+        for (int j = 0; j < 2; ++j) if (b.pair_increments(2, j, true, true, inc)) sink.pair(b.lab[2], b.lab[j], inc);
+        if (covered) return 3;
+        L[3] = next;
+        return run_extend<T, 3, MAXL>(b, tile, fs, m0, s0, L, tab, sink);
+    }
 }
 
 template <typename T, int MAXL>
@@ -155,7 +178,7 @@ static int run_case(int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_
                     ++hist[1];
                     continue;
                 }
-                const int k = run_levels<T, 2, MAXL>(tile.data(), fs, m0, s0, nvf, nvm, nvs, L, tab, sink);
+                const int k = run_levels<T, MAXL>(tile.data(), fs, m0, s0, nvf, nvm, nvs, L, tab, sink);
                 if (k > 0) { ++hist[k]; continue; }
                 ++hist[0];            // uncovered after the last level: everything that involves a label outside L[0 .. MAXL - 1]
                 for (int ds = 0; ds < nvs; ++ds) for (int dm = 0; dm < nvm; ++dm) for (int df = 0; df < nvf; ++df)
@@ -186,7 +209,7 @@ int main(int argc, char** argv) {
             case 1: bad += run_case<uint32_t, 4>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
             case 2: bad += run_case<uint16_t, 2>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
             case 3: bad += run_case<uint32_t, 3>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
-            case 4: bad += run_case<uint16_t, 5>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
+            case 4: bad += run_case<uint16_t, 6>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
             default: bad += run_case<uint32_t, 5>(nf, nm, nbuf, lo, hi, off, nl, mode, seed, hist); break;
         }
     }

@@ -63,6 +63,8 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     if (sizeof(T) == 2 && nlabels >= 3 && (seed & 1u)) names[1] = 0xFFFFu;      // the uint16 value that doubles as the MIXED code
     if (mode == 0) {
         for (auto& v : V.d) v = names[rng() % nlabels];
+    } else if (mode == 2) {          // one label almost everywhere: every lane of a warp carries a nearly full block of it
+        for (auto& v : V.d) v = names[rng() % 97 == 0 ? rng() % nlabels : 0];
     } else {
         std::vector<int> sx(nlabels), sy(nlabels), sz(nlabels);
         for (int k = 0; k < nlabels; ++k) { sx[k] = rng() % nf; sy[k] = rng() % nm; sz[k] = rng() % nbuf; }
@@ -171,7 +173,7 @@ int main(int argc, char** argv) {
         int lo = 0, hi = nbuf; long off = 0;
         if (c % 5 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }
         // c % 11 == 3: hundreds of labels in noise -- the per-brick label and pair tables fill up and spill to the global ones
-        const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = ((c / NWHICH) % 2 == 0 || c % 11 == 3) ? 0 : 1;
+        const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = c % 13 == 5 ? 2 : ((c / NWHICH) % 2 == 0 || c % 11 == 3) ? 0 : 1;
         const unsigned seed = rng();
         bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed)
                     : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed);

@@ -424,25 +424,24 @@ TA_HD void block_uniform_moments(uint32_t a, uint32_t b, uint32_t c, uint32_t v[
     v[10] = 0u; v[11] = 0u; v[12] = 0u; v[13] = a - 1u; v[14] = b - 1u; v[15] = c - 1u;
 }
 
-// N known labels of one block: window masks, dilations, coverage.
-template <typename T, int N> struct BlockLevel {
-    uint32_t lab[N];
-    u64 M1[N], M2[N], M3[N], D0[N], D1[N];
+// Up to CAP known labels of one block: window masks, dilations, coverage.  build<N0>() fills slots 0 .. N0 - 1 in one
+// fused pass over the window rows; extend<I>() adds slot I for one more label (the rare labels 4, 5, ... of a block).
+template <typename T, int CAP> struct BlockLevel {
+    uint32_t lab[CAP];
+    u64 M1[CAP], M2[CAP], M3[CAP], D0[CAP], D1[CAP];
     u64 cv0, cv1;             // centre voxels inside the volume, planes 1 and 2 of the window
+    u64 R0, R1, R2, R3;       // window positions covered by none of the labels so far
 
     TA_HD void clear() {
-        cv0 = cv1 = 0ull;
+        cv0 = cv1 = 0ull; R0 = R1 = R2 = R3 = 0ull;
 #pragma unroll
-        for (int i = 0; i < N; ++i) { lab[i] = 0u; M1[i] = M2[i] = M3[i] = D0[i] = D1[i] = 0ull; }
+        for (int i = 0; i < CAP; ++i) { lab[i] = 0u; M1[i] = M2[i] = M3[i] = D0[i] = D1[i] = 0ull; }
     }
+    template <int I> TA_HD void clear_slot() { lab[I] = 0u; M1[I] = M2[I] = M3[I] = D0[I] = D1[I] = 0ull; }
 
-    // L[0 .. N - 1]: distinct labels.  true: they cover the window; false: `next` = a label of the window that is none
-    // of them (the label at the first uncovered position).
-    TA_HD bool build(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, const uint32_t* L, uint32_t& next) {
-        constexpr int SEG = Blk<T>::SEG, ROWBITS = Blk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
-        constexpr u64 ALL = Blk<T>::PLANE_ALL;
-        const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
-        u64 neq[N][BLK_S + 2];
+    // NOT-equal planes of N labels, one fused pass: neq[i][p]
+    template <int N> static TA_HD void neq_planes(const uint4* tile, int t0, const uint32_t* L, u64 neq[][BLK_S + 2]) {
+        constexpr int ROWBITS = Blk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
 #pragma unroll
         for (int p = 0; p < BLK_S + 2; ++p) {
             uint32_t half[N][2];
@@ -462,27 +461,64 @@ template <typename T, int N> struct BlockLevel {
 #pragma unroll
             for (int i = 0; i < N; ++i) neq[i][p] = (u64)half[i][0] | ((u64)half[i][1] << (ROWBITS * HALF));
         }
-        u64 r0 = ALL, r1 = ALL, r2 = ALL, r3 = ALL;
+    }
+    // first uncovered position -> its label
+    TA_HD uint32_t first_uncovered(const uint4* tile, int t0) const {
+        constexpr int SEG = Blk<T>::SEG, ROWBITS = Blk<T>::ROWBITS;
+        const int p = R0 ? 0 : R1 ? 1 : R2 ? 2 : 3;
+        const u64 rp = R0 ? R0 : R1 ? R1 : R2 ? R2 : R3;
+        const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
+        return reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
+    }
+    template <int I> TA_HD void set_slot(uint32_t L, const u64 neq[BLK_S + 2]) {
+        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        R0 &= neq[0]; R1 &= neq[1]; R2 &= neq[2]; R3 &= neq[3];
+        u64 m[4], d[2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            r0 &= neq[i][0]; r1 &= neq[i][1]; r2 &= neq[i][2]; r3 &= neq[i][3];
-            u64 m[4], d[2];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) m[p] = ~neq[i][p] & ALL;
-            block_dilate18<T>(m, d);
-            lab[i] = L[i]; M1[i] = m[1]; M2[i] = m[2]; M3[i] = m[3]; D0[i] = d[0]; D1[i] = d[1];
-        }
+        for (int p = 0; p < 4; ++p) m[p] = ~neq[p] & ALL;
+        block_dilate18<T>(m, d);
+        lab[I] = L; M1[I] = m[1]; M2[I] = m[2]; M3[I] = m[3]; D0[I] = d[0]; D1[I] = d[1];
+    }
+
+    // L[0 .. N0 - 1]: distinct labels -> slots 0 .. N0 - 1.  true: they cover the window; false: `next` = a label of the
+    // window that is none of them (the label at the first uncovered position).
+    template <int N0>
+    TA_HD bool build(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, const uint32_t* L, uint32_t& next) {
+        static_assert(N0 <= CAP, "more labels than slots");
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
+        u64 neq[N0][BLK_S + 2];
+        neq_planes<N0>(tile, t0, L, neq);
+        R0 = R1 = R2 = R3 = ALL;
+        set_slots<N0, 0>(L, neq);
         u64 cv = 0ull;
 #pragma unroll
         for (int r = 1; r <= BLK_M; ++r)
             if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (ROWBITS * r);
         cv0 = nvs >= 1 ? cv : 0ull;
         cv1 = nvs >= 2 ? cv : 0ull;
-        if (!(r0 | r1 | r2 | r3)) return true;
-        const int p = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
-        const u64 rp = r0 ? r0 : r1 ? r1 : r2 ? r2 : r3;
-        const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
-        next = reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
+        if (!(R0 | R1 | R2 | R3)) return true;
+        next = first_uncovered(tile, t0);
+        return false;
+    }
+    template <int N0, int I> TA_HD void set_slots(const uint32_t* L, const u64 neq[][BLK_S + 2]) {
+        if constexpr (I < N0) {
+            set_slot<I>(L[I], neq[I]);
+            set_slots<N0, I + 1>(L, neq);
+        }
+    }
+
+    // one more label (not among slots 0 .. I - 1) -> slot I; same return as build
+    template <int I>
+    TA_HD bool extend(const uint4* tile, int fs, int m0, int s0, uint32_t Lnew, uint32_t& next) {
+        static_assert(I < CAP, "more labels than slots");
+        const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
+        u64 neq[1][BLK_S + 2];
+        neq_planes<1>(tile, t0, &Lnew, neq);
+        set_slot<I>(Lnew, neq[0]);
+        if (!(R0 | R1 | R2 | R3)) return true;
+        next = first_uncovered(tile, t0);
         return false;
     }
 

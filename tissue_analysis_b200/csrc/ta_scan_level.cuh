@@ -7,11 +7,14 @@
 //
 //   P1   one 8 x 4 x 2 block per thread: min / max label of its window.  Equal: closed-form moments, merged per warp.
 //        Different: the block goes to list 2 with both labels.
-//   PN   (N = 2 .. MAXL) list N is processed by full warps, one block per lane: one fused pass over the window rows builds
-//        the masks of the N known labels; the level emits what it adds (N = 2: both labels' moments and their pair;
-//        N > 2: the newest label's moments and its pairs with the older ones) through warp merges into the per-brick
-//        tables; a window position covered by no known label names label N + 1 -> list N + 1.
-//   PF   blocks still uncovered after level MAXL: per-voxel path, all threads share their voxels, restricted to what the
+//   P2   list 2, full warps, one block per lane: one fused pass over the window rows builds the masks of both labels;
+//        their moments and their pair go through warp merges into the per-brick tables.  A window position covered by
+//        neither label names a third one -> list 3.
+//   P3   list 3: fused masks of the three known labels; emitted: the third label's moments and its pairs with the other
+//        two.  Lanes whose window is still uncovered add one label at a time (one more mask, its moments, its pairs with
+//        every older label) up to MAXL labels -- lists 4, 5, ... would hold a handful of blocks per brick, so they are
+//        steps of this pass instead of phases of their own (a phase costs a block barrier and leaves most warps idle).
+//   PF   blocks still uncovered after MAXL labels: per-voxel path, all threads share their voxels, restricted to what the
 //        levels could not emit (a label outside the block's known set is involved).
 //
 // Cost model and expected gain: DESIGN.md section 6.  STATUS: exact on the CPU emulation of the CUDA execution model
@@ -28,12 +31,15 @@ namespace ta {
 #define TA_LEVEL_MAXL 4            // labels per block handled by bit algebra; more -> per-voxel path for the rest
 #endif
 constexpr int LV_MAXL = TA_LEVEL_MAXL;
+#ifndef TA_LEVEL_MINB
+#define TA_LEVEL_MINB 3            // CTAs per SM the register budget is cut for: 3 -> 80 registers (some spills), 2 -> 128
+#endif
 
 template <typename T> constexpr size_t scan_level_smem_bytes() {
     return scan_block_smem_bytes<T>() +
            256 * 4 +                               // packed row moments of every byte
            NTHREADS * LV_MAXL * 4 +                // known labels per block
-           LV_MAXL * NTHREADS * 2;                 // lists 2 .. MAXL and the fallback list (block ids)
+           3 * NTHREADS * 2;                       // list 2, list 3 and the fallback list (block ids)
 }
 
 // per-voxel path for one voxel of a block whose window holds labels outside `known[0 .. LV_MAXL - 1]`: only
@@ -74,13 +80,61 @@ __device__ __noinline__ void level_fallback_voxel(const BrickShared<T> sh, const
     }
 }
 
+// Warp merge of one label row per lane (all 32 lanes call; has = false: nothing to add), the packed form of
+// block_merge_label: a lane's row holds at most one block (64 voxels, brick-local coordinates f < 128, m < 16, s < 8), so
+// the ten sums of a whole warp fit seven words and the m / s boxes one bit mask: 10 full-mask redux per distinct label
+// instead of 16, and 10 + 10 live registers instead of 16 + 16 around the loop.
+//   w0 = n [12 bits] | sf << 12 [18]     w1 = sm [15] | sss << 15 [17]     w2 = ss [14] | sms << 14 [18]
+//   w3 = sff   w4 = sfm   w5 = sfs   w6 = smm          (warp maxima: n 2048, sf 252 928, sm 30 720, sss 100 352, ss 14 336,
+//                                                        sms 215 040 -- each below its field)
+template <typename T>
+__device__ __forceinline__ void level_merge_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status, bool has,
+                                                  uint32_t L, const uint32_t v[LT_FIELDS], u64 gF0, u64 gM0, u64 gS0, int lane) {
+    uint32_t w[7];
+    w[0] = v[0] | (v[1] << 12); w[1] = v[2] | (v[9] << 15); w[2] = v[3] | (v[8] << 14);
+    w[3] = v[4]; w[4] = v[5]; w[5] = v[6]; w[6] = v[7];
+    const uint32_t flo = v[10], fhi = v[13];
+    const uint32_t ms = (1u << v[11]) | (1u << v[14]) | (((1u << v[12]) | (1u << v[15])) << 16);
+    unsigned pending = __ballot_sync(0xffffffffu, has);
+    uint32_t tot[10];
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t Lk = __shfl_sync(0xffffffffu, L, leader);
+        const bool mine = has && (L == Lk);
+        const bool lead = (lane == leader);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? w[i] : 0u);
+            if (lead) tot[i] = r;
+        }
+        uint32_t r = __reduce_min_sync(0xffffffffu, mine ? flo : 0xFFFFFFFFu);
+        if (lead) tot[7] = r;
+        r = __reduce_max_sync(0xffffffffu, mine ? fhi : 0u);
+        if (lead) tot[8] = r;
+        r = __reduce_or_sync(0xffffffffu, mine ? ms : 0u);
+        if (lead) tot[9] = r;
+        am_leader = am_leader || lead;
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (am_leader) {
+        uint32_t u[LT_FIELDS];
+        u[0] = tot[0] & 0xFFFu; u[1] = tot[0] >> 12; u[2] = tot[1] & 0x7FFFu; u[9] = tot[1] >> 15;
+        u[3] = tot[2] & 0x3FFFu; u[8] = tot[2] >> 14; u[4] = tot[3]; u[5] = tot[4]; u[6] = tot[5]; u[7] = tot[6];
+        u[10] = tot[7]; u[13] = tot[8];
+        u[11] = (uint32_t)__ffs(tot[9] & 0xFFFFu) - 1u; u[14] = 31u - (uint32_t)__clz(tot[9] & 0xFFFFu);
+        u[12] = (uint32_t)__ffs(tot[9] >> 16) - 1u; u[15] = 31u - (uint32_t)__clz(tot[9] >> 16);
+        label_add<T>(sh, lt, status, L, u, gF0, gM0, gS0);
+    }
+}
+
 // What a level hands to the tables, per lane: up to two label rows and up to MAXL - 1 pair rows.
 template <typename T, bool MERGE>
 __device__ __forceinline__ void level_emit_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status, bool has,
                                                  uint32_t L, uint32_t v[LT_FIELDS], uint32_t bF, uint32_t bM, uint32_t bS, u64 gF0,
                                                  u64 gM0, u64 gS0, int lane) {
     if (has) block_shift_moments(v, bF, bM, bS);                        // block -> brick coordinates
-    if (MERGE) block_merge_label<T>(sh, lt, status, has, L, v, gF0, gM0, gS0, lane);
+    if (MERGE) level_merge_label<T>(sh, lt, status, has, L, v, gF0, gM0, gS0, lane);
     else if (has) label_add<T>(sh, lt, status, L, v, gF0, gM0, gS0);
 }
 template <typename T, bool MERGE>
@@ -90,18 +144,58 @@ __device__ __forceinline__ void level_emit_pair(const BrickShared<T>& sh, const 
     else if (has) pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
 }
 
-// Level N over list N.  Every warp runs the same number of rounds for all its lanes (lanes beyond the list end idle
-// with has = false), so the merges are full-mask.
+// what a step adds for slot I of a block: the label's moments and its pairs with every older slot (all lanes call)
+template <typename T, int CAP, int I, bool MERGE>
+__device__ __forceinline__ void level_emit_slot(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
+                                                const uint32_t* momtab, const BlockLevel<T, CAP>& b, bool active, uint32_t bF,
+                                                uint32_t bM, uint32_t bS, u64 gF0, u64 gM0, u64 gS0, int lane) {
+    const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
+    uint32_t v[LT_FIELDS], inc[PT_WORDS];
+    const bool has = active && do_mom && b.label_moments(I, momtab, v);
+    level_emit_label<T, MERGE>(sh, lt, pt.status, has, b.lab[I], v, bF, bM, bS, gF0, gM0, gS0, lane);
+    if (do_p6 || do_w18) {
+#pragma unroll
+        for (int j = 0; j < I; ++j) {
+            const bool hasp = active && b.pair_increments(I, j, do_p6, do_w18, inc);
+            level_emit_pair<T, MERGE>(sh, pt, hasp, b.lab[I], b.lab[j], inc, lane);
+        }
+    }
+}
+
+// extension steps I .. MAXL - 1 of P3: lanes whose window is still uncovered add one label each; the loop ends for the
+// whole warp as soon as no lane needs another step, so the merges stay full-mask
+template <typename T, int I, bool MERGE>
+__device__ __forceinline__ void level_extend(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
+                                             const uint32_t* momtab, uint32_t* known, BlockLevel<T, LV_MAXL>& b,
+                                             bool& more, uint32_t& next, int blk, int fs, int m0, int s0, uint32_t bF, uint32_t bM,
+                                             uint32_t bS, u64 gF0, u64 gM0, u64 gS0, int lane) {
+    if constexpr (I < LV_MAXL) {
+        if (!__ballot_sync(0xffffffffu, more)) return;
+        const bool act = more;
+        if (act) {
+            known[blk * LV_MAXL + I] = next;
+            more = !b.template extend<I>(sh.tile, fs, m0, s0, next, next);
+        } else {
+            b.template clear_slot<I>();
+        }
+        level_emit_slot<T, LV_MAXL, I, MERGE>(sh, P, lt, pt, momtab, b, act, bF, bM, bS, gF0, gM0, gS0, lane);
+        level_extend<T, I + 1, MERGE>(sh, P, lt, pt, momtab, known, b, more, next, blk, fs, m0, s0, bF, bM, bS, gF0, gM0, gS0, lane);
+    }
+}
+
+// P2 (N = 2) and P3 (N = 3) over their lists.  Every warp runs the same number of rounds for all its lanes (lanes beyond
+// the list end idle with active = false), so the merges are full-mask.
 template <typename T, int N, bool MERGE>
 __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
                                            const uint32_t* momtab, uint32_t* known, unsigned short* lists, int F0, int M0, int S0,
                                            u64 gF0, u64 gM0, u64 gS0, int tid) {
+    static_assert(N == 2 || N == 3, "list 2 or list 3");
     constexpr int SEG = Vox<T>::SEG;
+    constexpr int CAP = (N == 2) ? 2 : LV_MAXL;
     const int lane = tid & 31;
-    const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
     const int count = (int)sh.ctr[N - 2];
     const unsigned short* list = lists + (N - 2) * NTHREADS;
-    unsigned short* next_list = lists + (N - 1) * NTHREADS;
+    unsigned short* next_list = lists + (N - 1) * NTHREADS;       // list 3, or the fallback list
     for (int base = tid - lane; base < count; base += NTHREADS) {
         const int q = base + lane;
         const bool active = q < count;
@@ -110,62 +204,38 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
         const int nvf = min(SEG, (int)P.nf - (F0 + fs * SEG)), nvm = min(BLK_M, (int)P.nm - (M0 + m0)),
                   nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
         const uint32_t bF = (uint32_t)(fs * SEG), bM = (uint32_t)m0, bS = (uint32_t)s0;
-        BlockLevel<T, N> b;
+        BlockLevel<T, CAP> b;
         uint32_t L[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) L[i] = known[blk * LV_MAXL + i];
         bool more = false;
         uint32_t next = 0u;
-        if (active) more = !b.build(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
+        if (active) more = !b.template build<N>(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
         else b.clear();
-        if (more) {
-            // list N + 1 (for N == MAXL: the per-voxel list); its label slot exists only below MAXL
-            if (N < LV_MAXL) known[blk * LV_MAXL + (N < LV_MAXL ? N : 0)] = next;
-            next_list[atomicAdd(&sh.ctr[N - 1], 1u)] = (unsigned short)blk;
-        }
-        uint32_t v[LT_FIELDS], inc[PT_WORDS];
         if (N == 2) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const bool has = active && do_mom && b.label_moments(i, momtab, v);
-                level_emit_label<T, MERGE>(sh, lt, pt.status, has, b.lab[i], v, bF, bM, bS, gF0, gM0, gS0, lane);
+            if (more) {                                           // a third label: list 3
+                known[blk * LV_MAXL + 2] = next;
+                next_list[atomicAdd(&sh.ctr[1], 1u)] = (unsigned short)blk;
             }
-            if (do_p6 || do_w18) {
-                const bool has = active && b.pair_increments(0, 1, do_p6, do_w18, inc);
-                level_emit_pair<T, MERGE>(sh, pt, has, b.lab[0], b.lab[1], inc, lane);
-            }
+            level_emit_slot<T, CAP, 0, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
+            level_emit_slot<T, CAP, 1, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
         } else {
-            const bool has = active && do_mom && b.label_moments(N - 1, momtab, v);
-            level_emit_label<T, MERGE>(sh, lt, pt.status, has, b.lab[N - 1], v, bF, bM, bS, gF0, gM0, gS0, lane);
-            if (do_p6 || do_w18) {
-#pragma unroll
-                for (int j = 0; j < N - 1; ++j) {
-                    const bool hasp = active && b.pair_increments(N - 1, j, do_p6, do_w18, inc);
-                    level_emit_pair<T, MERGE>(sh, pt, hasp, b.lab[N - 1], b.lab[j], inc, lane);
-                }
-            }
+            level_emit_slot<T, CAP, 2, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
+            if constexpr (N == 3)
+                level_extend<T, 3, MERGE>(sh, P, lt, pt, momtab, known, b, more, next, blk, fs, m0, s0, bF, bM, bS, gF0, gM0, gS0, lane);
+            if (more) next_list[atomicAdd(&sh.ctr[2], 1u)] = (unsigned short)blk;       // labels beyond MAXL: per-voxel path
         }
     }
 }
 
-// levels 2 .. MAXL, one block barrier after each (list N + 1 is complete when level N has ended)
-template <typename T, int N, bool MERGE>
-__device__ __forceinline__ void level_passes(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
-                                             const uint32_t* momtab, uint32_t* known, unsigned short* lists, int F0, int M0, int S0,
-                                             u64 gF0, u64 gM0, u64 gS0, int tid) {
-    level_pass<T, N, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
-    __syncthreads();
-    if constexpr (N < LV_MAXL) level_passes<T, N + 1, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
-}
-
 // MERGE = true: warp merges for the table updates; false: plain atomics per block (to bisect against).
 template <typename T, bool MERGE>
-__global__ void __launch_bounds__(NTHREADS, 3)
+__global__ void __launch_bounds__(NTHREADS, TA_LEVEL_MINB)
 scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::PKey PKey;
     constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG, BF = NFS * SEG;
     static_assert(NTHREADS == NFS * (BM / BLK_M) * (BS / BLK_S), "one block per thread");
-    static_assert(LV_MAXL >= 2 && LV_MAXL <= 6, "sh.ctr[0 .. MAXL - 1] count lists 2 .. MAXL + 1; ctr[6 ..] is taken");
+    static_assert(LV_MAXL >= 3 && LV_MAXL <= 8, "labels per block handled by masks");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BrickShared<T> sh;
@@ -177,7 +247,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
     uint32_t* momtab = reinterpret_cast<uint32_t*>(sh.ctr + 16);                   // [256]
     uint32_t* known = momtab + 256;                                                // [NTHREADS * MAXL] labels per block
-    unsigned short* lists = reinterpret_cast<unsigned short*>(known + NTHREADS * LV_MAXL);   // [MAXL][NTHREADS] block ids
+    unsigned short* lists = reinterpret_cast<unsigned short*>(known + NTHREADS * LV_MAXL);   // [3][NTHREADS] block ids: list 2, list 3, fallback
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
@@ -210,8 +280,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         if (brick >= total) break;
         if (tid == 0) {
             sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
-#pragma unroll
-            for (int n = 0; n < LV_MAXL; ++n) sh.ctr[n] = 0u;          // lists 2 .. MAXL + 1
+            sh.ctr[0] = sh.ctr[1] = sh.ctr[2] = 0u;                    // list 2, list 3, fallback list
         }
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
@@ -248,13 +317,16 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         }
         __syncthreads();
 
-        // ---- P2 .. PMAXL: the lists ----------------------------------------------------------------------------------------
-        level_passes<T, 2, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
+        // ---- P2, P3: the lists (list 3 is complete when P2 has ended, the fallback list when P3 has) -----------------------
+        level_pass<T, 2, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
+        __syncthreads();
+        level_pass<T, 3, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
+        __syncthreads();
 
         // ---- PF: blocks with labels beyond their known set: all threads share their voxels -------------------------------
         {
-            const int ncrowded = (int)sh.ctr[LV_MAXL - 1];
-            const unsigned short* crowded = lists + (LV_MAXL - 1) * NTHREADS;
+            const int ncrowded = (int)sh.ctr[2];
+            const unsigned short* crowded = lists + 2 * NTHREADS;
             constexpr int BV = SEG * BLK_M * BLK_S;
             for (int q = tid; q < ncrowded * BV; q += NTHREADS) {
                 const int blk = crowded[q / BV], w = q % BV;
