@@ -6,6 +6,9 @@
 // Usage: kernel_emu_check <seed> ; exit code 0 = every case equal.
 #include "emu/cuda_emu.h"
 
+static unsigned long long g_user_stat[16];
+#define TA_STAT(which, n) (g_user_stat[which] += (unsigned long long)(n))
+
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
@@ -148,14 +151,22 @@ static void print_stats() {
     const int ncell = (int)((double)nf * nm * nbuf / 21500.0 + 0.5);
     printf("tissue-like volume %d x %d x %d, %d cells; operations per voxel\n", nf, nm, nbuf, ncell);
     printf("%-28s %9s %9s %9s %9s %9s %9s\n", "kernel", "atom.smem", "atom.glob", "redux/w", "ballot/w", "shfl/w", "bar/blk");
+    unsigned long long level_stat[16] = {};
     for (int w = 0; w < NWHICH; ++w) {
         emu::g_stats.clear();
+        memset(g_user_stat, 0, sizeof g_user_stat);
         const int bad = run_case<uint16_t>((Which)w, nf, nm, nbuf, 0, nbuf, 0, ncell, 1, 12345u);
         const double nv = (double)nf * nm * nbuf;
         const emu::Stats& s = emu::g_stats;
         printf("%-28s %9.4f %9.4f %9.4f %9.4f %9.4f %9.5f%s\n", which_name[w], s.atom_shared / nv, s.atom_global / nv, s.redux / nv,
                s.ballot / nv, s.shfl / nv, s.syncthreads / nv, bad ? "  (MISMATCH)" : "");
+        if (w == LEVEL_MERGE) memcpy(level_stat, g_user_stat, sizeof level_stat);
     }
+    const unsigned long long* u = level_stat;
+    printf("level kernel, dynamic counts: %llu bricks not one label, %llu blocks: %llu one label (%.1f %%), list 2: %llu blocks in %llu warp "
+           "rounds (%.1f lanes), list 3: %llu blocks in %llu warp rounds (%.1f lanes), extension steps: %llu warp-level for %llu "
+           "blocks, fallback: %llu blocks; merge loop rounds: labels %llu, pairs %llu\n", u[0], u[1], u[2], 100.0 * u[2] / u[1],
+           u[3], u[4], (double)u[3] / u[4], u[5], u[6], (double)u[5] / (u[6] ? u[6] : 1), u[7], u[8], u[9], u[10], u[11]);
 }
 
 int main(int argc, char** argv) {

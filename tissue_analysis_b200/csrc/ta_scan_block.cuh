@@ -135,6 +135,9 @@ __device__ __forceinline__ void block_merge_pair(const BrickShared<T>& sh, const
     uint32_t tot[PT_WORDS] = {0u, 0u, 0u, 0u};
     bool am_leader = false;
     while (pending) {
+#ifdef TA_STAT
+        if (lane == 0) TA_STAT(11, 1);
+#endif
         const int leader = __ffs(pending) - 1;
         const typename Vox<T>::PKey kk = __shfl_sync(0xffffffffu, key, leader);
         const bool mine = (key == kk);

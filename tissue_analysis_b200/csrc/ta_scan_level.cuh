@@ -25,6 +25,11 @@
 #pragma once
 #include "ta_scan_block.cuh"
 
+// dynamic counters for the CPU emulation (tests/host/kernel_emu_check.cpp --stats); nothing in a CUDA build
+#ifndef TA_STAT
+#define TA_STAT(which, n) ((void)0)
+#endif
+
 namespace ta {
 
 #ifndef TA_LEVEL_MAXL
@@ -99,6 +104,7 @@ __device__ __forceinline__ void level_merge_label(const BrickShared<T>& sh, cons
     uint32_t tot[10];
     bool am_leader = false;
     while (pending) {
+        if (lane == 0) TA_STAT(10, 1);
         const int leader = __ffs(pending) - 1;
         const uint32_t Lk = __shfl_sync(0xffffffffu, L, leader);
         const bool mine = has && (L == Lk);
@@ -172,6 +178,8 @@ __device__ __forceinline__ void level_extend(const BrickShared<T>& sh, const Sca
     if constexpr (I < LV_MAXL) {
         if (!__ballot_sync(0xffffffffu, more)) return;
         const bool act = more;
+        if (lane == 0) TA_STAT(7, 1);
+        if (act) TA_STAT(8, 1);
         if (act) {
             known[blk * LV_MAXL + I] = next;
             more = !b.template extend<I>(sh.tile, fs, m0, s0, next, next);
@@ -199,6 +207,8 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
     for (int base = tid - lane; base < count; base += NTHREADS) {
         const int q = base + lane;
         const bool active = q < count;
+        if (lane == 0) TA_STAT(N == 2 ? 4 : 6, 1);
+        if (active) TA_STAT(N == 2 ? 3 : 5, 1);
         const int blk = active ? (int)list[q] : 0;
         const int fs = blk % NFS, m0 = ((blk / NFS) % (BM / BLK_M)) * BLK_M, s0 = (blk / (NFS * (BM / BLK_M))) * BLK_S;
         const int nvf = min(SEG, (int)P.nf - (F0 + fs * SEG)), nvm = min(BLK_M, (int)P.nm - (M0 + m0)),
@@ -299,6 +309,9 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
             uint32_t lo = 0u, hi = 0u;
             if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi);
             const bool one = valid && lo == hi, many = valid && lo != hi;
+            if (tid == 0) TA_STAT(0, 1);
+            if (valid) TA_STAT(1, 1);
+            if (one) TA_STAT(2, 1);
             if (many) {                                       // list 2: both labels are labels of the window
                 known[tid * LV_MAXL + 0] = lo;
                 known[tid * LV_MAXL + 1] = hi;
@@ -326,6 +339,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         // ---- PF: blocks with labels beyond their known set: all threads share their voxels -------------------------------
         {
             const int ncrowded = (int)sh.ctr[2];
+            if (tid == 0) TA_STAT(9, ncrowded);
             const unsigned short* crowded = lists + 2 * NTHREADS;
             constexpr int BV = SEG * BLK_M * BLK_S;
             for (int q = tid; q < ncrowded * BV; q += NTHREADS) {
