@@ -51,6 +51,7 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
         if (nb[k] != a) pt[{std::min(a, nb[k]), std::max(a, nb[k])}][2 * k + (a < nb[k] ? 0 : 1)] += 1;
 }
 
+static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
 enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, NWHICH };
 static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
                                    "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>"};
@@ -74,7 +75,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
         for (int s = 0; s < nbuf; ++s) for (int m = 0; m < nm; ++m) for (int f = 0; f < nf; ++f) {
             long best = 1L << 60; int bk = 0;
             for (int k = 0; k < nlabels; ++k) {
-                long d = (long)(f - sx[k]) * (f - sx[k]) + (long)(m - sy[k]) * (m - sy[k]) * 2 + (long)(s - sz[k]) * (s - sz[k]) * 3;
+                long d = (long)(f - sx[k]) * (f - sx[k]) + (long)(m - sy[k]) * (m - sy[k]) * g_wm + (long)(s - sz[k]) * (s - sz[k]) * g_ws;
                 if (d < best) { best = d; bk = k; }
             }
             V.d[((size_t)s * nm + m) * nf + f] = names[bk];
@@ -147,7 +148,8 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
 // Operation counts per voxel of the six kernels on a tissue-like volume (cells of ~21 500 voxels as in C3): what the
 // table updates cost in shared-memory atomics and warp collectives.  Not a time; a GPU decides that.
 static void print_stats() {
-    const int nf = 256, nm = 64, nbuf = 32;
+    const int nf = 256, nm = 128, nbuf = 64;
+    g_wm = g_ws = 1;
     const int ncell = (int)((double)nf * nm * nbuf / 21500.0 + 0.5);
     printf("tissue-like volume %d x %d x %d, %d cells; operations per voxel\n", nf, nm, nbuf, ncell);
     printf("%-28s %9s %9s %9s %9s %9s %9s\n", "kernel", "atom.smem", "atom.glob", "redux/w", "ballot/w", "shfl/w", "bar/blk");

@@ -477,7 +477,11 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         P.phase_cycles = ctx->phase_cycles;
     }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
-    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" / "block" for every brick
+#if defined(TA_WITH_BLOCK_KERNEL) && defined(TA_DEFAULT_LEVEL)
+    // experiment build: the level kernel unless a pass names another one (0x800 forces the product kernel)
+    if (!(P.flags & (0x800u | 0x1000u | 0x4000u))) P.flags |= 0x4000u | 0x10000u;
+#endif
+    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" / "block" / "level" for every brick
         if (!strcmp(pp, "voxel")) P.flags |= 0x800u;
         else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
         else if (!strcmp(pp, "block")) P.flags |= 0x4000u;

@@ -334,9 +334,13 @@ TA_HD void block_sched_fence() {
 #endif
 }
 
-// Smallest and largest label of the window whose first row (m0 - 1, s0 - 1) is vector t0.
-template <typename T> TA_HD void block_window_minmax(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi);
-template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
+// Smallest and largest label of the window whose first row (m0 - 1, s0 - 1) is vector t0.  `swap` exchanges the order of
+// the two edge-lane loads of every row (the result does not depend on it): segments are 16 bytes apart, so the 32 edge
+// loads of a warp fall on 8 banks; when one half warp reads its left edges while the other reads its right edges they
+// fall on 16.
+template <typename T> TA_HD void block_window_minmax(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap = false);
+template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap) {
+    const int oa = swap ? 8 : -1, ob = swap ? -1 : 8;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
@@ -345,7 +349,7 @@ template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, 
             const int t = t0 + p * PLANEV + r * ROWV;
             const uint4 c = tile[t];
             const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
-            const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16);
+            const uint32_t ew = (uint32_t)e[oa] | ((uint32_t)e[ob] << 16);
             mn = ta_vminu2(ta_vminu2(ta_vminu2(mn, c.x), ta_vminu2(c.y, c.z)), ta_vminu2(c.w, ew));
             mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(mx, c.x), ta_vmaxu2(c.y, c.z)), ta_vmaxu2(c.w, ew));
         }
@@ -354,7 +358,8 @@ template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, 
     lo = (mn & 0xFFFFu) < (mn >> 16) ? (mn & 0xFFFFu) : (mn >> 16);
     hi = (mx & 0xFFFFu) > (mx >> 16) ? (mx & 0xFFFFu) : (mx >> 16);
 }
-template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
+template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap) {
+    const int oa = swap ? 4 : -1, ob = swap ? -1 : 4;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
@@ -363,7 +368,7 @@ template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, 
             const int t = t0 + p * PLANEV + r * ROWV;
             const uint4 c = tile[t];
             const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
-            const uint32_t a = e[-1], b = e[4];
+            const uint32_t a = e[oa], b = e[ob];
             const uint32_t n1 = c.x < c.y ? c.x : c.y, n2 = c.z < c.w ? c.z : c.w, n3 = a < b ? a : b;
             const uint32_t x1 = c.x > c.y ? c.x : c.y, x2 = c.z > c.w ? c.z : c.w, x3 = a > b ? a : b;
             const uint32_t n12 = n1 < n2 ? n1 : n2, x12 = x1 > x2 ? x1 : x2;

@@ -85,23 +85,42 @@ __device__ __noinline__ void level_fallback_voxel(const BrickShared<T> sh, const
     }
 }
 
-// Warp merge of one label row per lane (all 32 lanes call; has = false: nothing to add), the packed form of
-// block_merge_label: a lane's row holds at most one block (64 voxels, brick-local coordinates f < 128, m < 16, s < 8), so
-// the ten sums of a whole warp fit seven words and the m / s boxes one bit mask: 10 full-mask redux per distinct label
-// instead of 16, and 10 + 10 live registers instead of 16 + 16 around the loop.
+// One label row per lane in packed form.  A lane's row holds at most one block (64 voxels, brick-local coordinates
+// f < 128, m < 16, s < 8), so the ten sums of a whole WARP fit seven words and the m / s boxes one bit mask:
 //   w0 = n [12 bits] | sf << 12 [18]     w1 = sm [15] | sss << 15 [17]     w2 = ss [14] | sms << 14 [18]
 //   w3 = sff   w4 = sfm   w5 = sfs   w6 = smm          (warp maxima: n 2048, sf 252 928, sm 30 720, sss 100 352, ss 14 336,
 //                                                        sms 215 040 -- each below its field)
-template <typename T>
-__device__ __forceinline__ void level_merge_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status, bool has,
-                                                  uint32_t L, const uint32_t v[LT_FIELDS], u64 gF0, u64 gM0, u64 gS0, int lane) {
-    uint32_t w[7];
+//   w7 = f min   w8 = f max   w9 = 1 << m min | 1 << m max | (1 << s min | 1 << s max) << 16
+// The steps pack their rows as soon as the moments are known and merge afterwards, so that the masks of a block are not
+// live (and spilled) across the merge loops.
+constexpr int LV_ROW = 10;
+__device__ __forceinline__ void level_pack_row(const uint32_t v[LT_FIELDS], uint32_t w[LV_ROW]) {
     w[0] = v[0] | (v[1] << 12); w[1] = v[2] | (v[9] << 15); w[2] = v[3] | (v[8] << 14);
     w[3] = v[4]; w[4] = v[5]; w[5] = v[6]; w[6] = v[7];
-    const uint32_t flo = v[10], fhi = v[13];
-    const uint32_t ms = (1u << v[11]) | (1u << v[14]) | (((1u << v[12]) | (1u << v[15])) << 16);
+    w[7] = v[10]; w[8] = v[13];
+    w[9] = (1u << v[11]) | (1u << v[14]) | (((1u << v[12]) | (1u << v[15])) << 16);
+}
+__device__ __forceinline__ void level_unpack_row(const uint32_t w[LV_ROW], uint32_t u[LT_FIELDS]) {
+    u[0] = w[0] & 0xFFFu; u[1] = w[0] >> 12; u[2] = w[1] & 0x7FFFu; u[9] = w[1] >> 15;
+    u[3] = w[2] & 0x3FFFu; u[8] = w[2] >> 14; u[4] = w[3]; u[5] = w[4]; u[6] = w[5]; u[7] = w[6];
+    u[10] = w[7]; u[13] = w[8];
+    u[11] = (uint32_t)__ffs(w[9] & 0xFFFFu) - 1u; u[14] = 31u - (uint32_t)__clz(w[9] & 0xFFFFu);
+    u[12] = (uint32_t)__ffs(w[9] >> 16) - 1u; u[15] = 31u - (uint32_t)__clz(w[9] >> 16);
+}
+
+// The label row of a lane goes to the per-brick table.  MERGE: warp merge (all 32 lanes call; has = false: nothing to
+// add): uniform loop over the distinct labels of the warp, 10 full-mask redux each, the group leaders add in one SIMT
+// pass after the loop.  Otherwise: plain atomics per lane.
+template <typename T, bool MERGE>
+__device__ __forceinline__ void level_put_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status, bool has,
+                                                uint32_t L, const uint32_t w[LV_ROW], u64 gF0, u64 gM0, u64 gS0, int lane) {
+    uint32_t u[LT_FIELDS];
+    if (!MERGE) {
+        if (has) { level_unpack_row(w, u); label_add<T>(sh, lt, status, L, u, gF0, gM0, gS0); }
+        return;
+    }
     unsigned pending = __ballot_sync(0xffffffffu, has);
-    uint32_t tot[10];
+    uint32_t tot[LV_ROW];
     bool am_leader = false;
     while (pending) {
         if (lane == 0) TA_STAT(10, 1);
@@ -114,57 +133,53 @@ __device__ __forceinline__ void level_merge_label(const BrickShared<T>& sh, cons
             const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? w[i] : 0u);
             if (lead) tot[i] = r;
         }
-        uint32_t r = __reduce_min_sync(0xffffffffu, mine ? flo : 0xFFFFFFFFu);
+        uint32_t r = __reduce_min_sync(0xffffffffu, mine ? w[7] : 0xFFFFFFFFu);
         if (lead) tot[7] = r;
-        r = __reduce_max_sync(0xffffffffu, mine ? fhi : 0u);
+        r = __reduce_max_sync(0xffffffffu, mine ? w[8] : 0u);
         if (lead) tot[8] = r;
-        r = __reduce_or_sync(0xffffffffu, mine ? ms : 0u);
+        r = __reduce_or_sync(0xffffffffu, mine ? w[9] : 0u);
         if (lead) tot[9] = r;
         am_leader = am_leader || lead;
         pending &= ~__ballot_sync(0xffffffffu, mine);
     }
     if (am_leader) {
-        uint32_t u[LT_FIELDS];
-        u[0] = tot[0] & 0xFFFu; u[1] = tot[0] >> 12; u[2] = tot[1] & 0x7FFFu; u[9] = tot[1] >> 15;
-        u[3] = tot[2] & 0x3FFFu; u[8] = tot[2] >> 14; u[4] = tot[3]; u[5] = tot[4]; u[6] = tot[5]; u[7] = tot[6];
-        u[10] = tot[7]; u[13] = tot[8];
-        u[11] = (uint32_t)__ffs(tot[9] & 0xFFFFu) - 1u; u[14] = 31u - (uint32_t)__clz(tot[9] & 0xFFFFu);
-        u[12] = (uint32_t)__ffs(tot[9] >> 16) - 1u; u[15] = 31u - (uint32_t)__clz(tot[9] >> 16);
+        level_unpack_row(tot, u);
         label_add<T>(sh, lt, status, L, u, gF0, gM0, gS0);
     }
 }
-
-// What a level hands to the tables, per lane: up to two label rows and up to MAXL - 1 pair rows.
 template <typename T, bool MERGE>
-__device__ __forceinline__ void level_emit_label(const BrickShared<T>& sh, const LabelTable& lt, uint32_t* status, bool has,
-                                                 uint32_t L, uint32_t v[LT_FIELDS], uint32_t bF, uint32_t bM, uint32_t bS, u64 gF0,
-                                                 u64 gM0, u64 gS0, int lane) {
-    if (has) block_shift_moments(v, bF, bM, bS);                        // block -> brick coordinates
-    if (MERGE) level_merge_label<T>(sh, lt, status, has, L, v, gF0, gM0, gS0, lane);
-    else if (has) label_add<T>(sh, lt, status, L, v, gF0, gM0, gS0);
-}
-template <typename T, bool MERGE>
-__device__ __forceinline__ void level_emit_pair(const BrickShared<T>& sh, const PairTable& pt, bool has, uint32_t a, uint32_t b,
-                                                const uint32_t inc[PT_WORDS], int lane) {
+__device__ __forceinline__ void level_put_pair(const BrickShared<T>& sh, const PairTable& pt, bool has, uint32_t a, uint32_t b,
+                                               const uint32_t inc[PT_WORDS], int lane) {
     if (MERGE) block_merge_pair<T>(sh, pt, has ? Vox<T>::key(a, b) : Vox<T>::PEMPTY, inc, lane);
     else if (has) pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
 }
 
-// what a step adds for slot I of a block: the label's moments and its pairs with every older slot (all lanes call)
+// moments of slot I of a block as a packed row in brick coordinates; false: nothing to add
+template <typename T, int CAP>
+__device__ __forceinline__ bool level_slot_row(const BlockLevel<T, CAP>& b, int i, const uint32_t* momtab, bool wanted, uint32_t bF,
+                                               uint32_t bM, uint32_t bS, uint32_t w[LV_ROW]) {
+    uint32_t v[LT_FIELDS];
+    const bool has = wanted && b.label_moments(i, momtab, v);
+    if (has) { block_shift_moments(v, bF, bM, bS); level_pack_row(v, w); }
+    return has;
+}
+
+// what a step adds for slot I of a block: the label's moments and its pairs with every older slot (all lanes call).
+// Everything that needs the masks is computed first, the merges follow.
 template <typename T, int CAP, int I, bool MERGE>
 __device__ __forceinline__ void level_emit_slot(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
                                                 const uint32_t* momtab, const BlockLevel<T, CAP>& b, bool active, uint32_t bF,
                                                 uint32_t bM, uint32_t bS, u64 gF0, u64 gM0, u64 gS0, int lane) {
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
-    uint32_t v[LT_FIELDS], inc[PT_WORDS];
-    const bool has = active && do_mom && b.label_moments(I, momtab, v);
-    level_emit_label<T, MERGE>(sh, lt, pt.status, has, b.lab[I], v, bF, bM, bS, gF0, gM0, gS0, lane);
+    uint32_t w[LV_ROW], inc[I > 0 ? I : 1][PT_WORDS];
+    bool hasp[I > 0 ? I : 1];
+    const bool has = level_slot_row<T, CAP>(b, I, momtab, active && do_mom, bF, bM, bS, w);
+#pragma unroll
+    for (int j = 0; j < I; ++j) hasp[j] = active && (do_p6 || do_w18) && b.pair_increments(I, j, do_p6, do_w18, inc[j]);
+    level_put_label<T, MERGE>(sh, lt, pt.status, has, b.lab[I], w, gF0, gM0, gS0, lane);
     if (do_p6 || do_w18) {
 #pragma unroll
-        for (int j = 0; j < I; ++j) {
-            const bool hasp = active && b.pair_increments(I, j, do_p6, do_w18, inc);
-            level_emit_pair<T, MERGE>(sh, pt, hasp, b.lab[I], b.lab[j], inc, lane);
-        }
+        for (int j = 0; j < I; ++j) level_put_pair<T, MERGE>(sh, pt, hasp[j], b.lab[I], b.lab[j], inc[j], lane);
     }
 }
 
@@ -227,8 +242,16 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
                 known[blk * LV_MAXL + 2] = next;
                 next_list[atomicAdd(&sh.ctr[1], 1u)] = (unsigned short)blk;
             }
-            level_emit_slot<T, CAP, 0, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
-            level_emit_slot<T, CAP, 1, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
+            // both rows and the pair first: the masks are dead before the first merge loop
+            const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
+            uint32_t w0[LV_ROW], w1[LV_ROW], inc[PT_WORDS];
+            const bool has0 = level_slot_row<T, CAP>(b, 0, momtab, active && do_mom, bF, bM, bS, w0);
+            const bool has1 = level_slot_row<T, CAP>(b, 1, momtab, active && do_mom, bF, bM, bS, w1);
+            const bool hasp = active && (do_p6 || do_w18) && b.pair_increments(1, 0, do_p6, do_w18, inc);
+            const uint32_t L0 = b.lab[0], L1 = b.lab[1];
+            level_put_label<T, MERGE>(sh, lt, pt.status, has0, L0, w0, gF0, gM0, gS0, lane);
+            level_put_label<T, MERGE>(sh, lt, pt.status, has1, L1, w1, gF0, gM0, gS0, lane);
+            if (do_p6 || do_w18) level_put_pair<T, MERGE>(sh, pt, hasp, L1, L0, inc, lane);
         } else {
             level_emit_slot<T, CAP, 2, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
             if constexpr (N == 3)
@@ -307,7 +330,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
                       nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
             const bool valid = (nvf > 0 && nvm > 0 && nvs > 0);
             uint32_t lo = 0u, hi = 0u;
-            if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi);
+            if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi, (tid & 16) != 0);
             const bool one = valid && lo == hi, many = valid && lo != hi;
             if (tid == 0) TA_STAT(0, 1);
             if (valid) TA_STAT(1, 1);
@@ -322,11 +345,14 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
             if (lane == 0 && mm) base = atomicAdd(&sh.ctr[0], (unsigned int)__popc(mm));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (many) lists[base + (unsigned int)__popc(mm & ((1u << lane) - 1u))] = (unsigned short)tid;
-            uint32_t v[LT_FIELDS];
+            uint32_t v[LT_FIELDS], w[LV_ROW];
             const bool has = one && do_mom;
-            if (has) block_uniform_moments((uint32_t)nvf, (uint32_t)nvm, (uint32_t)nvs, v);
-            level_emit_label<T, MERGE>(sh, lt, pt.status, has, lo, v, (uint32_t)(fs * SEG), (uint32_t)m0, (uint32_t)s0, gF0, gM0,
-                                       gS0, lane);
+            if (has) {
+                block_uniform_moments((uint32_t)nvf, (uint32_t)nvm, (uint32_t)nvs, v);
+                block_shift_moments(v, (uint32_t)(fs * SEG), (uint32_t)m0, (uint32_t)s0);       // block -> brick coordinates
+                level_pack_row(v, w);
+            }
+            level_put_label<T, MERGE>(sh, lt, pt.status, has, lo, w, gF0, gM0, gS0, lane);
         }
         __syncthreads();
 
