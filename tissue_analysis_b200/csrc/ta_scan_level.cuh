@@ -14,8 +14,9 @@
 //        two.  Lanes whose window is still uncovered add one label at a time (one more mask, its moments, its pairs with
 //        every older label) up to MAXL labels -- lists 4, 5, ... would hold a handful of blocks per brick, so they are
 //        steps of this pass instead of phases of their own (a phase costs a block barrier and leaves most warps idle).
-//   PF   blocks still uncovered after MAXL labels: per-voxel path, all threads share their voxels, restricted to what the
-//        levels could not emit (a label outside the block's known set is involved).
+//   PF   blocks still uncovered after MAXL labels: per-voxel path inside the warp that found them (its 32 lanes share the
+//        voxels of one block; no list, no barrier), restricted to what the steps could not emit (a label outside the
+//        block's known set is involved).
 //
 // Cost model and expected gain: DESIGN.md section 6.  STATUS: exact on the CPU emulation of the CUDA execution model
 // (tests/host/kernel_emu_check.cpp) and, for the block arithmetic, on the host (tests/host/block_level_check.cu); compiles
@@ -44,7 +45,7 @@ template <typename T> constexpr size_t scan_level_smem_bytes() {
     return scan_block_smem_bytes<T>() +
            256 * 4 +                               // packed row moments of every byte
            NTHREADS * LV_MAXL * 4 +                // known labels per block
-           3 * NTHREADS * 2;                       // list 2, list 3 and the fallback list (block ids)
+           2 * NTHREADS * 2;                       // list 2 and list 3 (block ids)
 }
 
 // per-voxel path for one voxel of a block whose window holds labels outside `known[0 .. LV_MAXL - 1]`: only
@@ -218,7 +219,7 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
     const int lane = tid & 31;
     const int count = (int)sh.ctr[N - 2];
     const unsigned short* list = lists + (N - 2) * NTHREADS;
-    unsigned short* next_list = lists + (N - 1) * NTHREADS;       // list 3, or the fallback list
+    unsigned short* next_list = lists + (N - 1) * NTHREADS;       // list 3 (P2 only)
     for (int base = tid - lane; base < count; base += NTHREADS) {
         const int q = base + lane;
         const bool active = q < count;
@@ -256,7 +257,27 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
             level_emit_slot<T, CAP, 2, MERGE>(sh, P, lt, pt, momtab, b, active, bF, bM, bS, gF0, gM0, gS0, lane);
             if constexpr (N == 3)
                 level_extend<T, 3, MERGE>(sh, P, lt, pt, momtab, known, b, more, next, blk, fs, m0, s0, bF, bM, bS, gF0, gM0, gS0, lane);
-            if (more) next_list[atomicAdd(&sh.ctr[2], 1u)] = (unsigned short)blk;       // labels beyond MAXL: per-voxel path
+            // PF, inside the warp that found them (no list, no block barrier): blocks with labels beyond their known set
+            // take the per-voxel path for what the steps could not emit; the 32 lanes share the voxels of one block
+            unsigned fm = __ballot_sync(0xffffffffu, more);
+            if (fm) __syncwarp();                                  // the known labels of those blocks were written by their lanes
+            while (fm) {
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1u;
+                const int cblk = __shfl_sync(0xffffffffu, blk, src);
+                if (lane == 0) TA_STAT(9, 1);
+                const int cfs = cblk % NFS, cm0 = ((cblk / NFS) % (BM / BLK_M)) * BLK_M, cs0 = (cblk / (NFS * (BM / BLK_M))) * BLK_S;
+                constexpr int BV = SEG * BLK_M * BLK_S, ROWE = ROWV * SEG;
+                const T* tileT = reinterpret_cast<const T*>(sh.tile);
+                for (int w = lane; w < BV; w += 32) {
+                    const int df = w % SEG, dm = (w / SEG) % BLK_M, ds = w / (SEG * BLK_M);
+                    const uint32_t f = (uint32_t)(cfs * SEG + df), m = (uint32_t)(cm0 + dm), sp = (uint32_t)(cs0 + ds);
+                    if (F0 + (int)f >= (int)P.nf || M0 + (int)m >= (int)P.nm || S0 + (int)sp >= (int)P.own_hi) continue;
+                    const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + f;
+                    level_fallback_voxel<T>(sh, lt, pt, p, f, m, sp, known + cblk * LV_MAXL, gF0, gM0, gS0, P.flags & 1u, P.flags & 2u,
+                                            P.flags & 4u);
+                }
+            }
         }
     }
 }
@@ -280,7 +301,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
     uint32_t* momtab = reinterpret_cast<uint32_t*>(sh.ctr + 16);                   // [256]
     uint32_t* known = momtab + 256;                                                // [NTHREADS * MAXL] labels per block
-    unsigned short* lists = reinterpret_cast<unsigned short*>(known + NTHREADS * LV_MAXL);   // [3][NTHREADS] block ids: list 2, list 3, fallback
+    unsigned short* lists = reinterpret_cast<unsigned short*>(known + NTHREADS * LV_MAXL);   // [2][NTHREADS] block ids: list 2, list 3
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
@@ -313,7 +334,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         if (brick >= total) break;
         if (tid == 0) {
             sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
-            sh.ctr[0] = sh.ctr[1] = sh.ctr[2] = 0u;                    // list 2, list 3, fallback list
+            sh.ctr[0] = sh.ctr[1] = 0u;                                // list 2, list 3
         }
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
@@ -356,28 +377,10 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         }
         __syncthreads();
 
-        // ---- P2, P3: the lists (list 3 is complete when P2 has ended, the fallback list when P3 has) -----------------------
+        // ---- P2, P3: the lists (list 3 is complete when P2 has ended) ---------------------------------------------------------
         level_pass<T, 2, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
         __syncthreads();
         level_pass<T, 3, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
-        __syncthreads();
-
-        // ---- PF: blocks with labels beyond their known set: all threads share their voxels -------------------------------
-        {
-            const int ncrowded = (int)sh.ctr[2];
-            if (tid == 0) TA_STAT(9, ncrowded);
-            const unsigned short* crowded = lists + 2 * NTHREADS;
-            constexpr int BV = SEG * BLK_M * BLK_S;
-            for (int q = tid; q < ncrowded * BV; q += NTHREADS) {
-                const int blk = crowded[q / BV], w = q % BV;
-                const int cfs = blk % NFS, cm0 = ((blk / NFS) % (BM / BLK_M)) * BLK_M, cs0 = (blk / (NFS * (BM / BLK_M))) * BLK_S;
-                const int df = w % SEG, dm = (w / SEG) % BLK_M, ds = w / (SEG * BLK_M);
-                const uint32_t f = (uint32_t)(cfs * SEG + df), m = (uint32_t)(cm0 + dm), sp = (uint32_t)(cs0 + ds);
-                if (F0 + (int)f >= nf || M0 + (int)m >= nm || S0 + (int)sp >= (int)P.own_hi) continue;
-                const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + f;
-                level_fallback_voxel<T>(sh, lt, pt, p, f, m, sp, known + blk * LV_MAXL, gF0, gM0, gS0, do_mom, do_p6, do_w18);
-            }
-        }
         __syncthreads();
 
         // ---- flush the per-brick tables ------------------------------------------------------------------------------------
