@@ -431,6 +431,7 @@ TA_HD void block_uniform_moments(uint32_t a, uint32_t b, uint32_t c, uint32_t v[
 
 // Up to CAP known labels of one block: window masks, dilations, coverage.  build<N0>() fills slots 0 .. N0 - 1 in one
 // fused pass over the window rows; extend<I>() adds slot I for one more label (the rare labels 4, 5, ... of a block).
+constexpr int LV_STATE_WORDS = 14;
 template <typename T, int CAP> struct BlockLevel {
     uint32_t lab[CAP];
     u64 M1[CAP], M2[CAP], M3[CAP], D0[CAP], D1[CAP];
@@ -485,6 +486,33 @@ template <typename T, int CAP> struct BlockLevel {
         lab[I] = L; M1[I] = m[1]; M2[I] = m[2]; M3[I] = m[3]; D0[I] = d[0]; D1[I] = d[1];
     }
 
+    // Slots 0 and 1 and the uncovered positions, parked between level 2 and level 3 of a block (field-major: lane `pos`
+    // of a warp reads and writes consecutive 64-bit words).  LV_STATE_WORDS words per block.
+    TA_HD void store_state2(u64* st, int pos, int cap) const {
+        st[0 * cap + pos] = M1[0]; st[1 * cap + pos] = M2[0]; st[2 * cap + pos] = M3[0]; st[3 * cap + pos] = D0[0];
+        st[4 * cap + pos] = D1[0]; st[5 * cap + pos] = M1[1]; st[6 * cap + pos] = M2[1]; st[7 * cap + pos] = M3[1];
+        st[8 * cap + pos] = D0[1]; st[9 * cap + pos] = D1[1]; st[10 * cap + pos] = R0; st[11 * cap + pos] = R1;
+        st[12 * cap + pos] = R2; st[13 * cap + pos] = R3;
+    }
+    TA_HD void load_state2(const u64* st, int pos, int cap, uint32_t L0, uint32_t L1, int nvf, int nvm, int nvs) {
+        static_assert(CAP >= 2, "two slots");
+        lab[0] = L0; lab[1] = L1;
+        M1[0] = st[0 * cap + pos]; M2[0] = st[1 * cap + pos]; M3[0] = st[2 * cap + pos]; D0[0] = st[3 * cap + pos];
+        D1[0] = st[4 * cap + pos]; M1[1] = st[5 * cap + pos]; M2[1] = st[6 * cap + pos]; M3[1] = st[7 * cap + pos];
+        D0[1] = st[8 * cap + pos]; D1[1] = st[9 * cap + pos]; R0 = st[10 * cap + pos]; R1 = st[11 * cap + pos];
+        R2 = st[12 * cap + pos]; R3 = st[13 * cap + pos];
+        set_centre(nvf, nvm, nvs);
+    }
+    TA_HD void set_centre(int nvf, int nvm, int nvs) {
+        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        u64 cv = 0ull;
+#pragma unroll
+        for (int r = 1; r <= BLK_M; ++r)
+            if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (ROWBITS * r);
+        cv0 = nvs >= 1 ? cv : 0ull;
+        cv1 = nvs >= 2 ? cv : 0ull;
+    }
+
     // L[0 .. N0 - 1]: distinct labels -> slots 0 .. N0 - 1.  true: they cover the window; false: `next` = a label of the
     // window that is none of them (the label at the first uncovered position).
     template <int N0>
@@ -497,12 +525,7 @@ template <typename T, int CAP> struct BlockLevel {
         neq_planes<N0>(tile, t0, L, neq);
         R0 = R1 = R2 = R3 = ALL;
         set_slots<N0, 0>(L, neq);
-        u64 cv = 0ull;
-#pragma unroll
-        for (int r = 1; r <= BLK_M; ++r)
-            if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (ROWBITS * r);
-        cv0 = nvs >= 1 ? cv : 0ull;
-        cv1 = nvs >= 2 ? cv : 0ull;
+        set_centre(nvf, nvm, nvs);
         if (!(R0 | R1 | R2 | R3)) return true;
         next = first_uncovered(tile, t0);
         return false;

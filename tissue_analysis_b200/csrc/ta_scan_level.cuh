@@ -37,6 +37,11 @@ namespace ta {
 #define TA_LEVEL_MAXL 4            // labels per block handled by bit algebra; more -> per-voxel path for the rest
 #endif
 constexpr int LV_MAXL = TA_LEVEL_MAXL;
+#ifndef TA_LEVEL_STASH
+#define TA_LEVEL_STASH 96          // list-3 blocks per brick whose two masks P2 parks for P3 (multiple of 32; 0: P3 rebuilds)
+#endif
+constexpr int LV_STASH = TA_LEVEL_STASH;
+static_assert(LV_STASH % 32 == 0 && LV_STASH <= NTHREADS, "whole warp rounds");
 #ifndef TA_LEVEL_MINB
 #define TA_LEVEL_MINB 3            // CTAs per SM the register budget is cut for: 3 -> 80 registers (some spills), 2 -> 128
 #endif
@@ -45,7 +50,8 @@ template <typename T> constexpr size_t scan_level_smem_bytes() {
     return scan_block_smem_bytes<T>() +
            256 * 4 +                               // packed row moments of every byte
            NTHREADS * LV_MAXL * 4 +                // known labels per block
-           2 * NTHREADS * 2;                       // list 2 and list 3 (block ids)
+           2 * NTHREADS * 2 +                      // list 2 and list 3 (block ids)
+           (size_t)LV_STASH * LV_STATE_WORDS * 8;  // masks of the first LV_STASH blocks of list 3, parked by P2 for P3
 }
 
 // per-voxel path for one voxel of a block whose window holds labels outside `known[0 .. LV_MAXL - 1]`: only
@@ -211,8 +217,8 @@ __device__ __forceinline__ void level_extend(const BrickShared<T>& sh, const Sca
 // the list end idle with active = false), so the merges are full-mask.
 template <typename T, int N, bool MERGE>
 __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
-                                           const uint32_t* momtab, uint32_t* known, unsigned short* lists, int F0, int M0, int S0,
-                                           u64 gF0, u64 gM0, u64 gS0, int tid) {
+                                           const uint32_t* momtab, uint32_t* known, unsigned short* lists, u64* stash, int F0, int M0,
+                                           int S0, u64 gF0, u64 gM0, u64 gS0, int tid) {
     static_assert(N == 2 || N == 3, "list 2 or list 3");
     constexpr int SEG = Vox<T>::SEG;
     constexpr int CAP = (N == 2) ? 2 : LV_MAXL;
@@ -236,12 +242,25 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
         for (int i = 0; i < N; ++i) L[i] = known[blk * LV_MAXL + i];
         bool more = false;
         uint32_t next = 0u;
-        if (active) more = !b.template build<N>(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
-        else b.clear();
+        if (N == 3 && LV_STASH > 0 && base < LV_STASH) {
+            // a whole round of parked blocks: slots 0 and 1 from the stash, one mask build for the third label
+            if (active) {
+                b.load_state2(stash, q, LV_STASH, L[0], L[1], nvf, nvm, nvs);
+                more = !b.template extend<(N == 3 ? 2 : 0)>(sh.tile, fs, m0, s0, L[N - 1], next);
+            } else {
+                b.clear();
+            }
+        } else if (active) {
+            more = !b.template build<N>(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
+        } else {
+            b.clear();
+        }
         if (N == 2) {
-            if (more) {                                           // a third label: list 3
+            if (more) {                                           // a third label: list 3; the first LV_STASH park their masks
                 known[blk * LV_MAXL + 2] = next;
-                next_list[atomicAdd(&sh.ctr[1], 1u)] = (unsigned short)blk;
+                const int pos = (int)atomicAdd(&sh.ctr[1], 1u);
+                next_list[pos] = (unsigned short)blk;
+                if (pos < LV_STASH) b.store_state2(stash, pos, LV_STASH > 0 ? LV_STASH : 1);
             }
             // both rows and the pair first: the masks are dead before the first merge loop
             const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
@@ -302,6 +321,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
     uint32_t* momtab = reinterpret_cast<uint32_t*>(sh.ctr + 16);                   // [256]
     uint32_t* known = momtab + 256;                                                // [NTHREADS * MAXL] labels per block
     unsigned short* lists = reinterpret_cast<unsigned short*>(known + NTHREADS * LV_MAXL);   // [2][NTHREADS] block ids: list 2, list 3
+    u64* stash = reinterpret_cast<u64*>(lists + 2 * NTHREADS);                     // [LV_STATE_WORDS][LV_STASH], 8-byte aligned
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
@@ -378,9 +398,9 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         __syncthreads();
 
         // ---- P2, P3: the lists (list 3 is complete when P2 has ended) ---------------------------------------------------------
-        level_pass<T, 2, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
+        level_pass<T, 2, MERGE>(sh, P, lt, pt, momtab, known, lists, stash, F0, M0, S0, gF0, gM0, gS0, tid);
         __syncthreads();
-        level_pass<T, 3, MERGE>(sh, P, lt, pt, momtab, known, lists, F0, M0, S0, gF0, gM0, gS0, tid);
+        level_pass<T, 3, MERGE>(sh, P, lt, pt, momtab, known, lists, stash, F0, M0, S0, gF0, gM0, gS0, tid);
         __syncthreads();
 
         // ---- flush the per-brick tables ------------------------------------------------------------------------------------
