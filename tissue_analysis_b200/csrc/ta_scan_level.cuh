@@ -10,10 +10,12 @@
 //   P2   list 2, full warps, one block per lane: one fused pass over the window rows builds the masks of both labels;
 //        their moments and their pair go through warp merges into the per-brick tables.  A window position covered by
 //        neither label names a third one -> list 3.
-//   P3   list 3: fused masks of the three known labels; emitted: the third label's moments and its pairs with the other
-//        two.  Lanes whose window is still uncovered add one label at a time (one more mask, its moments, its pairs with
-//        every older label) up to MAXL labels -- lists 4, 5, ... would hold a handful of blocks per brick, so they are
-//        steps of this pass instead of phases of their own (a phase costs a block barrier and leaves most warps idle).
+//   P3   list 3: the masks of the first two labels come from a stash in shared memory where P2 parked them (the first
+//        LV_STASH blocks of the list; beyond it: fused masks of all three labels), one mask build for the third label;
+//        emitted: the third label's moments and its pairs with the other two.  Lanes whose window is still uncovered
+//        add one label at a time (one more mask, its moments, its pairs with every older label) up to MAXL labels --
+//        lists 4, 5, ... would hold a handful of blocks per brick, so they are steps of this pass instead of phases of
+//        their own (a phase costs a block barrier and leaves most warps idle).
 //   PF   blocks still uncovered after MAXL labels: per-voxel path inside the warp that found them (its 32 lanes share the
 //        voxels of one block; no list, no barrier), restricted to what the steps could not emit (a label outside the
 //        block's known set is involved).
@@ -21,8 +23,8 @@
 // Cost model and expected gain: DESIGN.md section 6.  STATUS: exact on the CPU emulation of the CUDA execution model
 // (tests/host/kernel_emu_check.cpp) and, for the block arithmetic, on the host (tests/host/block_level_check.cu); compiles
 // for sm_100a; written after the round's GPU budget was spent, so it has NOT run on a GPU and is NOT part of the product
-// build (-DTA_WITH_BLOCK_KERNEL).  First run: as in ta_scan_block.cuh with TA_PAIR_PATH=level (level_simple: plain
-// atomics instead of warp merges).
+// build (-DTA_WITH_BLOCK_KERNEL).  First run: tools/r02_first_call.sh (TA_PAIR_PATH=level; level_simple: plain atomics
+// instead of warp merges).  Build knobs: -DTA_LEVEL_MAXL, -DTA_LEVEL_STASH, -DTA_LEVEL_MINB, -DTA_DEFAULT_LEVEL.
 #pragma once
 #include "ta_scan_block.cuh"
 
