@@ -488,6 +488,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "block_simple")) P.flags |= 0x4000u | 0x8000u;
         else if (!strcmp(pp, "level")) P.flags |= 0x4000u | 0x10000u;
         else if (!strcmp(pp, "level_simple")) P.flags |= 0x4000u | 0x8000u | 0x10000u;
+        else if (!strcmp(pp, "level_pf")) P.flags |= 0x4000u | 0x10000u | 0x20000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {

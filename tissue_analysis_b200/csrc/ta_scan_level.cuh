@@ -24,7 +24,7 @@
 // (tests/host/kernel_emu_check.cpp) and, for the block arithmetic, on the host (tests/host/block_level_check.cu); compiles
 // for sm_100a; written after the round's GPU budget was spent, so it has NOT run on a GPU and is NOT part of the product
 // build (-DTA_WITH_BLOCK_KERNEL).  First run: tools/r02_first_call.sh (TA_PAIR_PATH=level; level_simple: plain atomics
-// instead of warp merges).  Build knobs: -DTA_LEVEL_MAXL, -DTA_LEVEL_STASH, -DTA_LEVEL_MINB, -DTA_DEFAULT_LEVEL.
+// instead of warp merges; level_pf: with an L2 prefetch of the next brick's tile).  Build knobs: -DTA_LEVEL_MAXL, -DTA_LEVEL_STASH, -DTA_LEVEL_MINB, -DTA_DEFAULT_LEVEL.
 #pragma once
 #include "ta_scan_block.cuh"
 
@@ -355,7 +355,16 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         const unsigned int brick = sh.ctr[6 + (iter & 1u)];
         if (brick >= total) break;
         if (tid == 0) {
-            sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
+            const unsigned int nb = atomicAdd(P.brick_counter, 1u);
+            sh.ctr[6 + ((iter + 1u) & 1u)] = nb;
+            if (use_tma && (P.flags & 0x20000u) && nb < total) {
+                // experiment (TA_PAIR_PATH=level_pf): ask the L2 for the NEXT brick's tile now (SASS UTMAPF.L2.3D), so that
+                // its box copy finds the data on chip; DRAM is idle 95 % of the time
+                const int nbf_ = nb % P.nbf, nbm_ = (nb / P.nbf) % P.nbm, nbs_ = nb / (P.nbf * P.nbm);
+                TA_PTX("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                       :: "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nbf_ * BF - SEG), "r"(nbm_ * BM - 1),
+                          "r"((int)P.own_lo + nbs_ * BS - 1) : "memory");
+            }
             sh.ctr[0] = sh.ctr[1] = 0u;                                // list 2, list 3
         }
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);

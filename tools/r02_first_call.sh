@@ -13,14 +13,14 @@ LIB2=$PWD/build/libtissue_b200_block_2cta.so
 [ -f $LIB ] || TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$LIB bash tissue_analysis_b200/csrc/build.sh
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> $out
 # 1. parity of every experimental kernel on the existing suite (the C ABI is the same; TA_PAIR_PATH picks the kernel)
-for path in level level_simple block block_simple; do
+for path in level level_pf level_simple block block_simple; do
   TA_LIB_PATH=$LIB TA_PAIR_PATH=$path timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/r02_parity_$path.log 2>&1
   echo "parity $path: exit $? | $(tail -1 gpurun_out/r02_parity_$path.log)" >> $out
 done
 # 2. scan times (third pass of profile_scan.py)
 for cfg in C3 C2 C4 C1; do
   echo "== $cfg product: $(timeout 600 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep 'pass 2')" >> $out
-  for path in level level_simple block; do
+  for path in level level_pf level_simple block; do
     echo "== $cfg $path: $(TA_LIB_PATH=$LIB TA_PAIR_PATH=$path timeout 600 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep 'pass 2\|rror' | head -2)" >> $out
   done
   if [ -f $LIB2 ]; then
