@@ -111,7 +111,7 @@ static int run_levels(const uint4* tile, int fs, int m0, int s0, int nvf, int nv
     uint32_t next = 0u, v[16], inc[4];
     {
         BlockLevel<T, 2> b;
-        const bool covered = b.template build<2>(tile, fs, m0, s0, nvf, nvm, nvs, L, next);
+        const bool covered = b.template build<2, true>(tile, fs, m0, s0, nvf, nvm, nvs, L, next);      // L[0], L[1] = min, max
         for (int i = 0; i < 2; ++i) if (b.label_moments(i, tab, v)) sink.label(b.lab[i], v);
         if (b.pair_increments(0, 1, true, true, inc)) sink.pair(b.lab[0], b.lab[1], inc);
         if (covered) return 2;

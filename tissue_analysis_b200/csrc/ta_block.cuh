@@ -399,6 +399,30 @@ template <int N> struct BlockRowNeq<uint16_t, N> {
         }
     }
 };
+// The same for level 2, whose two labels are the SMALLEST and the LARGEST label of the window (block_window_minmax over
+// exactly these lanes): every lane of x - A and of B - x is non-negative, so the packed 32-bit subtractions never borrow
+// across the 16-bit lanes and are exact per lane.  A subtraction may run on the FMA pipe (IMAD), the xor of the general
+// form cannot -- the mask build is bound by the ALU pipe.
+struct BlockRowNeqMinMax16 {
+    static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
+        const uint4 c = tile[t];
+        const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
+        const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16), one = 0x00010001u;
+        const uint32_t pa = L[0] * 0x00010001u, pb = L[1] * 0x00010001u;
+        {
+            const uint32_t tt = ta_vminu2(c.x - pa, one) | (ta_vminu2(c.y - pa, one) << 2) | (ta_vminu2(c.z - pa, one) << 4) |
+                                (ta_vminu2(c.w - pa, one) << 6);
+            const uint32_t te = ta_vminu2(ew - pa, one);
+            out[0] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
+        }
+        {
+            const uint32_t tt = ta_vminu2(pb - c.x, one) | (ta_vminu2(pb - c.y, one) << 2) | (ta_vminu2(pb - c.z, one) << 4) |
+                                (ta_vminu2(pb - c.w, one) << 6);
+            const uint32_t te = ta_vminu2(pb - ew, one);
+            out[1] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
+        }
+    }
+};
 template <int N> struct BlockRowNeq<uint32_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t];
@@ -446,7 +470,8 @@ template <typename T, int CAP> struct BlockLevel {
     template <int I> TA_HD void clear_slot() { lab[I] = 0u; M1[I] = M2[I] = M3[I] = D0[I] = D1[I] = 0ull; }
 
     // NOT-equal planes of N labels, one fused pass: neq[i][p]
-    template <int N> static TA_HD void neq_planes(const uint4* tile, int t0, const uint32_t* L, u64 neq[][BLK_S + 2]) {
+    template <int N, bool MINMAX = false>
+    static TA_HD void neq_planes(const uint4* tile, int t0, const uint32_t* L, u64 neq[][BLK_S + 2]) {
         constexpr int ROWBITS = Blk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
 #pragma unroll
         for (int p = 0; p < BLK_S + 2; ++p) {
@@ -458,7 +483,10 @@ template <typename T, int CAP> struct BlockLevel {
 #pragma unroll
                 for (int r = HALF - 1; r >= 0; --r) {                  // descending: acc = (acc << ROWBITS) + row
                     uint32_t row[N];
-                    BlockRowNeq<T, N>::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
+                    if constexpr (MINMAX && N == 2 && sizeof(T) == 2)
+                        BlockRowNeqMinMax16::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
+                    else
+                        BlockRowNeq<T, N>::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
 #pragma unroll
                     for (int i = 0; i < N; ++i) half[i][h] = (half[i][h] << ROWBITS) + row[i];
                 }
@@ -515,14 +543,15 @@ template <typename T, int CAP> struct BlockLevel {
 
     // L[0 .. N0 - 1]: distinct labels -> slots 0 .. N0 - 1.  true: they cover the window; false: `next` = a label of the
     // window that is none of them (the label at the first uncovered position).
-    template <int N0>
+    // MINMAX (N0 == 2 only): L[0] / L[1] are the smallest / largest label of the window, as block_window_minmax returns them.
+    template <int N0, bool MINMAX = false>
     TA_HD bool build(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, const uint32_t* L, uint32_t& next) {
         static_assert(N0 <= CAP, "more labels than slots");
         constexpr int ROWBITS = Blk<T>::ROWBITS;
         constexpr u64 ALL = Blk<T>::PLANE_ALL;
         const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
         u64 neq[N0][BLK_S + 2];
-        neq_planes<N0>(tile, t0, L, neq);
+        neq_planes<N0, MINMAX>(tile, t0, L, neq);
         R0 = R1 = R2 = R3 = ALL;
         set_slots<N0, 0>(L, neq);
         set_centre(nvf, nvm, nvs);

@@ -253,7 +253,8 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
                 b.clear();
             }
         } else if (active) {
-            more = !b.template build<N>(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
+            // list 2 carries (min, max) of the window: the borrow-free subtraction form of the compares
+            more = !b.template build<N, N == 2>(sh.tile, fs, m0, s0, nvf, nvm, nvs, L, next);
         } else {
             b.clear();
         }
