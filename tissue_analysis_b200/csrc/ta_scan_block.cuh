@@ -238,18 +238,19 @@ __device__ __forceinline__ bool block_uniform_tile(const BrickShared<T>& sh, con
     const int nf = (int)P.nf, nm = (int)P.nm;
     const bool do_mom = P.flags & 1u;
     const uint32_t ref_label = tileT[SEG];
-    bool all_ref = true;
+    // OR of the xors against the reference label: the 16 brick segments of every tile row as vectors (one LOP3 per word),
+    // then the two halo lanes of every row (one row per thread)
+    uint32_t diff = 0u;
     {
+        constexpr int ROWE = ROWV * SEG;
         const uint32_t pat = (SEG == 8) ? ref_label * 0x00010001u : ref_label;
-        for (int i = tid; i < TILE_SEGS; i += NTHREADS) {
-            const int fsv = i % ROWV;
-            const uint4 v = sh.tile[i];
-            // halo segments: only the lane beside the brick
-            if (fsv == 0) all_ref = all_ref && (((SEG == 8) ? (v.w >> 16) : v.w) == ref_label);
-            else if (fsv == ROWV - 1) all_ref = all_ref && (((SEG == 8) ? (v.x & 0xFFFFu) : v.x) == ref_label);
-            else all_ref = all_ref && (v.x == pat) && (v.y == pat) && (v.z == pat) && (v.w == pat);
+        for (int r = tid / NFS; r < TILE_ROWS; r += NTHREADS / NFS) {
+            const uint4 v = sh.tile[r * ROWV + 1 + (tid % NFS)];
+            diff |= (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
         }
+        if (tid < TILE_ROWS) diff |= ((uint32_t)tileT[tid * ROWE + SEG - 1] ^ ref_label) | ((uint32_t)tileT[tid * ROWE + SEG + BF] ^ ref_label);
     }
+    const bool all_ref = (diff == 0u);
     if (__syncthreads_and(all_ref)) {
         if (tid == 0 && do_mom) {
             const uint32_t a = (uint32_t)min(BF, nf - F0), b = (uint32_t)min(BM, nm - M0),
