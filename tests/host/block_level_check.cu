@@ -1,6 +1,6 @@
 // CPU check of the LEVEL formulation of the block pass (csrc/ta_block.cuh: block_window_minmax, BlockLevel<T, N>; test
-// infrastructure, no GPU needed).  A volume of several bricks is tiled as the scan kernel tiles it; every 8 x 4 x 2 (uint32:
-// 4 x 4 x 2) block goes through level 1 (window min / max, closed-form moments when they agree), level 2 (fused masks of both
+// infrastructure, no GPU needed).  A volume of several bricks is tiled as the scan kernel tiles it; every 8 x 4 x 2 block
+// (uint32: two 16-byte segments wide) goes through level 1 (window min / max, closed-form moments when they agree), level 2 (fused masks of both
 // labels), level 3 (fused masks of three labels) with its extension steps up to MAXL labels (one more mask per step;
 // emitted: what the step adds) and, when labels are still uncovered, the per-voxel fallback restricted to contributions
 // with a label outside the known set.  The global tables must equal a direct pass.
@@ -164,8 +164,8 @@ static int run_case(int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_
             for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (T)V.at(F0 + e - SEG, M0 + m, S0 + s);
         }
         for (int s0 = 0; s0 < BS && S0 + s0 < own_hi; s0 += BLK_S) for (int m0 = 0; m0 < BM && M0 + m0 < nm; m0 += BLK_M)
-            for (int fs = 0; fs < NFS && F0 + fs * SEG < nf; ++fs) {
-                const int nvf = std::min(SEG, nf - F0 - fs * SEG), nvm = std::min(BLK_M, nm - M0 - m0),
+            for (int fs = 0; fs < NFS && F0 + fs * SEG < nf; fs += LvBlk<T>::BSEGS) {
+                const int nvf = std::min((int)LvBlk<T>::BW, nf - F0 - fs * SEG), nvm = std::min(BLK_M, nm - M0 - m0),
                           nvs = std::min(BLK_S, own_hi - S0 - s0);
                 const Sink sink{&gotL, &gotP, (uint32_t)(fs * SEG), (uint32_t)m0, (uint32_t)s0, (u64)F0, (u64)M0, (u64)(S0 + slow_offset)};
                 const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);

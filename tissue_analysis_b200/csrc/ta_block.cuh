@@ -15,7 +15,8 @@
 //
 // No atomics, no hash, no worklist inside the block.  Everything here is host-compilable (TA_HD);
 // tests/host/block_host_check.cu runs it over whole tiles against a brute-force count.  Both label widths: a block row is
-// one 16-byte segment, i.e. 8 x 4 x 2 voxels for uint16 (window planes of 60 bits) and 4 x 4 x 2 for uint32 (36 bits).
+// one 16-byte segment, i.e. 8 x 4 x 2 voxels for uint16 (window planes of 60 bits) and 4 x 4 x 2 for uint32 (36 bits);
+// the level formulation further down uses 8 x 4 x 2 for both (LvBlk).
 #pragma once
 #include "ta_scan.cuh"
 
@@ -94,9 +95,8 @@ TA_HD uint32_t block_byte_moments(uint32_t b) {
 
 // 18-neighbourhood dilation of a label's window masks, for the two centre planes (p = 1, 2).  Bits outside the centre
 // (halo columns / rows, bits beyond the plane) are not meaningful: the callers AND with centre masks.
-template <typename T>
-TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) {
-    constexpr int BLK_ROWBITS = Blk<T>::ROWBITS;
+template <int BLK_ROWBITS>
+TA_HD void block_dilate18_rb(const u64 mask[4], u64 dil[2]) {
     u64 own[4], cross[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -109,6 +109,8 @@ TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) {
     dil[0] = own[1] | cross[0] | cross[2];
     dil[1] = own[2] | cross[1] | cross[3];
 }
+
+template <typename T> TA_HD void block_dilate18(const u64 mask[4], u64 dil[2]) { block_dilate18_rb<Blk<T>::ROWBITS>(mask, dil); }
 
 // Move a label's sums from coordinates local to a block (or brick) to coordinates shifted by (F, M, S): the algebra of
 // the kernel's label_to_global, in 32 bits (a brick: coordinates < 128, at most 16 384 voxels, sums < 2^32).
@@ -318,6 +320,18 @@ template <typename T, int MAXLAB> struct BlockSlots {
 //
 // Every list is processed by full warps of blocks with the same label count, so the cost follows the mean of the label
 // count distribution, not the warp maximum.  tests/host/block_level_check.cu runs this on the CPU against a direct pass.
+// Block geometry of the level formulation: 8 x 4 x 2 voxels for BOTH label widths (uint32: two 16-byte segments per block
+// row), so that the window planes, the dilation, the moments table and the pair counts are the same code and a uint32
+// voxel costs as little of them as a uint16 one.
+template <typename T> struct LvBlk {
+    static constexpr int BW = 8;                               // block width in voxels
+    static constexpr int BSEGS = BW / Vox<T>::SEG;             // segments per block row: 1 (uint16) or 2 (uint32)
+    static constexpr int NFB = NFS / BSEGS;                    // blocks per brick row
+    static constexpr int NBLK = NFB * (BM / BLK_M) * (BS / BLK_S);   // blocks per brick: 256 or 128
+    static constexpr int ROWBITS = BW + 2;
+    static constexpr u64 PLANE_ALL = (1ull << (ROWBITS * (BLK_M + 2))) - 1ull;
+    static constexpr uint32_t LANES = (1u << BW) - 1u;
+};
 TA_HD uint32_t ta_vmaxu2(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
     return __vmaxu2(a, b);
@@ -359,22 +373,18 @@ template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, 
     hi = (mx & 0xFFFFu) > (mx >> 16) ? (mx & 0xFFFFu) : (mx >> 16);
 }
 template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap) {
-    const int oa = swap ? 4 : -1, ob = swap ? -1 : 4;
+    const int oa = swap ? 8 : -1, ob = swap ? -1 : 8;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
 #pragma unroll
         for (int r = 0; r < BLK_M + 2; ++r) {
             const int t = t0 + p * PLANEV + r * ROWV;
-            const uint4 c = tile[t];
+            const uint4 c = tile[t], d = tile[t + 1];
             const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
-            const uint32_t a = e[oa], b = e[ob];
-            const uint32_t n1 = c.x < c.y ? c.x : c.y, n2 = c.z < c.w ? c.z : c.w, n3 = a < b ? a : b;
-            const uint32_t x1 = c.x > c.y ? c.x : c.y, x2 = c.z > c.w ? c.z : c.w, x3 = a > b ? a : b;
-            const uint32_t n12 = n1 < n2 ? n1 : n2, x12 = x1 > x2 ? x1 : x2;
-            const uint32_t n = n12 < n3 ? n12 : n3, x = x12 > x3 ? x12 : x3;
-            mn = mn < n ? mn : n;
-            mx = mx > x ? mx : x;
+            const uint32_t v[10] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, e[oa], e[ob]};
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { mn = mn < v[i] ? mn : v[i]; mx = mx > v[i] ? mx : v[i]; }
         }
         block_sched_fence();
     }
@@ -425,14 +435,15 @@ struct BlockRowNeqMinMax16 {
 };
 template <int N> struct BlockRowNeq<uint32_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
-        const uint4 c = tile[t];
+        const uint4 c = tile[t], d = tile[t + 1];
         const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
-        const uint32_t a = e[-1], b = e[4];
+        const uint32_t a = e[-1], b = e[8];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t l = L[i];
             out[i] = (a != l ? 1u : 0u) | (c.x != l ? 2u : 0u) | (c.y != l ? 4u : 0u) | (c.z != l ? 8u : 0u) |
-                     (c.w != l ? 16u : 0u) | (b != l ? 32u : 0u);
+                     (c.w != l ? 16u : 0u) | (d.x != l ? 32u : 0u) | (d.y != l ? 64u : 0u) | (d.z != l ? 128u : 0u) |
+                     (d.w != l ? 256u : 0u) | (b != l ? 512u : 0u);
         }
     }
 };
@@ -472,7 +483,7 @@ template <typename T, int CAP> struct BlockLevel {
     // NOT-equal planes of N labels, one fused pass: neq[i][p]
     template <int N, bool MINMAX = false>
     static TA_HD void neq_planes(const uint4* tile, int t0, const uint32_t* L, u64 neq[][BLK_S + 2]) {
-        constexpr int ROWBITS = Blk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
+        constexpr int ROWBITS = LvBlk<T>::ROWBITS, HALF = (BLK_M + 2) / 2;
 #pragma unroll
         for (int p = 0; p < BLK_S + 2; ++p) {
             uint32_t half[N][2];
@@ -498,19 +509,19 @@ template <typename T, int CAP> struct BlockLevel {
     }
     // first uncovered position -> its label
     TA_HD uint32_t first_uncovered(const uint4* tile, int t0) const {
-        constexpr int SEG = Blk<T>::SEG, ROWBITS = Blk<T>::ROWBITS;
+        constexpr int SEG = Vox<T>::SEG, ROWBITS = LvBlk<T>::ROWBITS;
         const int p = R0 ? 0 : R1 ? 1 : R2 ? 2 : 3;
         const u64 rp = R0 ? R0 : R1 ? R1 : R2 ? R2 : R3;
         const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
         return reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
     }
     template <int I> TA_HD void set_slot(uint32_t L, const u64 neq[BLK_S + 2]) {
-        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        constexpr u64 ALL = LvBlk<T>::PLANE_ALL;
         R0 &= neq[0]; R1 &= neq[1]; R2 &= neq[2]; R3 &= neq[3];
         u64 m[4], d[2];
 #pragma unroll
         for (int p = 0; p < 4; ++p) m[p] = ~neq[p] & ALL;
-        block_dilate18<T>(m, d);
+        block_dilate18_rb<LvBlk<T>::ROWBITS>(m, d);
         lab[I] = L; M1[I] = m[1]; M2[I] = m[2]; M3[I] = m[3]; D0[I] = d[0]; D1[I] = d[1];
     }
 
@@ -532,7 +543,7 @@ template <typename T, int CAP> struct BlockLevel {
         set_centre(nvf, nvm, nvs);
     }
     TA_HD void set_centre(int nvf, int nvm, int nvs) {
-        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        constexpr int ROWBITS = LvBlk<T>::ROWBITS;
         u64 cv = 0ull;
 #pragma unroll
         for (int r = 1; r <= BLK_M; ++r)
@@ -547,8 +558,8 @@ template <typename T, int CAP> struct BlockLevel {
     template <int N0, bool MINMAX = false>
     TA_HD bool build(const uint4* tile, int fs, int m0, int s0, int nvf, int nvm, int nvs, const uint32_t* L, uint32_t& next) {
         static_assert(N0 <= CAP, "more labels than slots");
-        constexpr int ROWBITS = Blk<T>::ROWBITS;
-        constexpr u64 ALL = Blk<T>::PLANE_ALL;
+        constexpr int ROWBITS = LvBlk<T>::ROWBITS;
+        constexpr u64 ALL = LvBlk<T>::PLANE_ALL;
         const int t0 = s0 * PLANEV + m0 * ROWV + (fs + 1);
         u64 neq[N0][BLK_S + 2];
         neq_planes<N0, MINMAX>(tile, t0, L, neq);
@@ -582,7 +593,7 @@ template <typename T, int CAP> struct BlockLevel {
     // moments and box of label i over its centre voxels, block-local coordinates; `tab` = block_byte_moments_packed of
     // every byte (256 entries, shared memory in the kernel).  false: no centre voxel.
     TA_HD bool label_moments(int i, const uint32_t* tab, uint32_t v[16]) const {
-        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        constexpr int ROWBITS = LvBlk<T>::ROWBITS;
         const u64 c0 = M1[i] & cv0, c1 = M2[i] & cv1;
         if (!(c0 | c1)) return false;
         uint32_t a0 = 0u, a1 = 0u, a2 = 0u, ap = 0u, apm = 0u, colmask = 0u, rows = 0u;
@@ -590,7 +601,7 @@ template <typename T, int CAP> struct BlockLevel {
         for (int p = 0; p < 2; ++p)
 #pragma unroll
             for (int r = 0; r < BLK_M; ++r) {
-                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (ROWBITS * (r + 1) + 1)) & Blk<T>::LANES;
+                const uint32_t b = (uint32_t)((p ? c1 : c0) >> (ROWBITS * (r + 1) + 1)) & LvBlk<T>::LANES;
                 const uint32_t t = tab[b];
                 a0 += t; a1 += (uint32_t)r * t; a2 += (uint32_t)(r * r) * t;
                 if (p) { ap += t; apm += (uint32_t)r * t; }
@@ -610,7 +621,7 @@ template <typename T, int CAP> struct BlockLevel {
     // both directions of the unordered pair (i, j) as packed increments of the per-brick pair table
     // ([w18|f0] [f1|f2] [f3|f4] [f5|-]: a face goes to slot 2k when its lower-index voxel carries the smaller label)
     TA_HD bool pair_increments(int i, int j, bool do_p6, bool do_w18, uint32_t inc[4]) const {
-        constexpr int ROWBITS = Blk<T>::ROWBITS;
+        constexpr int ROWBITS = LvBlk<T>::ROWBITS;
         const u64 ci0 = M1[i] & cv0, ci1 = M2[i] & cv1, cj0 = M1[j] & cv0, cj1 = M2[j] & cv1;
         uint32_t w18 = 0u, fi[3] = {0u, 0u, 0u}, fj[3] = {0u, 0u, 0u};
         if (do_w18)

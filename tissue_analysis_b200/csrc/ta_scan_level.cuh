@@ -5,7 +5,7 @@
 // labels (warp maximum 3.98 against a lane mean of 1.85 on C3-like tissue), and the 41 % of the blocks whose window is one
 // label still build a mask.  Here the label count is a property of a LIST:
 //
-//   P1   one 8 x 4 x 2 block per thread: min / max label of its window.  Equal: closed-form moments, merged per warp.
+//   P1   one 8 x 4 x 2 block per thread (uint32: two segments wide, 128 per brick): min / max label of its window.  Equal: closed-form moments, merged per warp.
 //        Different: the block goes to list 2 with both labels.
 //   P2   list 2, full warps, one block per lane: one fused pass over the window rows builds the masks of both labels;
 //        their moments and their pair go through warp merges into the per-brick tables.  A window position covered by
@@ -54,6 +54,15 @@ template <typename T> constexpr size_t scan_level_smem_bytes() {
            NTHREADS * LV_MAXL * 4 +                // known labels per block
            2 * NTHREADS * 2 +                      // list 2 and list 3 (block ids)
            (size_t)LV_STASH * LV_STATE_WORDS * 8;  // masks of the first LV_STASH blocks of list 3, parked by P2 for P3
+}
+
+// block id (0 .. NBLK - 1) -> first segment, first row and first plane inside the brick
+template <typename T>
+__device__ __forceinline__ void level_block_origin(int blk, int& fs, int& m0, int& s0) {
+    constexpr int NFB = LvBlk<T>::NFB;
+    fs = (blk % NFB) * LvBlk<T>::BSEGS;
+    m0 = ((blk / NFB) % (BM / BLK_M)) * BLK_M;
+    s0 = (blk / (NFB * (BM / BLK_M))) * BLK_S;
 }
 
 // per-voxel path for one voxel of a block whose window holds labels outside `known[0 .. LV_MAXL - 1]`: only
@@ -234,8 +243,9 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
         if (lane == 0) TA_STAT(N == 2 ? 4 : 6, 1);
         if (active) TA_STAT(N == 2 ? 3 : 5, 1);
         const int blk = active ? (int)list[q] : 0;
-        const int fs = blk % NFS, m0 = ((blk / NFS) % (BM / BLK_M)) * BLK_M, s0 = (blk / (NFS * (BM / BLK_M))) * BLK_S;
-        const int nvf = min(SEG, (int)P.nf - (F0 + fs * SEG)), nvm = min(BLK_M, (int)P.nm - (M0 + m0)),
+        int fs, m0, s0;
+        level_block_origin<T>(blk, fs, m0, s0);
+        const int nvf = min(LvBlk<T>::BW, (int)P.nf - (F0 + fs * SEG)), nvm = min(BLK_M, (int)P.nm - (M0 + m0)),
                   nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
         const uint32_t bF = (uint32_t)(fs * SEG), bM = (uint32_t)m0, bS = (uint32_t)s0;
         BlockLevel<T, CAP> b;
@@ -288,11 +298,12 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
                 fm &= fm - 1u;
                 const int cblk = __shfl_sync(0xffffffffu, blk, src);
                 if (lane == 0) TA_STAT(9, 1);
-                const int cfs = cblk % NFS, cm0 = ((cblk / NFS) % (BM / BLK_M)) * BLK_M, cs0 = (cblk / (NFS * (BM / BLK_M))) * BLK_S;
-                constexpr int BV = SEG * BLK_M * BLK_S, ROWE = ROWV * SEG;
+                int cfs, cm0, cs0;
+                level_block_origin<T>(cblk, cfs, cm0, cs0);
+                constexpr int BW = LvBlk<T>::BW, BV = BW * BLK_M * BLK_S, ROWE = ROWV * SEG;
                 const T* tileT = reinterpret_cast<const T*>(sh.tile);
                 for (int w = lane; w < BV; w += 32) {
-                    const int df = w % SEG, dm = (w / SEG) % BLK_M, ds = w / (SEG * BLK_M);
+                    const int df = w % BW, dm = (w / BW) % BLK_M, ds = w / (BW * BLK_M);
                     const uint32_t f = (uint32_t)(cfs * SEG + df), m = (uint32_t)(cm0 + dm), sp = (uint32_t)(cs0 + ds);
                     if (F0 + (int)f >= (int)P.nf || M0 + (int)m >= (int)P.nm || S0 + (int)sp >= (int)P.own_hi) continue;
                     const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + f;
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, TA_LEVEL_MINB)
 scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::PKey PKey;
     constexpr int SEG = Vox<T>::SEG, ROWE = ROWV * SEG, BF = NFS * SEG;
-    static_assert(NTHREADS == NFS * (BM / BLK_M) * (BS / BLK_S), "one block per thread");
+    static_assert(NTHREADS >= LvBlk<T>::NBLK, "at most one block per thread in P1");
     static_assert(LV_MAXL >= 3 && LV_MAXL <= 8, "labels per block handled by masks");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -378,10 +389,11 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
 
         // ---- P1: one block per thread, window min / max ------------------------------------------------------------------
         {
-            const int fs = tid % NFS, m0 = ((tid / NFS) % (BM / BLK_M)) * BLK_M, s0 = (tid / (NFS * (BM / BLK_M))) * BLK_S;
-            const int nvf = min(SEG, nf - (F0 + fs * SEG)), nvm = min(BLK_M, nm - (M0 + m0)),
+            int fs, m0, s0;
+            level_block_origin<T>(tid % LvBlk<T>::NBLK, fs, m0, s0);
+            const int nvf = min(LvBlk<T>::BW, nf - (F0 + fs * SEG)), nvm = min(BLK_M, nm - (M0 + m0)),
                       nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
-            const bool valid = (nvf > 0 && nvm > 0 && nvs > 0);
+            const bool valid = (tid < LvBlk<T>::NBLK && nvf > 0 && nvm > 0 && nvs > 0);
             uint32_t lo = 0u, hi = 0u;
             if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi, (tid & 16) != 0);
             const bool one = valid && lo == hi, many = valid && lo != hi;
