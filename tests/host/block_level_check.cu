@@ -161,7 +161,7 @@ static int run_case(int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_
     for (int S0 = own_lo; S0 < own_hi; S0 += BS) for (int M0 = 0; M0 < nm; M0 += BM) for (int F0 = 0; F0 < nf; F0 += BF) {
         for (int r = 0; r < TILE_ROWS; ++r) {
             const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
-            for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (T)V.at(F0 + e - SEG, M0 + m, S0 + s);
+            for (int e = 0; e < ROWE; ++e) tl[(size_t)r * ROWE + e] = (T)V.at(F0 + e - SEG - 1, M0 + m, S0 + s);      // the SHIFTED tile
         }
         for (int s0 = 0; s0 < BS && S0 + s0 < own_hi; s0 += BLK_S) for (int m0 = 0; m0 < BM && M0 + m0 < nm; m0 += BLK_M)
             for (int fs = 0; fs < NFS && F0 + fs * SEG < nf; fs += LvBlk<T>::BSEGS) {

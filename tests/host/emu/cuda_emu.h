@@ -6,8 +6,8 @@
 //     warp-wide rendezvous (full masks only, which is all the kernels use) -- a fiber that arrives yields until the last
 //     participant has arrived and computed everybody's result;
 //   * atomics are plain read-modify-writes (the fibers are cooperative, one OS thread);
-//   * inline PTX is swallowed (the kernels spell it TA_PTX(...)): they are run with vec_ok = 0 and use_tma = 0, i.e. on
-//     their scalar staging path, the only path without PTX;
+//   * inline PTX is swallowed (the kernels spell it TA_PTX(...)); the TMA box copy and its mbarrier have plain-code
+//     stand-ins under TA_EMU_TMA (ta_scan.cuh), so use_tma = 1 runs too; the cp.async path (vec_ok) does not;
 //   * a scheduler round in which nothing progresses is reported as a deadlock (a missing participant of a collective).
 //
 // Include this INSTEAD of compiling with nvcc, before the kernel headers:  #include "emu/cuda_emu.h"
@@ -246,7 +246,7 @@ inline unsigned __vminu2(unsigned a, unsigned b) {
     return l | (h << 16);
 }
 inline long long clock64() { return 0; }
-inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+inline void __trap() { fprintf(stderr, "emu: __trap() in thread %d of block %u\n", emu::g_cur, emu::g_blockIdx.x); abort(); }
 inline void __threadfence_system() {}
 inline void __threadfence() {}
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }

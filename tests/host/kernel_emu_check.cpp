@@ -6,6 +6,7 @@
 // Usage: kernel_emu_check <seed> ; exit code 0 = every case equal.
 #include "emu/cuda_emu.h"
 
+#define TA_EMU_TMA 1
 static unsigned long long g_user_stat[16];
 #define TA_STAT(which, n) (g_user_stat[which] += (unsigned long long)(n))
 
@@ -14,6 +15,7 @@ static unsigned long long g_user_stat[16];
 #include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
+void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
 
 using namespace ta;
 
@@ -58,7 +60,7 @@ static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
-                    unsigned seed) {
+                    unsigned seed, int use_tma = 0) {
     std::mt19937 rng(seed);
     Vol V{nf, nm, nbuf, std::vector<uint32_t>((size_t)nf * nm * nbuf)};
     const uint32_t top = sizeof(T) == 2 ? 4000u : 9000u;            // dense label table: keep it small
@@ -105,9 +107,16 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     P.vol = vol.data(); P.nf = nf; P.nm = nm; P.ns = nbuf; P.own_lo = own_lo; P.own_hi = own_hi; P.slow_offset = slow_offset;
     const int seg = 16 / (int)sizeof(T);
     P.nbf = (nf + NFS * seg - 1) / (NFS * seg); P.nbm = (nm + BM - 1) / BM; P.nbs = (own_hi - own_lo + BS - 1) / BS;
-    P.flags = 7u; P.vec_ok = 0; P.use_tma = 0; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
+    P.flags = 7u; P.vec_ok = 0; P.use_tma = use_tma; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
+    if (use_tma && which >= LEVEL_MERGE) P.flags |= (seed & 2u) ? 0x20000u : 0u;      // with and without the L2 prefetch (a no-op here)
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
+    {
+        // what ta_api.cu encodes for the kernels: the bound buffer, one box = tile (brick + halo)
+        ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), ROWV * seg, BM + 2, BS + 2};
+        static_assert(sizeof(ta::EmuTmap) <= sizeof(CUtensorMap), "the emulated map lives in the bytes of the real one");
+        memcpy(&tmap, &em, sizeof em);
+    }
     bool ok = true;
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
         ok = emu::run_block(block, 2, NTHREADS, [&]() {
@@ -137,9 +146,9 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     }
     if (!ok || status[0] || status[1] || gotL != refL || gotP != refP) {
         fprintf(stderr, "MISMATCH %s T=%d nf=%d nm=%d nbuf=%d own=[%d,%d) labels=%d mode=%d seed=%u: run %s, status %u %u, labels %zu/%zu "
-                        "(equal %d), pairs %zu/%zu (equal %d)\n", which_name[which], (int)sizeof(T), nf, nm, nbuf, own_lo, own_hi, nlabels,
+                        "(equal %d), pairs %zu/%zu (equal %d)%s\n", which_name[which], (int)sizeof(T), nf, nm, nbuf, own_lo, own_hi, nlabels,
                 mode, seed, ok ? "ok" : "DEADLOCK", status[0], status[1], gotL.size(), refL.size(), (int)(gotL == refL), gotP.size(),
-                refP.size(), (int)(gotP == refP));
+                refP.size(), (int)(gotP == refP), use_tma ? " [emulated TMA staging]" : "");
         return 1;
     }
     return 0;
@@ -188,8 +197,9 @@ int main(int argc, char** argv) {
         // c % 11 == 3: hundreds of labels in noise -- the per-brick label and pair tables fill up and spill to the global ones
         const int nl = 1 + rng() % (c % 11 == 3 ? 300 : c % 7 == 0 ? 40 : 12), mode = c % 13 == 5 ? 2 : ((c / NWHICH) % 2 == 0 || c % 11 == 3) ? 0 : 1;
         const unsigned seed = rng();
-        bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed)
-                    : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed);
+        const int use_tma = (c / NWHICH + c) % 2;          // every kernel alternates between the scalar and the (emulated) TMA staging
+        bad += wide ? run_case<uint32_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed, use_tma)
+                    : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed, use_tma);
         ++ran;
     }
     printf("kernel_emu_check: %d kernel runs on the CPU emulation, %d mismatches\n", ran, bad);

@@ -3,7 +3,9 @@ collectives are rendezvous points, atomics are plain) against a direct pass over
 
 Covers the source of the product kernel scan_kernel<T, false, false> for uint16 and uint32 (march, worklists, per-voxel
 pair phases, flush, slab ownership, ragged bricks), its one-hot instantiation, the experimental block kernels and the
-level kernels (ta_scan_level.cuh), each with and without warp merges -- on the scalar staging path (vec_ok = 0, use_tma = 0), the only one without inline PTX.  g++ only.
+level kernels (ta_scan_level.cuh), each with and without warp merges -- on the scalar staging path and on the TMA staging
+path with the box copy itself emulated (zero fill outside the buffer, re-clamping of edge tiles, the shifted tile of the
+level kernel).  g++ only.
 The GPU parity tests stay the authority for the compiled kernels; this one finds logic errors without a GPU.
 """
 import os

@@ -348,13 +348,13 @@ TA_HD void block_sched_fence() {
 #endif
 }
 
-// Smallest and largest label of the window whose first row (m0 - 1, s0 - 1) is vector t0.  `swap` exchanges the order of
-// the two edge-lane loads of every row (the result does not depend on it): segments are 16 bytes apart, so the 32 edge
-// loads of a warp fall on 8 banks; when one half warp reads its left edges while the other reads its right edges they
-// fall on 16.
-template <typename T> TA_HD void block_window_minmax(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap = false);
-template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap) {
-    const int oa = swap ? 8 : -1, ob = swap ? -1 : 8;
+// The level formulation reads a SHIFTED tile (block_stage_tile<T, 1>: brick column f at tile element SEG + 1 + f): the
+// window row of a block (columns -1 .. 8 relative to the block) starts on a 16-byte vector.  uint16: one vector (columns
+// -1 .. 6) + the first word of the next (columns 7, 8); uint32: two vectors + the first two words of the third.
+//
+// Smallest and largest label of the window whose first row (m0 - 1, s0 - 1) starts at vector t0.
+template <typename T> TA_HD void block_window_minmax(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi);
+template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
@@ -362,18 +362,16 @@ template <> TA_HD void block_window_minmax<uint16_t>(const uint4* tile, int t0, 
         for (int r = 0; r < BLK_M + 2; ++r) {
             const int t = t0 + p * PLANEV + r * ROWV;
             const uint4 c = tile[t];
-            const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
-            const uint32_t ew = (uint32_t)e[oa] | ((uint32_t)e[ob] << 16);
-            mn = ta_vminu2(ta_vminu2(ta_vminu2(mn, c.x), ta_vminu2(c.y, c.z)), ta_vminu2(c.w, ew));
-            mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(mx, c.x), ta_vmaxu2(c.y, c.z)), ta_vmaxu2(c.w, ew));
+            const uint32_t w = reinterpret_cast<const uint32_t*>(tile + t + 1)[0];
+            mn = ta_vminu2(ta_vminu2(ta_vminu2(mn, c.x), ta_vminu2(c.y, c.z)), ta_vminu2(c.w, w));
+            mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(mx, c.x), ta_vmaxu2(c.y, c.z)), ta_vmaxu2(c.w, w));
         }
         block_sched_fence();
     }
     lo = (mn & 0xFFFFu) < (mn >> 16) ? (mn & 0xFFFFu) : (mn >> 16);
     hi = (mx & 0xFFFFu) > (mx >> 16) ? (mx & 0xFFFFu) : (mx >> 16);
 }
-template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi, bool swap) {
-    const int oa = swap ? 8 : -1, ob = swap ? -1 : 8;
+template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, uint32_t& lo, uint32_t& hi) {
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int p = 0; p < BLK_S + 2; ++p) {
@@ -381,8 +379,8 @@ template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, 
         for (int r = 0; r < BLK_M + 2; ++r) {
             const int t = t0 + p * PLANEV + r * ROWV;
             const uint4 c = tile[t], d = tile[t + 1];
-            const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
-            const uint32_t v[10] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, e[oa], e[ob]};
+            const uint2 e = reinterpret_cast<const uint2*>(tile + t + 2)[0];
+            const uint32_t v[10] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, e.x, e.y};
 #pragma unroll
             for (int i = 0; i < 10; ++i) { mn = mn < v[i] ? mn : v[i]; mx = mx > v[i] ? mx : v[i]; }
         }
@@ -391,21 +389,22 @@ template <> TA_HD void block_window_minmax<uint32_t>(const uint4* tile, int t0, 
     lo = mn; hi = mx;
 }
 
-// NOT-equal bits of one window row (vector index t of its segment) against N labels at once: out[i] bit x (0 .. SEG + 1,
-// the positions of block_row_mask) is set where the voxel differs from label i.  The row is loaded once for all labels.
+// NOT-equal bits of one window row (starting at vector t) against N labels at once: out[i] bit x (0 .. 9, column x - 1
+// relative to the block) is set where the voxel differs from label i.  The row is loaded once for all labels.
+// uint16: five words of two lanes each; xor, VIMNMX against 1 -> one bit per lane at bits 0 and 16; the words are summed
+// at 2-bit steps (even columns at bits 0, 2, .. 8, odd columns at 16, 18, .. 24) and folded.
+TA_HD uint32_t block_fold10(uint32_t tt) { return (tt & 0x155u) | ((tt >> 15) & 0x2AAu); }
 template <typename T, int N> struct BlockRowNeq;
 template <int N> struct BlockRowNeq<uint16_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t];
-        const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
-        const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16), one = 0x00010001u;
+        const uint32_t w = reinterpret_cast<const uint32_t*>(tile + t + 1)[0], one = 0x00010001u;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t pat = L[i] * 0x00010001u;
-            const uint32_t tt = ta_vminu2(c.x ^ pat, one) | (ta_vminu2(c.y ^ pat, one) << 2) | (ta_vminu2(c.z ^ pat, one) << 4) |
-                                (ta_vminu2(c.w ^ pat, one) << 6);
-            const uint32_t te = ta_vminu2(ew ^ pat, one);              // bit 0: lane left of the segment, bit 16: right of it
-            out[i] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
+            const uint32_t tt = ta_vminu2(c.x ^ pat, one) + (ta_vminu2(c.y ^ pat, one) << 2) + (ta_vminu2(c.z ^ pat, one) << 4) +
+                                (ta_vminu2(c.w ^ pat, one) << 6) + (ta_vminu2(w ^ pat, one) << 8);
+            out[i] = block_fold10(tt);
         }
     }
 };
@@ -416,34 +415,24 @@ template <int N> struct BlockRowNeq<uint16_t, N> {
 struct BlockRowNeqMinMax16 {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t];
-        const unsigned short* e = reinterpret_cast<const unsigned short*>(tile + t);
-        const uint32_t ew = (uint32_t)e[-1] | ((uint32_t)e[8] << 16), one = 0x00010001u;
+        const uint32_t w = reinterpret_cast<const uint32_t*>(tile + t + 1)[0], one = 0x00010001u;
         const uint32_t pa = L[0] * 0x00010001u, pb = L[1] * 0x00010001u;
-        {
-            const uint32_t tt = ta_vminu2(c.x - pa, one) | (ta_vminu2(c.y - pa, one) << 2) | (ta_vminu2(c.z - pa, one) << 4) |
-                                (ta_vminu2(c.w - pa, one) << 6);
-            const uint32_t te = ta_vminu2(ew - pa, one);
-            out[0] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
-        }
-        {
-            const uint32_t tt = ta_vminu2(pb - c.x, one) | (ta_vminu2(pb - c.y, one) << 2) | (ta_vminu2(pb - c.z, one) << 4) |
-                                (ta_vminu2(pb - c.w, one) << 6);
-            const uint32_t te = ta_vminu2(pb - ew, one);
-            out[1] = (((tt | (tt >> 15)) & 0xFFu) << 1) | (te & 1u) | ((te >> 7) & 0x200u);
-        }
+        out[0] = block_fold10(ta_vminu2(c.x - pa, one) + (ta_vminu2(c.y - pa, one) << 2) + (ta_vminu2(c.z - pa, one) << 4) +
+                              (ta_vminu2(c.w - pa, one) << 6) + (ta_vminu2(w - pa, one) << 8));
+        out[1] = block_fold10(ta_vminu2(pb - c.x, one) + (ta_vminu2(pb - c.y, one) << 2) + (ta_vminu2(pb - c.z, one) << 4) +
+                              (ta_vminu2(pb - c.w, one) << 6) + (ta_vminu2(pb - w, one) << 8));
     }
 };
 template <int N> struct BlockRowNeq<uint32_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t], d = tile[t + 1];
-        const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + t);
-        const uint32_t a = e[-1], b = e[8];
+        const uint2 e = reinterpret_cast<const uint2*>(tile + t + 2)[0];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t l = L[i];
-            out[i] = (a != l ? 1u : 0u) | (c.x != l ? 2u : 0u) | (c.y != l ? 4u : 0u) | (c.z != l ? 8u : 0u) |
-                     (c.w != l ? 16u : 0u) | (d.x != l ? 32u : 0u) | (d.y != l ? 64u : 0u) | (d.z != l ? 128u : 0u) |
-                     (d.w != l ? 256u : 0u) | (b != l ? 512u : 0u);
+            out[i] = (c.x != l ? 1u : 0u) | (c.y != l ? 2u : 0u) | (c.z != l ? 4u : 0u) | (c.w != l ? 8u : 0u) |
+                     (d.x != l ? 16u : 0u) | (d.y != l ? 32u : 0u) | (d.z != l ? 64u : 0u) | (d.w != l ? 128u : 0u) |
+                     (e.x != l ? 256u : 0u) | (e.y != l ? 512u : 0u);
         }
     }
 };
@@ -513,7 +502,7 @@ template <typename T, int CAP> struct BlockLevel {
         const int p = R0 ? 0 : R1 ? 1 : R2 ? 2 : 3;
         const u64 rp = R0 ? R0 : R1 ? R1 : R2 ? R2 : R3;
         const int bit = ta_ffs64(rp) - 1, r = bit / ROWBITS, x = bit % ROWBITS;
-        return reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + (x - 1)];
+        return reinterpret_cast<const T*>(tile)[(size_t)(t0 + p * PLANEV + r * ROWV) * SEG + x];      // shifted tile
     }
     template <int I> TA_HD void set_slot(uint32_t L, const u64 neq[BLK_S + 2]) {
         constexpr u64 ALL = LvBlk<T>::PLANE_ALL;

@@ -104,6 +104,32 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // ---- TMA staging: one 3-D box copy (brick + halo) per tile, completion on an mbarrier ------------------------------
+#ifdef TA_EMU_TMA
+// CPU emulation only (tests/host/emu; never defined in a CUDA build): the box copy and its barrier as plain code, so that
+// the kernels' TMA paths -- box coordinates, zero fill outside the tensor, the re-clamping of edge tiles -- run under the
+// emulation too.  The harness puts an EmuTmap into the bytes of the CUtensorMap.
+struct EmuTmap { const void* base; long long n0, n1, n2; int elem, box0, box1, box2; };
+inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0ull; }                       // completed phases
+inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+void ta_emu_yield();            // the harness: let the other fibers run (a cooperative fiber must not spin)
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    const bool done = ((uint32_t)(*bar) & 1u) != parity;
+    if (!done) ta_emu_yield();
+    return done;
+}
+inline void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    EmuTmap m;
+    memcpy(&m, map, sizeof m);
+    unsigned char* d = (unsigned char*)smem_dst;
+    for (int k = 0; k < m.box2; ++k) for (int j = 0; j < m.box1; ++j) for (int i = 0; i < m.box0; ++i) {
+        const long long g0 = c0 + i, g1 = c1 + j, g2 = c2 + k;
+        unsigned char* dst = d + (((size_t)k * m.box1 + j) * m.box0 + i) * m.elem;
+        if (g0 < 0 || g0 >= m.n0 || g1 < 0 || g1 >= m.n1 || g2 < 0 || g2 >= m.n2) memset(dst, 0, m.elem);
+        else memcpy(dst, (const unsigned char*)m.base + ((g2 * m.n1 + g1) * m.n0 + g0) * m.elem, m.elem);
+    }
+    *bar += 1ull;
+}
+#else
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     TA_PTX("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -124,6 +150,8 @@ __device__ __forceinline__ void tma_load_box_3d(void* smem_dst, const CUtensorMa
                  :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
                     "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+
+#endif
 
 template <typename T> struct BrickShared {
     uint4* tile;                       // [TILE_SEGS]

@@ -153,8 +153,13 @@ __device__ __forceinline__ void block_merge_pair(const BrickShared<T>& sh, const
 }
 
 // ---- pieces shared by the block kernels (this file and ta_scan_level.cuh) ----------------------------------------------
-// phase A: the tile (brick + one-voxel halo), as in the product kernel: one TMA box copy, or the scalar path
-template <typename T>
+// phase A: the tile (brick + one-voxel halo), as in the product kernel: one TMA box copy, or the scalar path.
+// SHIFT = 0: the product kernel's layout (brick column f at tile element SEG + f).  SHIFT = 1 (level kernel): the whole
+// tile one voxel to the right (column f at element SEG + 1 + f), so that the 10-voxel window row of an 8-wide block
+// STARTS on a 16-byte vector: columns -1 .. 6 are one LDS.128, columns 7 and 8 the first word of the next vector -- no
+// separate edge-lane loads (they fall on 8 banks) and no edge-lane special case in the compares.  A TMA box may start at
+// any element; the scalar path just reads shifted columns.
+template <typename T, int SHIFT = 0>
 __device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const ScanParams& P, const CUtensorMap& tmap, uint64_t* tma_bar,
                                                  uint32_t& tma_parity, bool use_tma, int F0, int M0, int S0, unsigned iter,
                                                  unsigned int brick, int tid) {
@@ -165,7 +170,7 @@ __device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const
         if (tid == 0) {
             TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(tma_bar, (uint32_t)(TILE_SEGS * 16));
-            tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG, M0 - 1, S0 - 1);
+            tma_load_box_3d(sh.tile, &tmap, tma_bar, F0 - SEG - SHIFT, M0 - 1, S0 - 1);
         }
         __syncwarp();
         unsigned spins = 0;
@@ -183,8 +188,8 @@ __device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const
         const bool edge = (F0 == 0) | (F0 + BF + 1 > nf) | (M0 == 0) | (M0 + BM + 1 > nm) | (S0 < 1) | (S0 + BS + 1 > ns);
         if (edge) {
             T* tw = reinterpret_cast<T*>(sh.tile);
-            const int xl = (F0 == 0) ? SEG : 0;
-            const int xr = min(ROWE, nf - F0 + SEG);
+            const int xl = (F0 == 0) ? SEG + SHIFT : 0;            // elements before volume column 0
+            const int xr = min(ROWE, nf - F0 + SEG + SHIFT);       // first element beyond the last volume column
             for (int r = tid; r < TILE_ROWS; r += NTHREADS) {
                 T* row = tw + r * ROWE;
                 if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
@@ -210,7 +215,7 @@ __device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const
             const int m = r % (BM + 2) - 1, s = r / (BM + 2) - 1;
             const int gs = min(max(S0 + s, 0), ns - 1);
             const int gm = min(max(M0 + m, 0), nm - 1);
-            const int gf = F0 + fsv * SEG;
+            const int gf = F0 + fsv * SEG - SHIFT;
             const T* row = vol + ((size_t)gs * nm + gm) * (size_t)nf;
             T tmp[SEG];
 #pragma unroll
@@ -230,16 +235,17 @@ __device__ __forceinline__ void block_stage_tile(const BrickShared<T>& sh, const
 }
 
 // one-label tile: closed-form moments, no pairs.  true: the brick is done (all threads agree).
-template <typename T>
+template <typename T, int SHIFT = 0>
 __device__ __forceinline__ bool block_uniform_tile(const BrickShared<T>& sh, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
                                                    int F0, int M0, int S0, u64 gF0, u64 gM0, u64 gS0, int tid) {
     constexpr int SEG = Vox<T>::SEG, BF = NFS * SEG;
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
     const int nf = (int)P.nf, nm = (int)P.nm;
     const bool do_mom = P.flags & 1u;
-    const uint32_t ref_label = tileT[SEG];
-    // OR of the xors against the reference label: the 16 brick segments of every tile row as vectors (one LOP3 per word),
-    // then the two halo lanes of every row (one row per thread)
+    const uint32_t ref_label = tileT[SEG + SHIFT];
+    // OR of the xors against the reference label over columns -1 .. BF of every tile row: vectors 1 .. 16 (one LOP3 per
+    // word), then the two elements they leave out (SHIFT = 0: one on either side; SHIFT = 1: both on the right), one row
+    // per thread
     uint32_t diff = 0u;
     {
         constexpr int ROWE = ROWV * SEG;
@@ -248,7 +254,8 @@ __device__ __forceinline__ bool block_uniform_tile(const BrickShared<T>& sh, con
             const uint4 v = sh.tile[r * ROWV + 1 + (tid % NFS)];
             diff |= (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
         }
-        if (tid < TILE_ROWS) diff |= ((uint32_t)tileT[tid * ROWE + SEG - 1] ^ ref_label) | ((uint32_t)tileT[tid * ROWE + SEG + BF] ^ ref_label);
+        constexpr int E0 = SHIFT ? SEG + BF : SEG - 1, E1 = SHIFT ? SEG + BF + 1 : SEG + BF;
+        if (tid < TILE_ROWS) diff |= ((uint32_t)tileT[tid * ROWE + E0] ^ ref_label) | ((uint32_t)tileT[tid * ROWE + E1] ^ ref_label);
     }
     const bool all_ref = (diff == 0u);
     if (__syncthreads_and(all_ref)) {

@@ -306,7 +306,7 @@ __device__ __forceinline__ void level_pass(const BrickShared<T>& sh, const ScanP
                     const int df = w % BW, dm = (w / BW) % BLK_M, ds = w / (BW * BLK_M);
                     const uint32_t f = (uint32_t)(cfs * SEG + df), m = (uint32_t)(cm0 + dm), sp = (uint32_t)(cs0 + ds);
                     if (F0 + (int)f >= (int)P.nf || M0 + (int)m >= (int)P.nm || S0 + (int)sp >= (int)P.own_hi) continue;
-                    const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + f;
+                    const T* p = tileT + (size_t)((sp + 1) * (BM + 2) + (m + 1)) * ROWE + SEG + 1 + f;     // shifted tile
                     level_fallback_voxel<T>(sh, lt, pt, p, f, m, sp, known + cblk * LV_MAXL, gF0, gM0, gS0, P.flags & 1u, P.flags & 2u,
                                             P.flags & 4u);
                 }
@@ -374,7 +374,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
                 // its box copy finds the data on chip; DRAM is idle 95 % of the time
                 const int nbf_ = nb % P.nbf, nbm_ = (nb / P.nbf) % P.nbm, nbs_ = nb / (P.nbf * P.nbm);
                 TA_PTX("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                       :: "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nbf_ * BF - SEG), "r"(nbm_ * BM - 1),
+                       :: "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nbf_ * BF - SEG - 1), "r"(nbm_ * BM - 1),
                           "r"((int)P.own_lo + nbs_ * BS - 1) : "memory");
             }
             sh.ctr[0] = sh.ctr[1] = 0u;                                // list 2, list 3
@@ -384,8 +384,8 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
 
         // ---- phase A: the tile (ends with a block barrier), then the one-label tile shortcut ----------------------------
-        block_stage_tile<T>(sh, P, tmap, tma_bar, tma_parity, use_tma, F0, M0, S0, iter, brick, tid);
-        if (block_uniform_tile<T>(sh, P, lt, pt, F0, M0, S0, gF0, gM0, gS0, tid)) continue;
+        block_stage_tile<T, 1>(sh, P, tmap, tma_bar, tma_parity, use_tma, F0, M0, S0, iter, brick, tid);
+        if (block_uniform_tile<T, 1>(sh, P, lt, pt, F0, M0, S0, gF0, gM0, gS0, tid)) continue;
 
         // ---- P1: one block per thread, window min / max ------------------------------------------------------------------
         {
@@ -395,7 +395,7 @@ scan_level_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_consta
                       nvs = min(BLK_S, (int)P.own_hi - (S0 + s0));
             const bool valid = (tid < LvBlk<T>::NBLK && nvf > 0 && nvm > 0 && nvs > 0);
             uint32_t lo = 0u, hi = 0u;
-            if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi, (tid & 16) != 0);
+            if (valid) block_window_minmax<T>(sh.tile, s0 * PLANEV + m0 * ROWV + (fs + 1), lo, hi);
             const bool one = valid && lo == hi, many = valid && lo != hi;
             if (tid == 0) TA_STAT(0, 1);
             if (valid) TA_STAT(1, 1);
