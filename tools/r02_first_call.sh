@@ -5,11 +5,13 @@
 # Build the experiment libraries BEFORE the call (they travel with the snapshot; build/ is git-ignored only):
 #   TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$PWD/build/libtissue_b200_block.so bash tissue_analysis_b200/csrc/build.sh
 #   TA_NVCC_EXTRA="-DTA_WITH_BLOCK_KERNEL -DTA_LEVEL_MINB=2" TA_OUT=$PWD/build/libtissue_b200_block_2cta.so bash tissue_analysis_b200/csrc/build.sh
+#   TA_NVCC_EXTRA="-DTA_WITH_BLOCK_KERNEL -DTA_LEVEL_MAXL=5" TA_OUT=$PWD/build/libtissue_b200_block_maxl5.so bash tissue_analysis_b200/csrc/build.sh
 out=gpurun_out/r02_first_call.txt
 mkdir -p gpurun_out
 : > $out
 LIB=$PWD/build/libtissue_b200_block.so
 LIB2=$PWD/build/libtissue_b200_block_2cta.so
+LIB3=$PWD/build/libtissue_b200_block_maxl5.so
 [ -f $LIB ] || TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL TA_OUT=$LIB bash tissue_analysis_b200/csrc/build.sh
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> $out
 # 1. parity of every experimental kernel on the existing suite (the C ABI is the same; TA_PAIR_PATH picks the kernel)
@@ -25,6 +27,9 @@ for cfg in C3 C2 C4 C1; do
   done
   if [ -f $LIB2 ]; then
     echo "== $cfg level, 2 CTAs/SM build: $(TA_LIB_PATH=$LIB2 TA_PAIR_PATH=level timeout 600 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep 'pass 2\|rror' | head -2)" >> $out
+  fi
+  if [ -f $LIB3 ]; then
+    echo "== $cfg level, 5 labels per block by masks: $(TA_LIB_PATH=$LIB3 TA_PAIR_PATH=level timeout 600 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep 'pass 2\|rror' | head -2)" >> $out
   fi
 done
 # 3. full-size parity of the level kernel (conservation laws, slab split, C oracle slab)
