@@ -6,8 +6,9 @@
 // results go to the per-brick shared tables through slot-wise warp merges (MERGE = true) or, in the simpler form kept
 // to bisect against, with plain atomics per block (MERGE = false).  Both forms fill exact tables on the CPU emulation
 // of the CUDA execution model (tests/host/kernel_emu_check.cpp: fibers for threads, rendezvous for the collectives;
-// scalar staging path).  It
-// compiles for sm_100a but was written after the round's GPU budget was spent: it has NOT run on a GPU, and it is NOT
+// scalar and emulated-TMA staging).  Superseded as the candidate for the next product kernel by the level formulation
+// (ta_scan_level.cuh, which shares the staging / uniform-tile / flush helpers and the pair merge below); kept as the
+// simpler form to measure against.  It compiles for sm_100a but was written after the round's GPU budget was spent: it has NOT run on a GPU, and it is NOT
 // part of the product build (ta_api.cu includes it only under -DTA_WITH_BLOCK_KERNEL; a product library answers flag
 // 0x4000 with TA_ERR_BAD_ARG).  Known before the first run: the per-voxel fallback and the plain-atomics updates are
 // out of line (inlined, the kernel took minutes to compile); at 80 registers ptxas spills ~130 bytes in the simple form
