@@ -35,6 +35,9 @@ done
 # 3. full-size parity of the level kernel (conservation laws, slab split, C oracle slab)
 TA_LIB_PATH=$LIB TA_PAIR_PATH=level timeout 1200 python -m pytest tests/test_gpu_fullsize.py -x -q > gpurun_out/r02_fullsize_level.log 2>&1
 echo "fullsize level: exit $? | $(tail -1 gpurun_out/r02_fullsize_level.log)" >> $out
+# 3b. the bench line with the level kernel in place of the product kernel (same step, same roofline arithmetic)
+TA_LIB_PATH=$LIB TA_PAIR_PATH=level timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_level_n1.json 2> gpurun_out/r02_bench_level_n1.err
+echo "bench level: exit $? | $(cut -c1-260 gpurun_out/r02_bench_level_n1.json)" >> $out
 # 4. ncu: launch list, then the full set for the level kernel on C3 (only after the plain runs above)
 TA_LIB_PATH=$LIB TA_PAIR_PATH=level timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_level_kernel -c 1 \
   -o gpurun_out/r02_level_c3 python tools/profile_scan.py --config C3 --passes 1 > gpurun_out/r02_ncu_level.log 2>&1
