@@ -423,6 +423,10 @@ struct BlockRowNeqMinMax16 {
                               (ta_vminu2(pb - c.w, one) << 6) + (ta_vminu2(pb - w, one) << 8));
     }
 };
+// uint32: ten words of one lane each; min(x ^ L, 1) is the lane's bit, summed at 1-bit steps (one compare-free ALU op and
+// one shift-add per lane instead of compare + select + or).  Level 2 (MINMAX: L[0] / L[1] = smallest / largest label of
+// the window) subtracts instead of xoring, which may run on the FMA pipe.
+TA_HD uint32_t ta_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
 template <int N> struct BlockRowNeq<uint32_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t], d = tile[t + 1];
@@ -430,10 +434,23 @@ template <int N> struct BlockRowNeq<uint32_t, N> {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t l = L[i];
-            out[i] = (c.x != l ? 1u : 0u) | (c.y != l ? 2u : 0u) | (c.z != l ? 4u : 0u) | (c.w != l ? 8u : 0u) |
-                     (d.x != l ? 16u : 0u) | (d.y != l ? 32u : 0u) | (d.z != l ? 64u : 0u) | (d.w != l ? 128u : 0u) |
-                     (e.x != l ? 256u : 0u) | (e.y != l ? 512u : 0u);
+            out[i] = ta_minu(c.x ^ l, 1u) + (ta_minu(c.y ^ l, 1u) << 1) + (ta_minu(c.z ^ l, 1u) << 2) + (ta_minu(c.w ^ l, 1u) << 3) +
+                     (ta_minu(d.x ^ l, 1u) << 4) + (ta_minu(d.y ^ l, 1u) << 5) + (ta_minu(d.z ^ l, 1u) << 6) +
+                     (ta_minu(d.w ^ l, 1u) << 7) + (ta_minu(e.x ^ l, 1u) << 8) + (ta_minu(e.y ^ l, 1u) << 9);
         }
+    }
+};
+struct BlockRowNeqMinMax32 {
+    static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
+        const uint4 c = tile[t], d = tile[t + 1];
+        const uint2 e = reinterpret_cast<const uint2*>(tile + t + 2)[0];
+        const uint32_t a = L[0], b = L[1];
+        out[0] = ta_minu(c.x - a, 1u) + (ta_minu(c.y - a, 1u) << 1) + (ta_minu(c.z - a, 1u) << 2) + (ta_minu(c.w - a, 1u) << 3) +
+                 (ta_minu(d.x - a, 1u) << 4) + (ta_minu(d.y - a, 1u) << 5) + (ta_minu(d.z - a, 1u) << 6) +
+                 (ta_minu(d.w - a, 1u) << 7) + (ta_minu(e.x - a, 1u) << 8) + (ta_minu(e.y - a, 1u) << 9);
+        out[1] = ta_minu(b - c.x, 1u) + (ta_minu(b - c.y, 1u) << 1) + (ta_minu(b - c.z, 1u) << 2) + (ta_minu(b - c.w, 1u) << 3) +
+                 (ta_minu(b - d.x, 1u) << 4) + (ta_minu(b - d.y, 1u) << 5) + (ta_minu(b - d.z, 1u) << 6) +
+                 (ta_minu(b - d.w, 1u) << 7) + (ta_minu(b - e.x, 1u) << 8) + (ta_minu(b - e.y, 1u) << 9);
     }
 };
 
@@ -485,6 +502,8 @@ template <typename T, int CAP> struct BlockLevel {
                     uint32_t row[N];
                     if constexpr (MINMAX && N == 2 && sizeof(T) == 2)
                         BlockRowNeqMinMax16::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
+                    else if constexpr (MINMAX && N == 2 && sizeof(T) == 4)
+                        BlockRowNeqMinMax32::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
                     else
                         BlockRowNeq<T, N>::run(tile, t0 + p * PLANEV + (h * HALF + r) * ROWV, L, row);
 #pragma unroll
