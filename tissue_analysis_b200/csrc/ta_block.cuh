@@ -426,7 +426,15 @@ struct BlockRowNeqMinMax16 {
 // uint32: ten words of one lane each; min(x ^ L, 1) is the lane's bit, summed at 1-bit steps (one compare-free ALU op and
 // one shift-add per lane instead of compare + select + or).  Level 2 (MINMAX: L[0] / L[1] = smallest / largest label of
 // the window) subtracts instead of xoring, which may run on the FMA pipe.
-TA_HD uint32_t ta_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
+TA_HD uint32_t ta_minu(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;                        // spelled in PTX: the compiler turns min(x, 1) back into compare + select
+    asm("min.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return a < b ? a : b;
+#endif
+}
 template <int N> struct BlockRowNeq<uint32_t, N> {
     static TA_HD void run(const uint4* tile, int t, const uint32_t* L, uint32_t* out) {
         const uint4 c = tile[t], d = tile[t + 1];
