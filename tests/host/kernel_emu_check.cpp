@@ -13,6 +13,7 @@ static unsigned long long g_user_stat[16];
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_scan_meta.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
 void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
@@ -54,9 +55,9 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
-enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, NWHICH };
+enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, META, NWHICH };
 static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
-                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>"};
+                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>", "scan_meta_kernel<T>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -113,7 +114,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     memset(&tmap, 0, sizeof tmap);
     {
         // what ta_api.cu encodes for the kernels: the bound buffer, one box = tile (brick + halo)
-        ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), ROWV * seg, BM + 2, BS + 2};
+        ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), (which == META ? MK_ROWV : ROWV) * seg, BM + 2, BS + 2};
         static_assert(sizeof(ta::EmuTmap) <= sizeof(CUtensorMap), "the emulated map lives in the bytes of the real one");
         memcpy(&tmap, &em, sizeof em);
     }
@@ -125,6 +126,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
             else if (which == BLOCK_MERGE) scan_block_kernel<T, true>(P, lt, pt, tmap);
             else if (which == BLOCK_SIMPLE) scan_block_kernel<T, false>(P, lt, pt, tmap);
             else if (which == LEVEL_MERGE) scan_level_kernel<T, true>(P, lt, pt, tmap);
+            else if (which == META) scan_meta_kernel<T>(P, lt, pt, tmap);
             else scan_level_kernel<T, false>(P, lt, pt, tmap);
         });
     }
@@ -186,9 +188,10 @@ int main(int argc, char** argv) {
     if (argc > 1 && !strcmp(argv[1], "--stats")) { print_stats(); return 0; }
     std::mt19937 rng(argc > 1 ? (unsigned)atoi(argv[1]) : 1u);
     const int ncases = argc > 2 ? atoi(argv[2]) : 36;
+    const int only = argc > 3 ? atoi(argv[3]) : -1;
     int bad = 0, ran = 0;
     for (int c = 0; c < ncases; ++c) {
-        const Which which = (Which)(c % NWHICH);
+        const Which which = only >= 0 ? (Which)only : (Which)(c % NWHICH);
         const bool wide = (c / NWHICH) % 3 == 2;                                   // every third round: uint32 labels
         const int maxf = wide ? 150 : 300;
         const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;

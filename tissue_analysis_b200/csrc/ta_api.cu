@@ -17,6 +17,7 @@
 #include "ta_scan_block.cuh"
 #include "ta_scan_level.cuh"
 #endif
+#include "ta_scan_meta.cuh"
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -316,7 +317,7 @@ typedef CUresult (*ta_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map) {
+static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map, int rowv = ta::ROWV) {
     static ta_encode_tiled_fn encode = nullptr;
     static bool looked = false;
     if (!looked) {
@@ -333,7 +334,7 @@ static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map) {
     const int seg = 16 / ctx->elem;
     const cuuint64_t dims[3] = {(cuuint64_t)ctx->nf, (cuuint64_t)ctx->nm, (cuuint64_t)ctx->ns};
     const cuuint64_t strides[2] = {(cuuint64_t)ctx->nf * ctx->elem, (cuuint64_t)ctx->nf * ctx->nm * ctx->elem};
-    const cuuint32_t box[3] = {(cuuint32_t)(ta::ROWV * seg), (cuuint32_t)(ta::BM + 2), (cuuint32_t)(ta::BS + 2)};
+    const cuuint32_t box[3] = {(cuuint32_t)(rowv * seg), (cuuint32_t)(ta::BM + 2), (cuuint32_t)(ta::BS + 2)};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, ctx->elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
                         const_cast<void*>(ctx->vol), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -352,6 +353,18 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
+    if (P.flags & 0x40000u) {
+        // the record kernel (ta_scan_meta.cuh)
+        typedef void (*meta_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
+        meta_fn fn = ctx->elem == 2 ? (meta_fn)ta::scan_meta_kernel<uint16_t> : (meta_fn)ta::scan_meta_kernel<uint32_t>;
+        const size_t msmem = ctx->elem == 2 ? ta::scan_meta_smem_bytes<uint16_t>() : ta::scan_meta_smem_bytes<uint32_t>();
+        TA_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        const int mgrid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * TA_META_MINB);
+        fn<<<mgrid, ta::NTHREADS, msmem, st>>>(P, ctx->lt, ctx->pt, tmap);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
 #ifdef TA_WITH_BLOCK_KERNEL
     if (P.flags & 0x4000u) {
         // experimental block-bitmask kernel (ta_scan_block.cuh): only on request, configured on first use so that the
@@ -489,7 +502,9 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "level")) P.flags |= 0x4000u | 0x10000u;
         else if (!strcmp(pp, "level_simple")) P.flags |= 0x4000u | 0x8000u | 0x10000u;
         else if (!strcmp(pp, "level_pf")) P.flags |= 0x4000u | 0x10000u | 0x20000u;
+        else if (!strcmp(pp, "meta")) P.flags |= 0x40000u;
     }
+    if ((P.flags & 0x40000u) && P.use_tma) P.use_tma = make_tile_map(ctx, &tmap, ta::MK_ROWV) ? 1 : 0;
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {
         for (int k = 0; k < ranges->n; ++k) {
