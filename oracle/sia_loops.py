@@ -446,13 +446,17 @@ class LoopOracle(object):
     def wall_voxels_per_cells_pairs(self, labels=None, neighborhood=None, only_epidermis=False,
                                     ignore_background=False, min_contact_area=None, real_area=True,
                                     verbose=True):
-        if only_epidermis:
-            raise NotImplementedError("only_epidermis path reads a different image (SIA:1062-1063)")
+        # SIA:1062-1065: the first-voxel-layer image only ever supplies the label list (SIA:1073-1074); the voxels still
+        # come from self.image.  That list is an ndarray (np.unique), so ``labels + [background]`` below is numpy's
+        # element-wise sum, as in the reference.
+        image = self.voxel_first_layer(True) if only_epidermis else self.image
         compute_neighborhood = neighborhood is None
         if isinstance(labels, list) and isinstance(neighborhood, dict):
             labels = [l for l in labels if l in neighborhood]
-        if labels is None:
+        if labels is None and not only_epidermis:
             labels = self.labels()
+        elif labels is None and only_epidermis:
+            labels = np.unique(image)
         elif isinstance(labels, list):
             labels.sort()
             if not isinstance(neighborhood, dict):

@@ -175,6 +175,11 @@ static void print_stats() {
                s.ballot / nv, s.shfl / nv, s.syncthreads / nv, bad ? "  (MISMATCH)" : "");
         if (w == LEVEL_MERGE) memcpy(level_stat, g_user_stat, sizeof level_stat);
     }
+    {
+        const unsigned long long* m = g_user_stat;      // the last kernel run: scan_meta_kernel
+        printf("record kernel: %llu bricks not one label, %llu blocks: %llu one label, %llu listed in %llu warp rounds; label steps: %llu warp-level "
+               "for %llu lanes; fallback blocks %llu (BAD %llu); 3+-label octs %llu\n", m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9]);
+    }
     const unsigned long long* u = level_stat;
     printf("level kernel, dynamic counts: %llu bricks not one label, %llu blocks: %llu one label (%.1f %%), list 2: %llu blocks in %llu warp "
            "rounds (%.1f lanes), list 3: %llu blocks in %llu warp rounds (%.1f lanes), extension steps: %llu warp-level for %llu "

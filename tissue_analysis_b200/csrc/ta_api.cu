@@ -504,7 +504,6 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "level_pf")) P.flags |= 0x4000u | 0x10000u | 0x20000u;
         else if (!strcmp(pp, "meta")) P.flags |= 0x40000u;
     }
-    if ((P.flags & 0x40000u) && P.use_tma) P.use_tma = make_tile_map(ctx, &tmap, ta::MK_ROWV) ? 1 : 0;
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {
         for (int k = 0; k < ranges->n; ++k) {

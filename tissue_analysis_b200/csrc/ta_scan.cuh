@@ -120,6 +120,8 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 inline void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     EmuTmap m;
     memcpy(&m, map, sizeof m);
+    // the hardware faults ("illegal instruction") on a box that does not start on a 16-byte boundary of the row
+    if (((long long)c0 * m.elem) % 16 != 0) { fprintf(stderr, "emu: TMA box origin %d is not 16-byte aligned\n", c0); abort(); }
     unsigned char* d = (unsigned char*)smem_dst;
     for (int k = 0; k < m.box2; ++k) for (int j = 0; j < m.box1; ++j) for (int i = 0; i < m.box0; ++i) {
         const long long g0 = c0 + i, g1 = c1 + j, g2 = c2 + k;

@@ -16,9 +16,10 @@
 // min / max over 24 records.
 //
 // Phases per brick (128 x 16 x 8 voxels for uint16, 64 x 16 x 8 for uint32; 256 threads):
-//   A   the tile (brick + one-voxel halo) by ONE TMA box copy of 17 x 18 x 10 vectors, shifted so that an oct window starts
-//       on a 16-byte vector; issued for brick k + 1 as soon as phase M of brick k has ended (the raw tile is not read after
-//       phase M: even the per-voxel fallback reads global memory), so the copy overlaps P1 / P2
+//   A   the tile (brick + one-voxel halo) by ONE TMA box copy of 18 x 18 x 10 vectors (the box must start on a 16-byte
+//       boundary of the row: a box shifted by one voxel faults with "illegal instruction" on the hardware); issued for
+//       brick k + 1 as soon as phase M of brick k has ended (the raw tile is not read after phase M: even the per-voxel
+//       fallback reads global memory), so the copy overlaps P1 / P2
 //   U   one-label tile (background, cell interior): closed-form moments, done
 //   M   one record per oct of the tile (2880 / 1440), M2: the side-table entries of the 3- and 4-label octs
 //   P1  one 8 x 4 x 2 block per thread: min / max over its 24 records.  One label: closed-form moments.  Otherwise -> list
@@ -31,9 +32,13 @@
 #pragma once
 #include "ta_block.cuh"
 
+#ifndef TA_STAT
+#define TA_STAT(which, n) ((void)0)
+#endif
+
 namespace ta {
 
-constexpr int MK_ROWV = 17;                          // vectors per tile row: columns -1 .. 8 * 17 - 2 of the brick
+constexpr int MK_ROWV = ROWV;                        // vectors per tile row: one halo vector, the brick row, one halo vector
 constexpr int MK_ROWS = (BS + 2) * (BM + 2);         // 180 tile rows
 constexpr int MK_VECS = MK_ROWS * MK_ROWV;
 constexpr int MK_OVF = 256;                          // side-table entries per brick
@@ -106,17 +111,22 @@ template <> struct MkRec<uint32_t> {
 
 // ---- phase M: one oct window -> lo, hi, lanes != lo, lanes != hi -----------------------------------------------------------
 struct MkOct { uint32_t lo, hi, notlo, nothi; };
-// uint16: five words of two lanes (low half = the earlier column)
-TA_HD MkOct mk_oct16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
-    const uint32_t mn = ta_vminu2(ta_vminu2(ta_vminu2(w0, w1), ta_vminu2(w2, w3)), w4);
-    const uint32_t mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(w0, w1), ta_vmaxu2(w2, w3)), w4);
+// uint16: the oct's four words of two lanes (low half = the earlier column) and the halo word: left neighbour in the low
+// half, right neighbour in the high half.  Mask bit 0 = left neighbour, bits 1 .. 8 = the oct, bit 9 = right neighbour.
+TA_HD uint32_t mk_fold16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3, uint32_t zh) {
+    const uint32_t tt = z0 + (z1 << 2) + (z2 << 4) + (z3 << 6);
+    return ((((tt & 0x55u) | ((tt >> 15) & 0xAAu)) << 1) | (zh & 1u)) | ((zh >> 7) & 0x200u);
+}
+TA_HD MkOct mk_oct16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t wh) {
+    const uint32_t mn = ta_vminu2(ta_vminu2(ta_vminu2(w0, w1), ta_vminu2(w2, w3)), wh);
+    const uint32_t mx = ta_vmaxu2(ta_vmaxu2(ta_vmaxu2(w0, w1), ta_vmaxu2(w2, w3)), wh);
     const uint32_t LL = ta_vminu2(mn, mk_swap16(mn)), HH = ta_vmaxu2(mx, mk_swap16(mx)), one = 0x00010001u;
     MkOct r;
     r.lo = LL & 0xFFFFu; r.hi = HH & 0xFFFFu;
-    r.notlo = block_fold10(ta_vminu2(w0 ^ LL, one) + (ta_vminu2(w1 ^ LL, one) << 2) + (ta_vminu2(w2 ^ LL, one) << 4) +
-                           (ta_vminu2(w3 ^ LL, one) << 6) + (ta_vminu2(w4 ^ LL, one) << 8));
-    r.nothi = block_fold10(ta_vminu2(w0 ^ HH, one) + (ta_vminu2(w1 ^ HH, one) << 2) + (ta_vminu2(w2 ^ HH, one) << 4) +
-                           (ta_vminu2(w3 ^ HH, one) << 6) + (ta_vminu2(w4 ^ HH, one) << 8));
+    r.notlo = mk_fold16(ta_vminu2(w0 ^ LL, one), ta_vminu2(w1 ^ LL, one), ta_vminu2(w2 ^ LL, one), ta_vminu2(w3 ^ LL, one),
+                        ta_vminu2(wh ^ LL, one));
+    r.nothi = mk_fold16(ta_vminu2(w0 ^ HH, one), ta_vminu2(w1 ^ HH, one), ta_vminu2(w2 ^ HH, one), ta_vminu2(w3 ^ HH, one),
+                        ta_vminu2(wh ^ HH, one));
     return r;
 }
 TA_HD MkOct mk_oct32(const uint32_t w[10]) {
@@ -348,6 +358,8 @@ __device__ __forceinline__ void mk_steps(const MkShared<T>& sh, const ScanParams
     if constexpr (I < MK_MAXL) {
         if (!__ballot_sync(0xffffffffu, more)) return;
         const bool act = more;
+        if (lane == 0) TA_STAT(5, 1);
+        if (act) TA_STAT(6, 1);
         if (act) {
             constexpr u64 ALL = LvBlk<T>::PLANE_ALL;
             const int p = b.R0 ? 0 : b.R1 ? 1 : b.R2 ? 2 : 3;
@@ -423,7 +435,7 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             const int bf = b0 % P.nbf, bm = (b0 / P.nbf) % P.nbm, bs = b0 / (P.nbf * P.nbm);
             TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(sh.bar, (uint32_t)(MK_VECS * 16));
-            tma_load_box_3d(sh.tile, &tmap, sh.bar, bf * BF - 1, bm * BM - 1, (int)P.own_lo + bs * BS - 1);
+            tma_load_box_3d(sh.tile, &tmap, sh.bar, bf * BF - SEG, bm * BM - 1, (int)P.own_lo + bs * BS - 1);
         }
     }
     __syncthreads();
@@ -464,11 +476,11 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             // out-of-buffer elements arrive as zeros: bricks on a face of the buffer re-clamp them
             const bool edge = (F0 == 0) | (F0 + BF + 1 > nf) | (M0 == 0) | (M0 + BM + 1 > nm) | (S0 < 1) | (S0 + BS + 1 > ns);
             if (edge) {
-                const int xl = (F0 == 0) ? 1 : 0;                    // elements before volume column 0
-                const int xr = min(ROWE, nf - F0 + 1);               // first element beyond the last volume column
+                const int xl = (F0 == 0) ? SEG : 0;                  // elements before volume column 0
+                const int xr = min(ROWE, nf - F0 + SEG);             // first element beyond the last volume column
                 for (int r = tid; r < MK_ROWS; r += NTHREADS) {
                     T* row = tileT + r * ROWE;
-                    if (xl) row[0] = row[1];
+                    if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
                     if (xr < ROWE) { const T v = row[xr - 1]; for (int x = xr; x < ROWE; ++x) row[x] = v; }
                 }
                 __syncthreads();
@@ -487,7 +499,7 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             const T* vol = reinterpret_cast<const T*>(P.vol);
             for (int e = tid; e < MK_ROWS * ROWE; e += NTHREADS) {
                 const int r = e / ROWE, x = e - r * ROWE, tp = r / (BM + 2), tr = r - tp * (BM + 2);
-                const int f = max(0, min(F0 - 1 + x, nf - 1)), m = max(0, min(M0 - 1 + tr, nm - 1)), s = max(0, min(S0 - 1 + tp, ns - 1));
+                const int f = max(0, min(F0 - SEG + x, nf - 1)), m = max(0, min(M0 - 1 + tr, nm - 1)), s = max(0, min(S0 - 1 + tp, ns - 1));
                 tileT[e] = vol[((size_t)s * nm + m) * (size_t)nf + f];
             }
             __syncthreads();
@@ -495,14 +507,15 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
 
         // ---- phase U: one-label tile (columns -1 .. BF of every row) -------------------------------------------------------
         {
-            const uint32_t ref = (uint32_t)tileT[0];
+            const uint32_t ref = (uint32_t)tileT[SEG];
             const uint32_t pat = (SEG == 8) ? ref * 0x00010001u : ref;
             uint32_t diff = 0u;
             for (int i = tid; i < MK_VECS; i += NTHREADS) {
                 const uint4 v = sh.tile[i];
                 const int j = i % MK_ROWV;
-                if (j < MK_ROWV - 1) diff |= (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
-                else diff |= (v.x ^ pat) | (SEG == 4 ? (v.y ^ pat) : 0u);
+                if (j == 0) diff |= (SEG == 8) ? ((v.w ^ pat) >> 16) : (v.w ^ pat);                   // column -1
+                else if (j == MK_ROWV - 1) diff |= (SEG == 8) ? ((v.x ^ pat) & 0xFFFFu) : (v.x ^ pat);   // column BF
+                else diff |= (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
             }
             const bool uniform = __syncthreads_and(diff == 0u);
             if (sh.ctr[4]) {                                   // a tile copy timed out somewhere in this CTA
@@ -515,7 +528,7 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
                         const int nbf_ = next_brick % P.nbf, nbm_ = (next_brick / P.nbf) % P.nbm, nbs_ = next_brick / (P.nbf * P.nbm);
                         TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
                         mbar_arrive_expect_tx(sh.bar, (uint32_t)(MK_VECS * 16));
-                        tma_load_box_3d(sh.tile, &tmap, sh.bar, nbf_ * BF - 1, nbm_ * BM - 1, (int)P.own_lo + nbs_ * BS - 1);
+                        tma_load_box_3d(sh.tile, &tmap, sh.bar, nbf_ * BF - SEG, nbm_ * BM - 1, (int)P.own_lo + nbs_ * BS - 1);
                     }
                     if (do_mom) {
                         uint32_t v[16];
@@ -528,21 +541,23 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             }
         }
 
+        if (tid == 0) TA_STAT(0, 1);
         // ---- phase M: one record per oct of the tile -------------------------------------------------------------------------
         for (int base = tid - lane; base < G::NITEMS; base += NTHREADS) {
             const int i = base + lane;
             const int r = i / NOCT, o = i - r * NOCT, tp = r / (BM + 2), tr = r - tp * (BM + 2);
-            const uint4* vp = sh.tile + r * MK_ROWV + o * OV;
+            const uint4* vp = sh.tile + r * MK_ROWV + 1 + o * OV;
             MkOct mo;
             if constexpr (sizeof(T) == 2) {
                 const uint4 c = vp[0];
-                uint32_t w4 = __shfl_sync(0xffffffffu, c.x, (lane + 1) & 31);      // the next oct of the row starts with lanes 8, 9
-                if (o == NOCT - 1) w4 = vp[1].x;
-                mo = mk_oct16(c.x, c.y, c.z, c.w, w4);
+                // the neighbour lanes come from the octs either side: lanes of this warp, except at the ends of the row
+                uint32_t pw = __shfl_sync(0xffffffffu, c.w, (lane + 31) & 31), nx = __shfl_sync(0xffffffffu, c.x, (lane + 1) & 31);
+                if (o == 0) pw = vp[-1].w;
+                if (o == NOCT - 1) nx = vp[1].x;
+                mo = mk_oct16(c.x, c.y, c.z, c.w, (pw >> 16) | (nx << 16));
             } else {
                 const uint4 c = vp[0], d = vp[1];
-                const uint2 e = reinterpret_cast<const uint2*>(vp + 2)[0];
-                const uint32_t w[10] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, e.x, e.y};
+                const uint32_t w[10] = {vp[-1].w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, vp[2].x};
                 mo = mk_oct32(w);
             }
             const int ri = mk_rec_index<T>(tp, tr, o);
@@ -566,10 +581,11 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
         // ---- M2: side-table entries of the octs with 3 or 4 labels (5 and more: BAD) ------------------------------------------
         {
             const int novf = min((int)sh.ctr[3], MK_OVF);
+            if (tid == 0) TA_STAT(9, sh.ctr[3]);
             for (int e = tid; e < novf; e += NTHREADS) {
                 const int ri = (int)sh.ovf_rec[e];
                 const int tp = ri / PS, rem = ri - tp * PS, tr = rem / NOCT, o = rem - tr * NOCT;
-                const T* el = tileT + (tp * (BM + 2) + tr) * ROWE + 8 * o;
+                const T* el = tileT + (tp * (BM + 2) + tr) * ROWE + SEG - 1 + 8 * o;
                 uint32_t l0 = (uint32_t)el[0], l1 = l0, l2 = l0, l3 = l0, m0 = 1u, m1 = 0u, m2 = 0u, m3 = 0u;
                 int nl = 1;
                 bool bad = false;
@@ -602,7 +618,7 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             const int nbf_ = next_brick % P.nbf, nbm_ = (next_brick / P.nbf) % P.nbm, nbs_ = next_brick / (P.nbf * P.nbm);
             TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(sh.bar, (uint32_t)(MK_VECS * 16));
-            tma_load_box_3d(sh.tile, &tmap, sh.bar, nbf_ * BF - 1, nbm_ * BM - 1, (int)P.own_lo + nbs_ * BS - 1);
+            tma_load_box_3d(sh.tile, &tmap, sh.bar, nbf_ * BF - SEG, nbm_ * BM - 1, (int)P.own_lo + nbs_ * BS - 1);
         }
 
         // ---- P1: one block per thread: one label -> closed form, else -> list ------------------------------------------------
@@ -621,6 +637,9 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             }
             const uint32_t wlo = mmx.lo(), whi = mmx.hi();
             const bool one = valid && wlo == whi, many = valid && wlo != whi;
+            if (valid) TA_STAT(1, 1);
+            if (one) TA_STAT(2, 1);
+            if (many) TA_STAT(3, 1);
             const unsigned mm = __ballot_sync(0xffffffffu, many);
             unsigned int pos0 = 0u;
             if (lane == 0 && mm) pos0 = atomicAdd(&sh.ctr[2], (unsigned int)__popc(mm));
@@ -644,6 +663,7 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
             for (int base = tid - lane; base < count; base += NTHREADS) {
                 const int qi = base + lane;
                 const bool active = qi < count;
+                if (lane == 0) TA_STAT(4, 1);
                 const int blk = active ? (int)sh.list[qi] : 0;
                 const int o = blk % NOCT, sbq = (blk / NOCT) % (BS / BLK_S), mbq = blk / (NOCT * (BS / BLK_S));
                 const int nvf = min(8, nf - (F0 + 8 * o)), nvm = min(BLK_M, nm - (M0 + BLK_M * mbq)),
@@ -672,6 +692,8 @@ scan_meta_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constan
                 // blocks the steps did not finish (more than MK_MAXL labels, or a BAD record: nothing emitted): per-voxel
                 // path inside this warp, restricted to contributions that involve a label outside the known set
                 const bool fb = active && (more || badblk);
+                if (fb) TA_STAT(7, 1);
+                if (active && badblk) TA_STAT(8, 1);
                 unsigned fm = __ballot_sync(0xffffffffu, fb);
                 while (fm) {
                     const int src = __ffs(fm) - 1;
