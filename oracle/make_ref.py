@@ -16,6 +16,7 @@ Rewrite rules (syntax only, plus the three numpy >= 2 incompatibilities SURVEY.m
   SIA:861   ``if x != []`` on an ndarray (element-wise today) -> ``if len(x) != 0``;
   SIA:37, 42  ``dilation`` / ``dilation_by`` return a LIST of slices, an index numpy >= 1.23 rejects (the reference's bare
             ``except:`` would then silently use the whole image) -> a tuple, what the numpy of its time made of it;
+  SIA:514   ``nd.find_objects(self.image==0)``: today's scipy rejects a boolean input -> ``.astype(np.uint8)``;
   SIA:1000  ``map(int, l)`` -> ``list(map(int, l))``.
 ``openalea.image.serial.basics`` (absent here) is replaced by ``oracle/ref_stubs.py`` through ``sys.modules``.
 """
@@ -106,6 +107,8 @@ def convert(src):
                 "return [ slice(max(0,s.start-amount), s.stop+amount) for s in slices ]"):
         assert old in s, old
         s = s.replace(old, "return tuple(" + old[len("return "):] + ")")
+    # scipy today rejects a boolean input of find_objects (SIA:514)
+    s = s.replace("nd.find_objects(self.image==0)[0]", "nd.find_objects((self.image==0).astype(np.uint8))[0]")
     # py2 map() returns a list (SIA:1000 sorts and indexes it)
     s = s.replace("integers = lambda l : map(int, l)", "integers = lambda l : list(map(int, l))")
     return s

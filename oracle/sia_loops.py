@@ -205,8 +205,8 @@ class LoopOracle(object):
 
     # ------------------------------------------------------- boundingbox SIA:483-535
     def boundingbox(self, labels=None, real=False):
-        if isinstance(labels, int) and labels == 0:
-            return nd.find_objects(self.image == 0)[0]
+        if isinstance(labels, (int, np.integer)) and labels == 0:    # SIA:513 ``if labels == 0`` (numpy scalars too)
+            return nd.find_objects((self.image == 0).astype(np.uint8))[0]    # scipy >= 1.12 rejects a boolean input
         if self._bbox is None:
             self._bbox = nd.find_objects(self.image)
         if labels is None:

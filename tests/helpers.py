@@ -200,3 +200,14 @@ def compare_api(prod, orc, check_wall_voxels=True, rtol=1e-6, eig=True, real_mod
         assert (rows >= 0).all()
         for k, r in zip(wvp, rows):
             assert t.wall18[r] == wvp[k].shape[1]
+        if bg is not None:
+            # SIA:1062-1074: the label list comes from the first voxel layer (np.unique: an ndarray, so the reference's
+            # ``labels + [background]`` is an element-wise sum)
+            for kw in (dict(), dict(ignore_background=True)):
+                ep = prod.wall_voxels_per_cells_pairs(only_epidermis=True, verbose=False, **kw)
+                eo = orc.wall_voxels_per_cells_pairs(only_epidermis=True, verbose=False, **kw)
+                assert set(ep) == set((int(a), int(b)) for a, b in eo), kw
+                for (a, b), xyz in eo.items():
+                    assert np.array_equal(ep[(int(a), int(b))], xyz), (a, b)
+    k6 = prod.neighbor_kernels()
+    assert len(k6) == 6 and all(np.array_equal(x, y) for x, y in zip(k6, orc.neighbor_kernels()))

@@ -151,6 +151,7 @@ inline bool run_block(unsigned block, unsigned grid, int nthreads, std::function
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
 #define volatile                                   /* single OS thread: plain accesses (define AFTER every std header) */
+#define TA_SHARED static                           /* statically sized __shared__ variables: one block at a time, so a static */
 #define TA_PTX(...) ((void)0)                      /* inline PTX: only on paths the emulation does not take */
 
 inline void __syncthreads() {

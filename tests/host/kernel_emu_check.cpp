@@ -14,6 +14,7 @@ static unsigned long long g_user_stat[16];
 #include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_meta.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_scan_rec.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
 void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
@@ -55,9 +56,9 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
-enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, META, NWHICH };
+enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, META, REC, NWHICH };
 static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
-                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>", "scan_meta_kernel<T>"};
+                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>", "scan_meta_kernel<T>", "rec_build + rec_blocks<T>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -119,6 +120,18 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
         memcpy(&tmap, &em, sizeof em);
     }
     bool ok = true;
+    if (which == REC) {
+        // the two-kernel record scan: what launch_scan of ta_api.cu does
+        RecBuf R{};
+        R.noct = (nf + 7) / 8; R.plane0 = std::max(own_lo - 1, 0); R.nplanes = std::min(own_hi + 1, nbuf) - R.plane0;
+        const size_t nrec = (size_t)R.nplanes * nm * R.noct;
+        std::vector<uint32_t> ra(nrec, 0xDEADBEEFu), rb(nrec, 0xDEADBEEFu), rq(nrec, 0xDEADBEEFu), re(nrec, 0xDEADBEEFu), re2(nrec, 0xDEADBEEFu);
+        R.a = ra.data(); R.b = rb.data(); R.q = rq.data(); R.e = re.data(); R.e2 = re2.data();
+        P.nbf = (nf + RB_BF - 1) / RB_BF;
+        const unsigned g1 = (unsigned)std::min<size_t>((nrec + 255) / 256, 3);
+        for (unsigned block = 0; block < g1 && ok; ++block) ok = emu::run_block(block, g1, 256, [&]() { rec_build_kernel<T>(P, R); });
+        for (unsigned block = 0; block < 2 && ok; ++block) ok = emu::run_block(block, 2, NTHREADS, [&]() { rec_blocks_kernel<T>(P, R, lt, pt); });
+    } else
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
         ok = emu::run_block(block, 2, NTHREADS, [&]() {
             if (which == PRODUCT) scan_kernel<T, false, false>(P, lt, pt, tmap);
@@ -151,6 +164,28 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
                         "(equal %d), pairs %zu/%zu (equal %d)%s\n", which_name[which], (int)sizeof(T), nf, nm, nbuf, own_lo, own_hi, nlabels,
                 mode, seed, ok ? "ok" : "DEADLOCK", status[0], status[1], gotL.size(), refL.size(), (int)(gotL == refL), gotP.size(),
                 refP.size(), (int)(gotP == refP), use_tma ? " [emulated TMA staging]" : "");
+        if (getenv("EMU_DIFF")) {
+            int shown = 0;
+            for (auto& kv : refL) {
+                auto it = gotL.find(kv.first);
+                if (it == gotL.end()) { if (shown++ < 6) fprintf(stderr, "  label %u missing (ref n=%llu)\n", kv.first, kv.second.v[0]); continue; }
+                if (!(it->second == kv.second) && shown++ < 6) {
+                    fprintf(stderr, "  label %u ref:", kv.first); for (int k = 0; k < 10; ++k) fprintf(stderr, " %llu", kv.second.v[k]);
+                    fprintf(stderr, " box %ld %ld %ld - %ld %ld %ld\n             got:", kv.second.bmin[0], kv.second.bmin[1], kv.second.bmin[2], kv.second.bmax[0], kv.second.bmax[1], kv.second.bmax[2]);
+                    for (int k = 0; k < 10; ++k) fprintf(stderr, " %llu", it->second.v[k]);
+                    fprintf(stderr, " box %ld %ld %ld - %ld %ld %ld\n", it->second.bmin[0], it->second.bmin[1], it->second.bmin[2], it->second.bmax[0], it->second.bmax[1], it->second.bmax[2]);
+                }
+            }
+            shown = 0;
+            for (auto& kv : refP) {
+                auto it = gotP.find(kv.first);
+                if ((it == gotP.end() || it->second != kv.second) && shown++ < 6) {
+                    fprintf(stderr, "  pair (%u,%u) ref:", kv.first.first, kv.first.second); for (int k = 0; k < 7; ++k) fprintf(stderr, " %llu", kv.second[k]);
+                    fprintf(stderr, "  got:"); if (it != gotP.end()) for (int k = 0; k < 7; ++k) fprintf(stderr, " %llu", it->second[k]); else fprintf(stderr, " none");
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
         return 1;
     }
     return 0;

@@ -18,6 +18,7 @@
 #include "ta_scan_level.cuh"
 #endif
 #include "ta_scan_meta.cuh"
+#include "ta_scan_rec.cuh"
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -60,6 +61,8 @@ struct ta_ctx {
     cudaEvent_t ev[6] = {};
     cudaStream_t copy_stream = nullptr;          // H2D chunks of ta_run_pass_host
     std::vector<cudaEvent_t> chunk_ev;
+    uint32_t* rec_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // record scratch of the two-kernel scan (a, b, q, e, e2)
+    size_t rec_have[5] = {0, 0, 0, 0, 0};
     float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
     uint64_t launches = 0;
 };
@@ -166,6 +169,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
+    for (auto& rb : ctx->rec_buf) cudaFree(rb);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->diag_host) cudaFreeHost(ctx->diag_host);
@@ -353,6 +357,36 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
+    if (P.flags & 0x80000u) {
+        // the two-kernel record scan (ta_scan_rec.cuh): records of planes [own_lo - 1, own_hi], then one warp per brick
+        ta::RecBuf R{};
+        R.noct = (int)((ctx->nf + 7) / 8);
+        R.plane0 = (int)std::max<long long>(own_lo - 1, 0);
+        R.nplanes = (int)(std::min<long long>(own_hi + 1, ctx->ns) - R.plane0);
+        const size_t nrec = (size_t)R.nplanes * (size_t)ctx->nm * (size_t)R.noct;
+        if (nrec >= (1ull << 31)) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass of the record scan");
+        const int nbuf = ctx->elem == 2 ? 3 : 5;
+        const int which[5] = {0, 2, 3, 1, 4};                 // uint16 uses a, q, e
+        for (int k = 0; k < nbuf; ++k) {
+            int rc = ensure(ctx, &ctx->rec_buf[which[k]], &ctx->rec_have[which[k]], nrec);
+            if (rc) return rc;
+        }
+        R.a = ctx->rec_buf[0]; R.b = ctx->rec_buf[1]; R.q = ctx->rec_buf[2]; R.e = ctx->rec_buf[3]; R.e2 = ctx->rec_buf[4];
+        P.nbf = (int)((ctx->nf + ta::RB_BF - 1) / ta::RB_BF);
+        const size_t rtotal = (size_t)P.nbf * P.nbm * P.nbs;
+        const int g1 = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ctx->num_sms * 16);
+        const int g2 = (int)std::min<size_t>((rtotal + ta::RB_WARPS - 1) / ta::RB_WARPS, (size_t)ctx->num_sms * TA_REC_MINB);
+        if (ctx->elem == 2) {
+            ta::rec_build_kernel<uint16_t><<<g1, 256, 0, st>>>(P, R);
+            ta::rec_blocks_kernel<uint16_t><<<g2, ta::NTHREADS, 0, st>>>(P, R, ctx->lt, ctx->pt);
+        } else {
+            ta::rec_build_kernel<uint32_t><<<g1, 256, 0, st>>>(P, R);
+            ta::rec_blocks_kernel<uint32_t><<<g2, ta::NTHREADS, 0, st>>>(P, R, ctx->lt, ctx->pt);
+        }
+        ctx->launches += 2;
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
     if (P.flags & 0x40000u) {
         // the record kernel (ta_scan_meta.cuh)
         typedef void (*meta_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
@@ -503,6 +537,7 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         else if (!strcmp(pp, "level_simple")) P.flags |= 0x4000u | 0x8000u | 0x10000u;
         else if (!strcmp(pp, "level_pf")) P.flags |= 0x4000u | 0x10000u | 0x20000u;
         else if (!strcmp(pp, "meta")) P.flags |= 0x40000u;
+        else if (!strcmp(pp, "rec")) P.flags |= 0x80000u;
     }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {

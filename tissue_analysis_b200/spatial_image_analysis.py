@@ -307,7 +307,7 @@ class AbstractSpatialImageAnalysis(object):
     def boundingbox(self, labels=None, real=False):
         # SIA:483-535
         t = self._tables()
-        if isinstance(labels, int) and labels == 0:
+        if isinstance(labels, (int, np.integer)) and labels == 0:       # SIA:513 ``if labels == 0`` (numpy scalars too)
             if t.count[0] == 0:
                 raise IndexError("list index out of range")
             return _as_slices(t.bmin[0], t.bmax[0])
@@ -406,6 +406,24 @@ class AbstractSpatialImageAnalysis(object):
             if areas[(i, j)] < min_contact_area:
                 nei.remove(i if j == label else j)
         return nei
+
+    def neighbor_kernels(self):
+        """SIA:695-732: the six one-sided structuring elements the reference dilates with (a = 0: +x, 1: -x, 2: +y,
+        3: -y, 4: +z, 5: -z).  Nothing here dilates with them -- the scan counts the faces per direction -- the accessor is
+        part of the public surface."""
+        if self._kernels is None:
+            kernels = []
+            for axis in range(3):
+                for drop in (0, 2):
+                    k = np.zeros((3, 3, 3), np.bool_)
+                    idx = [1, 1, 1]
+                    idx[axis] = slice(None)
+                    k[tuple(idx)] = True
+                    idx[axis] = drop
+                    k[tuple(idx)] = False
+                    kernels.append(k)
+            self._kernels = tuple(kernels)
+        return self._kernels
 
     def neighbors_number(self, labels=None, min_contact_area=None, real_area=True, verbose=True):
         # SIA:734-742
@@ -570,13 +588,16 @@ class AbstractSpatialImageAnalysis(object):
                                     ignore_background=False, min_contact_area=None, real_area=True, verbose=True):
         # SIA:1049-1111 -- the per-label loop only decides WHICH pairs are extracted; the voxels of all of them come
         # from one device pass.
-        if only_epidermis:
-            raise NotImplementedError("only_epidermis reads the first-voxel-layer image (SIA:1062-1063)")
+        # only_epidermis (SIA:1062-1065, 1073-1074): the first-voxel-layer image only ever supplies the label list,
+        # np.unique of it (an ndarray: 0, the background mark and the labels of the layer); the voxels still come from
+        # the image itself.
         compute_neighborhood = neighborhood is None
         if isinstance(labels, list) and isinstance(neighborhood, dict):
             labels = [label for label in labels if label in neighborhood]
-        if labels is None:
+        if labels is None and not only_epidermis:
             labels = self.labels()
+        elif labels is None and only_epidermis:
+            labels = np.unique(np.asarray(self.voxel_first_layer(True)))
         elif isinstance(labels, list):
             labels.sort()
             if not isinstance(neighborhood, dict):
@@ -585,7 +606,12 @@ class AbstractSpatialImageAnalysis(object):
             labels = [labels]
         else:
             raise ValueError("Couldn't find any labels.")
-        allowed = set(labels) if ignore_background else set(labels) | set([self.background()])
+        if isinstance(labels, np.ndarray):
+            # ``labels + [background]`` (SIA:1101) on an ndarray is numpy's element-wise sum, not a concatenation
+            allowed = set(labels.tolist()) if ignore_background else set((labels + [self.background()]).tolist())
+            labels = [int(l) for l in labels]
+        else:
+            allowed = set(labels) if ignore_background else set(labels) | set([self.background()])
         wanted, seen = [], set()
         for label in labels:
             if compute_neighborhood:
