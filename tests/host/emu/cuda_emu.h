@@ -166,6 +166,14 @@ inline int __syncthreads_and(int pred) {
                                     for (int i = 0; i < n; ++i) r[i] = all;
                                 }, &emu::g_stats.syncthreads);
 }
+inline int __syncthreads_or(int pred) {
+    return (int)emu::rendezvous(emu::g_block, emu::g_cur, emu::g_nthreads, pred ? 1ull : 0ull,
+                                [](unsigned long long* v, unsigned long long* r, int n) {
+                                    unsigned long long any = 0ull;
+                                    for (int i = 0; i < n; ++i) any |= v[i];
+                                    for (int i = 0; i < n; ++i) r[i] = any;
+                                }, &emu::g_stats.syncthreads);
+}
 inline void emu_check_mask(unsigned mask) {
     if (mask != 0xffffffffu) { fprintf(stderr, "emu: only full-mask warp collectives are emulated\n"); abort(); }
 }
@@ -209,14 +217,21 @@ template <typename V> inline V __shfl_up_sync(unsigned mask, V var, unsigned del
     const V got = __shfl_sync(mask, var, ln >= (int)delta ? ln - (int)delta : ln, width);
     return got;
 }
+// redux with per-lane member masks (the match_any + redux pattern: every lane of the warp calls, each names its own group;
+// a lane's result is the reduction over the lanes of ITS mask)
 #define EMU_REDUX(name, init, op)                                                                                    \
     inline unsigned name(unsigned mask, unsigned v) {                                                                 \
-        emu_check_mask(mask);                                                                                         \
-        return (unsigned)emu::rendezvous(emu::my_warp(), emu::lane(), emu::warp_size_here(), (unsigned long long)v,   \
+        if (!((mask >> emu::lane()) & 1u)) { fprintf(stderr, "emu: redux: the caller is not in its member mask\n"); abort(); } \
+        return (unsigned)emu::rendezvous(emu::my_warp(), emu::lane(), emu::warp_size_here(),                          \
+                                         ((unsigned long long)mask << 32) | (unsigned long long)v,                    \
                                          [](unsigned long long* x, unsigned long long* r, int n) {                    \
-                                             unsigned a = (init);                                                     \
-                                             for (int i = 0; i < n; ++i) { const unsigned b = (unsigned)x[i]; a = (op); } \
-                                             for (int i = 0; i < n; ++i) r[i] = a;                                    \
+                                             for (int me = 0; me < n; ++me) {                                         \
+                                                 const unsigned mk = (unsigned)(x[me] >> 32);                         \
+                                                 unsigned a = (init);                                                 \
+                                                 for (int i = 0; i < n; ++i)                                          \
+                                                     if ((mk >> i) & 1u) { const unsigned b = (unsigned)x[i]; a = (op); } \
+                                                 r[me] = a;                                                           \
+                                             }                                                                        \
                                          }, &emu::g_stats.redux);                                                     \
     }
 EMU_REDUX(__reduce_add_sync, 0u, a + b)
@@ -225,6 +240,20 @@ EMU_REDUX(__reduce_max_sync, 0u, (a > b ? a : b))
 EMU_REDUX(__reduce_or_sync, 0u, a | b)
 EMU_REDUX(__reduce_and_sync, 0xFFFFFFFFu, a & b)
 
+template <typename V> inline unsigned __match_any_sync(unsigned mask, V key) {
+    emu_check_mask(mask);
+    static_assert(sizeof(V) <= 8, "match on at most 64 bits");
+    unsigned long long bits = 0;
+    memcpy(&bits, &key, sizeof(V));
+    return (unsigned)emu::rendezvous(emu::my_warp(), emu::lane(), emu::warp_size_here(), bits,
+                                     [](unsigned long long* x, unsigned long long* r, int n) {
+                                         for (int me = 0; me < n; ++me) {
+                                             unsigned long long m = 0;
+                                             for (int i = 0; i < n; ++i) if (x[i] == x[me]) m |= 1ull << i;
+                                             r[me] = m;
+                                         }
+                                     }, &emu::g_stats.ballot);
+}
 template <typename V> inline V atomicAdd(V* p, V v) { emu::count_atomic(p); V o = *p; *p = (V)(o + v); return o; }
 inline unsigned atomicAdd(unsigned* p, int v) { emu::count_atomic(p); unsigned o = *p; *p = o + (unsigned)v; return o; }
 template <typename V> inline V atomicMin(V* p, V v) { emu::count_atomic(p); V o = *p; if (v < o) *p = v; return o; }

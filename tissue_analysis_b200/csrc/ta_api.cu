@@ -374,7 +374,8 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
         R.a = ctx->rec_buf[0]; R.b = ctx->rec_buf[1]; R.q = ctx->rec_buf[2]; R.e = ctx->rec_buf[3]; R.e2 = ctx->rec_buf[4];
         P.nbf = (int)((ctx->nf + ta::RB_BF - 1) / ta::RB_BF);
         const size_t rtotal = (size_t)P.nbf * P.nbm * P.nbs;
-        const int g1 = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ctx->num_sms * 16);
+        const size_t nchunks = (size_t)R.nplanes * (size_t)ctx->nm * (size_t)((R.noct + 31) / 32);      // one warp per 32 octs of a row
+        const int g1 = (int)std::min<size_t>((nchunks + 7) / 8, (size_t)ctx->num_sms * 16);
         const int g2 = (int)std::min<size_t>((rtotal + ta::RB_WARPS - 1) / ta::RB_WARPS, (size_t)ctx->num_sms * TA_REC_MINB);
         if (ctx->elem == 2) {
             ta::rec_build_kernel<uint16_t><<<g1, 256, 0, st>>>(P, R);

@@ -31,6 +31,17 @@
 #pragma once
 #include "ta_scan_meta.cuh"
 
+#ifndef TA_SHARED
+#define TA_SHARED __shared__
+#endif
+// the warps of rec_blocks_kernel are never in step with each other, so its code has to stay in the instruction cache:
+// the big helpers are real functions unless TA_REC_INLINE is defined
+#ifdef TA_REC_INLINE
+#define TA_REC_FN __device__ __forceinline__
+#else
+#define TA_REC_FN __device__ __noinline__
+#endif
+
 namespace ta {
 
 struct RecBuf {
@@ -112,16 +123,18 @@ rec_build_kernel(ScanParams P, RecBuf R) {
     constexpr int SEG = Vox<T>::SEG;
     const T* vol = reinterpret_cast<const T*>(P.vol);
     const int nf = (int)P.nf, nm = (int)P.nm, noct = R.noct;
-    const long long total = (long long)R.nplanes * nm * noct;
     const int lane = threadIdx.x & 31;
     const bool fast = P.vec_ok && (nf % 8) == 0;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
-        const long long i = i0 + lane;
-        const bool active = i < total;
-        const long long row = active ? i / noct : 0;
-        const int o = active ? (int)(i - row * noct) : 0;
-        const int pl = (int)(row / nm), m = (int)(row - (long long)pl * nm);
-        const T* rp = vol + ((size_t)(R.plane0 + pl) * nm + m) * (size_t)nf;
+    // one warp per run of 32 octs of one row (no warp straddles two rows): two 32-bit divisions per warp, none per thread
+    const unsigned cpr = (unsigned)(noct + 31) / 32u, nrows = (unsigned)R.nplanes * (unsigned)nm;
+    const unsigned nchunks = nrows * cpr, nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nchunks; wi += nwarps) {
+        const unsigned row = wi / cpr, ch = wi - row * cpr;
+        const int o = (int)(ch * 32u) + lane;
+        const bool active = o < noct;
+        const unsigned pl = row / (unsigned)nm, m = row - pl * (unsigned)nm;
+        const long long i = (long long)row * noct + o;
+        const T* rp = vol + ((size_t)(R.plane0 + (int)pl) * nm + m) * (size_t)nf;
         MkOct mo;
         uint32_t w[10];                       // uint32 labels: the ten lanes; uint16: w[0..3] the oct, w[4] the neighbour word
         if constexpr (sizeof(T) == 2) {
@@ -191,6 +204,9 @@ rec_build_kernel(ScanParams P, RecBuf R) {
     }
 }
 
+TA_REC_FN void rec_label_to_global(const LabelTable lt, uint32_t* status, uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0) {
+    label_to_global(lt, status, L, v, F0, M0, S0);
+}
 // ---- kernel 2 helpers ---------------------------------------------------------------------------------------------------
 // Where a block's 24 window records live: index = planeoff[p] + rowoff[r]  (p = 0 .. 3 window planes, r = 0 .. 5 window rows)
 struct RecWin { int po[4]; int ro[6]; };
@@ -208,8 +224,11 @@ __device__ __forceinline__ uint32_t rec_mask(const RecBuf& R, int i, uint32_t L)
     }
     return a;
 }
+struct Planes4 { u64 p[4]; };
 template <typename T>
-__device__ __forceinline__ void rec_label_planes(const RecBuf& R, const RecWin& W, uint32_t L, u64 A[4]) {
+TA_REC_FN Planes4 rec_label_planes(const RecBuf R, const RecWin W, uint32_t L) {
+    Planes4 out;
+    u64* A = out.p;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         uint32_t h0 = 0u, h1 = 0u;
@@ -220,6 +239,7 @@ __device__ __forceinline__ void rec_label_planes(const RecBuf& R, const RecWin& 
         }
         A[p] = (u64)h0 | ((u64)h1 << 30);
     }
+    return out;
 }
 template <typename T>
 __device__ __forceinline__ uint32_t rec_label_at(const RecBuf& R, const RecWin& W, int p, int bit) {
@@ -242,6 +262,7 @@ __device__ __forceinline__ uint32_t rec_label_at(const RecBuf& R, const RecWin& 
 
 // moments and box of the voxels c0 (plane 0 of the block) | c1 (plane 1) in block-local coordinates; false: no voxel.
 // (The table form of BlockLevel::label_moments, on bare masks.)
+struct MomRow { uint32_t w[MK_ROW]; bool has; };
 __device__ __forceinline__ bool rec_mask_moments(u64 c0, u64 c1, const uint32_t* tab, uint32_t v[16]) {
     if (!(c0 | c1)) return false;
     uint32_t a0 = 0u, a1 = 0u, a2 = 0u, ap = 0u, apm = 0u, colmask = 0u, rows = 0u;
@@ -266,6 +287,14 @@ __device__ __forceinline__ bool rec_mask_moments(u64 c0, u64 c1, const uint32_t*
     return true;
 }
 
+// the same, moved to brick coordinates and packed for the warp merge
+TA_REC_FN MomRow rec_mask_row(u64 c0, u64 c1, const uint32_t* tab, uint32_t bF, uint32_t bM, uint32_t bS) {
+    MomRow r;
+    uint32_t v[16];
+    r.has = rec_mask_moments(c0, c1, tab, v);
+    if (r.has) { block_shift_moments(v, bF, bM, bS); mk_pack_row(v, r.w); }
+    return r;
+}
 // per-voxel path, restricted to what the label steps could not emit (global memory, clamped).  The 18 neighbours are
 // read once; wall18 counts a neighbour label at its first occurrence.
 template <typename T>
@@ -277,7 +306,7 @@ __device__ __noinline__ void rec_fallback_voxel(const ScanParams P, const LabelT
     const bool a_in = (nk > 0 && k0 == a) || (nk > 1 && k1 == a) || (nk > 2 && k2 == a) || (nk > 3 && k3 == a);
     if (do_mom && !a_in) {
         uint32_t v[16] = {1u, bf, bm, bs, bf * bf, bf * bm, bf * bs, bm * bm, bm * bs, bs * bs, bf, bm, bs, bf, bm, bs};
-        label_to_global(lt, pt.status, a, v, gF0, gM0, gS0);
+        rec_label_to_global(lt, pt.status, a, v, gF0, gM0, gS0);
     }
     if (!(do_p6 || do_w18)) return;
     constexpr int df[18] = {1, 0, 0, -1, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1, 0, 0, 0, 0};
@@ -302,9 +331,201 @@ __device__ __noinline__ void rec_fallback_voxel(const ScanParams P, const LabelT
     }
 }
 
+
+// ---- table updates: match + redux merge across the warp, then per-WARP tables in shared memory, flushed once per brick ----
+// A warp works on one brick at a time, so its tables hold brick-local sums (u32) of at most WL_SLOTS labels / WP_SLOTS
+// pairs; what does not fit goes straight to the global tables.  Only group leaders (one lane per distinct key) touch a
+// table, and a key has one leader per call: plain read-modify-write, a CAS only to claim a slot.
+constexpr int WL_SLOTS = 16, WP_SLOTS = 32;
+template <typename T> struct WarpTabs {
+    uint32_t* lkey;                        // [WL_SLOTS] label, TA_EMPTY32 when free
+    uint32_t* lval;                        // [WL_SLOTS][16] fields of label_to_global
+    typename Vox<T>::PKey* pkey;           // [WP_SLOTS]
+    uint32_t* pval;                        // [WP_SLOTS][4] packed 16-bit counters [w18|f0] [f1|f2] [f3|f4] [f5|-]
+};
+template <typename T> struct WarpTabsSize {
+    static constexpr size_t value = WL_SLOTS * 4 + WL_SLOTS * 16 * 4 + WP_SLOTS * sizeof(typename Vox<T>::PKey) + WP_SLOTS * 4 * 4;
+};
+template <typename T>
+__device__ __forceinline__ void warp_tabs_clear(const WarpTabs<T>& t, int lane) {
+    if (lane < WL_SLOTS) {
+        t.lkey[lane] = TA_EMPTY32;
+#pragma unroll
+        for (int f = 0; f < 16; ++f) t.lval[lane * 16 + f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+    }
+    t.pkey[lane] = Vox<T>::PEMPTY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t.pval[lane * 4 + w] = 0u;
+}
+template <typename T>
+__device__ __noinline__ void warp_tabs_add_label(const WarpTabs<T> t, const LabelTable lt, uint32_t* status, uint32_t L,
+                                                 uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6,
+                                                 uint32_t w7, uint32_t w8, uint32_t w9, u64 gF0, u64 gM0, u64 gS0) {
+    const uint32_t w[MK_ROW] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9};
+    uint32_t u[16];
+    mk_unpack_row(w, u);
+    uint32_t slot = (L * 0x9E3779B1u) >> 28;
+    int found = -1;
+    for (int probe = 0; probe < WL_SLOTS; ++probe) {
+        const uint32_t k = *((volatile uint32_t*)&t.lkey[slot]);
+        if (k == L) { found = (int)slot; break; }
+        if (k == TA_EMPTY32) {
+            const uint32_t old = atomicCAS(&t.lkey[slot], TA_EMPTY32, L);
+            if (old == TA_EMPTY32 || old == L) { found = (int)slot; break; }
+        }
+        slot = (slot + 1) & (WL_SLOTS - 1);
+    }
+    if (found < 0) { rec_label_to_global(lt, status, L, u, gF0, gM0, gS0); return; }
+    uint32_t* d = t.lval + found * 16;
+#pragma unroll
+    for (int f = 0; f < 10; ++f) d[f] += u[f];
+#pragma unroll
+    for (int f = 10; f < 13; ++f) d[f] = min(d[f], u[f]);
+#pragma unroll
+    for (int f = 13; f < 16; ++f) d[f] = max(d[f], u[f]);
+}
+template <typename T>
+__device__ __noinline__ void warp_tabs_add_pair(const WarpTabs<T> t, const PairTable pt, typename Vox<T>::PKey key, uint32_t i0, uint32_t i1,
+                                                uint32_t i2, uint32_t i3) {
+    typedef typename Vox<T>::PKey PKey;
+    uint32_t slot = Vox<T>::hash(key) & (WP_SLOTS - 1);
+    int found = -1;
+    for (int probe = 0; probe < WP_SLOTS; ++probe) {
+        const PKey k = *((volatile PKey*)&t.pkey[slot]);
+        if (k == key) { found = (int)slot; break; }
+        if (k == Vox<T>::PEMPTY) {
+            const PKey old = atomicCAS(&t.pkey[slot], Vox<T>::PEMPTY, key);
+            if (old == Vox<T>::PEMPTY || old == key) { found = (int)slot; break; }
+        }
+        slot = (slot + 1) & (WP_SLOTS - 1);
+    }
+    const uint32_t inc[4] = {i0, i1, i2, i3};
+    if (found >= 0) {
+        uint32_t* d = t.pval + found * 4;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) d[w] += inc[w];
+        return;
+    }
+    const int g = ta_pair_slot(pt, Vox<T>::key64(key));
+    if (g < 0) return;
+    uint32_t* v = &pt.vals[(size_t)g * TA_PAIR_STRIDE];
+#pragma unroll
+    for (int idx = 0; idx < 7; ++idx) {
+        const uint32_t n = (inc[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+        if (n) atomicAdd(&v[idx == 0 ? 6 : idx - 1], n);
+    }
+}
+// brick done: every slot to the global tables, tables empty again (all lanes call)
+template <typename T>
+__device__ __noinline__ void warp_tabs_flush(const WarpTabs<T> t, const LabelTable lt, const PairTable pt, u64 gF0, u64 gM0, u64 gS0, int lane) {
+    __syncwarp();
+    if (lane < WL_SLOTS) {
+        const uint32_t L = t.lkey[lane];
+        if (L != TA_EMPTY32) {
+            uint32_t* d = t.lval + lane * 16;
+            rec_label_to_global(lt, pt.status, L, d, gF0, gM0, gS0);
+            t.lkey[lane] = TA_EMPTY32;
+#pragma unroll
+            for (int f = 0; f < 16; ++f) d[f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+        }
+    }
+    {
+        const typename Vox<T>::PKey key = t.pkey[lane];
+        if (key != Vox<T>::PEMPTY) {
+            uint32_t* d = t.pval + lane * 4;
+            const int g = ta_pair_slot(pt, Vox<T>::key64(key));
+            if (g >= 0) {
+                uint32_t* v = &pt.vals[(size_t)g * TA_PAIR_STRIDE];
+#pragma unroll
+                for (int idx = 0; idx < 7; ++idx) {
+                    const uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+                    if (n) atomicAdd(&v[idx == 0 ? 6 : idx - 1], n);
+                }
+            }
+            t.pkey[lane] = Vox<T>::PEMPTY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) d[w] = 0u;
+        }
+    }
+    __syncwarp();
+}
+// all 32 lanes call; has = false: nothing to add.  A warp-uniform loop over the distinct keys, full-mask redux (a redux
+// over a sub-mask that differs from lane to lane is a loop over the groups in the compiler's own code: measured, 12 % of
+// the kernel's instructions), then the group leaders add in one SIMT pass.
+template <typename T>
+__device__ __forceinline__ void rec_put_label(const WarpTabs<T>& t, const LabelTable& lt, uint32_t* status, bool has, uint32_t L,
+                                              const uint32_t w[MK_ROW], u64 gF0, u64 gM0, u64 gS0, int lane) {
+    __syncwarp();
+    unsigned pending = __ballot_sync(0xffffffffu, has);
+    uint32_t tot[MK_ROW];
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const uint32_t Lk = __shfl_sync(0xffffffffu, L, leader);
+        const bool mine = has && (L == Lk);
+        const bool lead = (lane == leader);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? w[i] : 0u);
+            if (lead) tot[i] = r;
+        }
+        uint32_t r = __reduce_min_sync(0xffffffffu, mine ? w[7] : 0xFFFFFFFFu);
+        if (lead) tot[7] = r;
+        r = __reduce_max_sync(0xffffffffu, mine ? w[8] : 0u);
+        if (lead) tot[8] = r;
+        r = __reduce_or_sync(0xffffffffu, mine ? w[9] : 0u);
+        if (lead) tot[9] = r;
+        am_leader = am_leader || lead;
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (am_leader)
+        warp_tabs_add_label<T>(t, lt, status, L, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], tot[7], tot[8], tot[9], gF0, gM0, gS0);
+}
+template <typename T>
+__device__ __forceinline__ void rec_put_pair(const WarpTabs<T>& t, const PairTable& pt, bool has, uint32_t a, uint32_t b, const uint32_t inc[4],
+                                             int lane) {
+    typedef typename Vox<T>::PKey PKey;
+    __syncwarp();
+    const PKey key = has ? Vox<T>::key(a, b) : Vox<T>::PEMPTY;
+    unsigned pending = __ballot_sync(0xffffffffu, has);
+    uint32_t tot[4] = {0u, 0u, 0u, 0u};
+    bool am_leader = false;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const PKey kk = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = has && (key == kk);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t r = __reduce_add_sync(0xffffffffu, mine ? inc[w] : 0u);
+            if (lane == leader) tot[w] = r;
+        }
+        am_leader = am_leader || (lane == leader);
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (am_leader) warp_tabs_add_pair<T>(t, pt, key, tot[0], tot[1], tot[2], tot[3]);
+}
+
 // list 3: what step I adds for a block: the moments of slot I and its pairs with the older slots
 template <typename T, int I>
-__device__ __forceinline__ void rec_steps(const RecBuf& R, const RecWin& W, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
+__device__ __forceinline__ void rec_emit_slot(const WarpTabs<T>& tabs, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
+                                              const uint32_t* momtab, const BlockLevel<T, MK_MAXL>& b, bool active, uint32_t bF, uint32_t bM,
+                                              uint32_t bS, u64 gF0, u64 gM0, u64 gS0, int lane) {
+    const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
+    uint32_t inc[I > 0 ? I : 1][4];
+    bool hasp[I > 0 ? I : 1];
+    MomRow row;
+    row.has = false;
+    if (active && do_mom) row = rec_mask_row(b.M1[I] & b.cv0, b.M2[I] & b.cv1, momtab, bF, bM, bS);
+#pragma unroll
+    for (int j = 0; j < I; ++j) hasp[j] = active && (do_p6 || do_w18) && b.pair_increments(I, j, do_p6, do_w18, inc[j]);
+    rec_put_label<T>(tabs, lt, pt.status, row.has, b.lab[I], row.w, gF0, gM0, gS0, lane);
+    if (do_p6 || do_w18) {
+#pragma unroll
+        for (int j = 0; j < I; ++j) rec_put_pair<T>(tabs, pt, hasp[j], b.lab[I], b.lab[j], inc[j], lane);
+    }
+}
+template <typename T, int I>
+__device__ __forceinline__ void rec_steps(const WarpTabs<T>& tabs, const RecBuf& R, const RecWin& W, const ScanParams& P, const LabelTable& lt, const PairTable& pt,
                                           const uint32_t* momtab, BlockLevel<T, MK_MAXL>& b, bool& more, uint32_t bF, uint32_t bM, uint32_t bS,
                                           u64 gF0, u64 gM0, u64 gS0, int lane) {
     if constexpr (I < MK_MAXL) {
@@ -317,22 +538,19 @@ __device__ __forceinline__ void rec_steps(const RecBuf& R, const RecWin& W, cons
             const int p = b.R0 ? 0 : b.R1 ? 1 : b.R2 ? 2 : 3;
             const u64 rp = b.R0 ? b.R0 : b.R1 ? b.R1 : b.R2 ? b.R2 : b.R3;
             const uint32_t L = rec_label_at<T>(R, W, p, ta_ffs64(rp) - 1);
-            u64 A[4];
-            rec_label_planes<T>(R, W, L, A);
-            const u64 neq[4] = {~A[0] & ALL, ~A[1] & ALL, ~A[2] & ALL, ~A[3] & ALL};
+            const Planes4 A4 = rec_label_planes<T>(R, W, L);
+            const u64 neq[4] = {~A4.p[0] & ALL, ~A4.p[1] & ALL, ~A4.p[2] & ALL, ~A4.p[3] & ALL};
             b.template set_slot<I>(L, neq);
             more = (b.R0 | b.R1 | b.R2 | b.R3) != 0ull;
         } else {
             b.template clear_slot<I>();
         }
-        mk_emit_slot<T, I>(P, lt, pt, momtab, b, act, bF, bM, bS, gF0, gM0, gS0, lane);
-        rec_steps<T, I + 1>(R, W, P, lt, pt, momtab, b, more, bF, bM, bS, gF0, gM0, gS0, lane);
+        rec_emit_slot<T, I>(tabs, P, lt, pt, momtab, b, act, bF, bM, bS, gF0, gM0, gS0, lane);
+        rec_steps<T, I + 1>(tabs, R, W, P, lt, pt, momtab, b, more, bF, bM, bS, gF0, gM0, gS0, lane);
     }
 }
 
-#ifndef TA_SHARED
-#define TA_SHARED __shared__
-#endif
+
 #ifndef TA_FORCE_LIST3
 #define TA_FORCE_LIST3 0
 #endif
@@ -347,8 +565,15 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
     TA_SHARED uint32_t momtab[256];
     TA_SHARED unsigned short list2[RB_WARPS][RB_NBLK], list3[RB_WARPS][RB_NBLK];
     TA_SHARED uint32_t l2lo[RB_WARPS][RB_NBLK], l2hi[RB_WARPS][RB_NBLK];
+    TA_SHARED unsigned long long tabmem[RB_WARPS][(WarpTabsSize<T>::value + 7) / 8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256; i += NTHREADS) momtab[i] = block_byte_moments_packed((uint32_t)i);
+    WarpTabs<T> tabs;
+    tabs.pkey = reinterpret_cast<typename Vox<T>::PKey*>(&tabmem[warp][0]);
+    tabs.lkey = reinterpret_cast<uint32_t*>(tabs.pkey + WP_SLOTS);
+    tabs.lval = tabs.lkey + WL_SLOTS;
+    tabs.pval = tabs.lval + WL_SLOTS * 16;
+    warp_tabs_clear<T>(tabs, lane);
     __syncthreads();
 
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
@@ -360,7 +585,13 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
         unsigned int brick = 0u;
         if (lane == 0) brick = atomicAdd(P.brick_counter, 1u);
         brick = __shfl_sync(0xffffffffu, brick, 0);
-        if (brick >= total) break;
+        // The warps of a CTA work on different bricks but run the same PHASE at the same time (block barriers between the
+        // phases): warps scattered over 12 000 instructions miss the instruction cache on almost every fetch (measured:
+        // 79 stall cycles per issue, 6 % issue utilisation).  A warp without a brick walks through the barriers.
+        const bool have = brick < total;
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+        bool skip = !have;
+        if (!have) brick = 0u;
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * RB_BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS, og0 = bf * RB_NOCT;
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
@@ -372,7 +603,7 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
             RecIO<T>::lohi(R, ((S0 - R.plane0) * nm + M0) * noct + og0, ref, dummy);
             bool same = true;
             const int o = lane & 15;
-            for (int r0 = 0; r0 < MK_ROWS && same; r0 += 16) {      // 8 rows at a time for the early exit
+            for (int r0 = 0; r0 < MK_ROWS && same && !skip; r0 += 16) {      // 8 rows at a time for the early exit
                 bool ok = true;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -385,20 +616,21 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
                 }
                 same = __ballot_sync(0xffffffffu, !ok) == 0u;
             }
-            if (same) {
+            if (same && !skip) {
                 if (lane == 0 && do_mom) {
                     uint32_t v[16];
                     block_uniform_moments((uint32_t)min(RB_BF, nf - F0), (uint32_t)min(BM, nm - M0), (uint32_t)min(BS, (int)P.own_hi - S0), v);
-                    label_to_global(lt, pt.status, ref, v, gF0, gM0, gS0);
+                    rec_label_to_global(lt, pt.status, ref, v, gF0, gM0, gS0);
                 }
-                continue;
+                skip = true;
             }
         }
-        if (lane == 0) TA_STAT(0, 1);
+        if (lane == 0 && !skip) TA_STAT(0, 1);
 
         // ---- P1: 32 blocks at a time ---------------------------------------------------------------------------------------
         int n2 = 0, n3 = 0;
-        for (int it = 0; it < RB_NBLK / 32; ++it) {
+        __syncthreads();
+        for (int it = 0; it < (skip ? 0 : RB_NBLK / 32); ++it) {
             const int blk = it * 32 + lane;
             const int o = blk % RB_NOCT, sbq = (blk / RB_NOCT) % SB, mbq = blk / (RB_NOCT * SB);
             const int nvf = min(8, nf - (F0 + 8 * o)), nvm = min(BLK_M, nm - (M0 + BLK_M * mbq)),
@@ -445,10 +677,10 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
                     block_shift_moments(v, (uint32_t)(8 * o), (uint32_t)(BLK_M * mbq), (uint32_t)(BLK_S * sbq));
                     mk_pack_row(v, w);
                 }
-                mk_put_label(lt, pt.status, has, wlo, w, gF0, gM0, gS0, lane);
+                rec_put_label<T>(tabs, lt, pt.status, has, wlo, w, gF0, gM0, gS0, lane);
             }
         }
-        __syncwarp();
+        __syncthreads();
 
         // ---- P2a: two-label blocks: one mask, its complement ----------------------------------------------------------------
         for (int base = 0; base < n2; base += 32) {
@@ -486,14 +718,13 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
                 if (r <= nvm) cv |= (u64)(((1u << nvf) - 1u) << 1) << (10 * r);
             const u64 cv0 = (active && nvs >= 1) ? cv : 0ull, cv1 = (active && nvs >= 2) ? cv : 0ull;
             const u64 ca0 = A[1] & cv0, ca1 = A[2] & cv1, cb0 = B[1] & cv0, cb1 = B[2] & cv1;
-            uint32_t wa[MK_ROW], wb[MK_ROW], inc[4] = {0u, 0u, 0u, 0u};
-            bool hasa = false, hasb = false, hasp = false;
+            uint32_t inc[4] = {0u, 0u, 0u, 0u};
+            MomRow ra, rb;
+            ra.has = rb.has = false;
+            bool hasp = false;
             if (do_mom) {
-                uint32_t v[16];
-                hasa = rec_mask_moments(ca0, ca1, momtab, v);
-                if (hasa) { block_shift_moments(v, bF, bM, bS); mk_pack_row(v, wa); }
-                hasb = rec_mask_moments(cb0, cb1, momtab, v);
-                if (hasb) { block_shift_moments(v, bF, bM, bS); mk_pack_row(v, wb); }
+                ra = rec_mask_row(ca0, ca1, momtab, bF, bM, bS);
+                rb = rec_mask_row(cb0, cb1, momtab, bF, bM, bS);
             }
             if (do_p6 || do_w18) {
                 uint32_t w18 = 0u, e0 = 0u, e1 = 0u, e2 = 0u, o0 = 0u, o1 = 0u, o2 = 0u;
@@ -514,11 +745,12 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
                 inc[0] = w18 | (e0 << 16); inc[1] = o0 | (e1 << 16); inc[2] = o1 | (e2 << 16); inc[3] = o2;
                 hasp = active && (inc[0] | inc[1] | inc[2] | inc[3]) != 0u;
             }
-            mk_put_label(lt, pt.status, hasa, wlo, wa, gF0, gM0, gS0, lane);
-            mk_put_label(lt, pt.status, hasb, whi, wb, gF0, gM0, gS0, lane);
-            if (do_p6 || do_w18) mk_put_pair<T>(pt, hasp, wlo, whi, inc, lane);
+            rec_put_label<T>(tabs, lt, pt.status, ra.has, wlo, ra.w, gF0, gM0, gS0, lane);
+            rec_put_label<T>(tabs, lt, pt.status, rb.has, whi, rb.w, gF0, gM0, gS0, lane);
+            if (do_p6 || do_w18) rec_put_pair<T>(tabs, pt, hasp, wlo, whi, inc, lane);
         }
 
+        __syncthreads();
         // ---- P2b: the other blocks, label after label --------------------------------------------------------------------------
         for (int base = 0; base < n3; base += 32) {
             const int qi = base + lane;
@@ -547,10 +779,20 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
             constexpr u64 ALL = LvBlk<T>::PLANE_ALL;
             b.R0 = b.R1 = b.R2 = b.R3 = ALL;
             bool more = active && !badblk;
-            rec_steps<T, 0>(R, W, P, lt, pt, momtab, b, more, bF, bM, bS, gF0, gM0, gS0, lane);
+            rec_steps<T, 0>(tabs, R, W, P, lt, pt, momtab, b, more, bF, bM, bS, gF0, gM0, gS0, lane);
             const bool fb = active && (more || badblk);
             if (fb) TA_STAT(7, 1);
             if (active && badblk) TA_STAT(8, 1);
+            // voxels the per-voxel path has to look at: those not covered by a known label, and those with such a voxel
+            // among their 18 neighbours (everything else was emitted by the steps); a BAD block: all of them
+            u64 nd0, nd1;
+            {
+                const u64 Rm[4] = {b.R0, b.R1, b.R2, b.R3};
+                u64 dR[2];
+                block_dilate18_rb<10>(Rm, dR);
+                nd0 = badblk ? b.cv0 : ((dR[0] | b.R1) & b.cv0);
+                nd1 = badblk ? b.cv1 : ((dR[1] | b.R2) & b.cv1);
+            }
             unsigned fm = __ballot_sync(0xffffffffu, fb);
             while (fm) {
                 const int src = __ffs(fm) - 1;
@@ -559,15 +801,18 @@ rec_blocks_kernel(ScanParams P, RecBuf R, LabelTable lt, PairTable pt) {
                 const int nk = __shfl_sync(0xffffffffu, badblk ? 0 : MK_MAXL, src);
                 const uint32_t k0 = __shfl_sync(0xffffffffu, b.lab[0], src), k1 = __shfl_sync(0xffffffffu, b.lab[1], src),
                                k2 = __shfl_sync(0xffffffffu, b.lab[2], src), k3 = __shfl_sync(0xffffffffu, b.lab[3], src);
+                const u64 c0 = __shfl_sync(0xffffffffu, nd0, src), c1 = __shfl_sync(0xffffffffu, nd1, src);
                 const int co = cblk % RB_NOCT, csb = (cblk / RB_NOCT) % SB, cmb = cblk / (RB_NOCT * SB);
                 for (int w = lane; w < 64; w += 32) {
                     const int df = w & 7, dm = (w >> 3) & 3, dsx = w >> 5;
+                    if (!(((dsx ? c1 : c0) >> (10 * (dm + 1) + df + 1)) & 1ull)) continue;
                     const uint32_t f = (uint32_t)(8 * co + df), m = (uint32_t)(BLK_M * cmb + dm), sp = (uint32_t)(BLK_S * csb + dsx);
-                    if (F0 + (int)f >= nf || M0 + (int)m >= nm || S0 + (int)sp >= (int)P.own_hi) continue;
                     rec_fallback_voxel<T>(P, lt, pt, F0 + (int)f, M0 + (int)m, S0 + (int)sp, f, m, sp, k0, k1, k2, k3, nk, gF0, gM0, gS0);
                 }
             }
         }
+        __syncthreads();
+        warp_tabs_flush<T>(tabs, lt, pt, gF0, gM0, gS0, lane);
         __syncwarp();
     }
 }
