@@ -1,8 +1,7 @@
-// Runs the scan kernels THEMSELVES on the CPU (tests/host/emu/cuda_emu.h: fibers for threads, rendezvous for the warp and
-// block collectives) and compares the tables they fill with a direct pass over the voxels.  Covered: the product kernel
-// scan_kernel<T, false, false> (march, worklists, per-voxel pair phases, flush), its one-hot instantiation, the
-// experimental block kernels of ta_scan_block.cuh and the level kernels of ta_scan_level.cuh, each with and without warp
-// merges -- on the scalar staging path (vec_ok = 0, use_tma = 0: the only path without inline PTX).  Test infrastructure: g++ only, no GPU, no nvcc.
+// Runs the scan kernel ITSELF on the CPU (tests/host/emu/cuda_emu.h: fibers for threads, rendezvous for the warp and block
+// collectives) and compares the tables it fills with a direct pass over the voxels: scan_kernel<T, false> for both label
+// widths (march, worklists, per-voxel pair phases, flush, slab ownership, ragged bricks) on the scalar staging path and on
+// the TMA staging path with the box copy itself emulated.  Test infrastructure: g++ only, no GPU, no nvcc.
 // Usage: kernel_emu_check <seed> ; exit code 0 = every case equal.
 #include "emu/cuda_emu.h"
 
@@ -11,10 +10,6 @@ static unsigned long long g_user_stat[16];
 #define TA_STAT(which, n) (g_user_stat[which] += (unsigned long long)(n))
 
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
-#include "../../tissue_analysis_b200/csrc/ta_scan_block.cuh"
-#include "../../tissue_analysis_b200/csrc/ta_scan_level.cuh"
-#include "../../tissue_analysis_b200/csrc/ta_scan_meta.cuh"
-#include "../../tissue_analysis_b200/csrc/ta_scan_rec.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
 void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
@@ -56,9 +51,8 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
-enum Which { PRODUCT, ONEHOT, BLOCK_MERGE, BLOCK_SIMPLE, LEVEL_MERGE, LEVEL_SIMPLE, META, REC, NWHICH };
-static const char* which_name[] = {"scan_kernel<T,false,false>", "scan_kernel<T,true,false>", "scan_block_kernel<T,true>",
-                                   "scan_block_kernel<T,false>", "scan_level_kernel<T,true>", "scan_level_kernel<T,false>", "scan_meta_kernel<T>", "rec_build + rec_blocks<T>"};
+enum Which { PRODUCT, NWHICH };
+static const char* which_name[] = {"scan_kernel<T,false>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -110,37 +104,18 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     const int seg = 16 / (int)sizeof(T);
     P.nbf = (nf + NFS * seg - 1) / (NFS * seg); P.nbm = (nm + BM - 1) / BM; P.nbs = (own_hi - own_lo + BS - 1) / BS;
     P.flags = 7u; P.vec_ok = 0; P.use_tma = use_tma; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
-    if (use_tma && which >= LEVEL_MERGE) P.flags |= (seed & 2u) ? 0x20000u : 0u;      // with and without the L2 prefetch (a no-op here)
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     {
         // what ta_api.cu encodes for the kernels: the bound buffer, one box = tile (brick + halo)
-        ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), (which == META ? MK_ROWV : ROWV) * seg, BM + 2, BS + 2};
+        ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), ROWV * seg, BM + 2, BS + 2};
         static_assert(sizeof(ta::EmuTmap) <= sizeof(CUtensorMap), "the emulated map lives in the bytes of the real one");
         memcpy(&tmap, &em, sizeof em);
     }
     bool ok = true;
-    if (which == REC) {
-        // the two-kernel record scan: what launch_scan of ta_api.cu does
-        RecBuf R{};
-        R.noct = (nf + 7) / 8; R.plane0 = std::max(own_lo - 1, 0); R.nplanes = std::min(own_hi + 1, nbuf) - R.plane0;
-        const size_t nrec = (size_t)R.nplanes * nm * R.noct;
-        std::vector<uint32_t> ra(nrec, 0xDEADBEEFu), rb(nrec, 0xDEADBEEFu), rq(nrec, 0xDEADBEEFu), re(nrec, 0xDEADBEEFu), re2(nrec, 0xDEADBEEFu);
-        R.a = ra.data(); R.b = rb.data(); R.q = rq.data(); R.e = re.data(); R.e2 = re2.data();
-        P.nbf = (nf + RB_BF - 1) / RB_BF;
-        const unsigned g1 = (unsigned)std::min<size_t>((nrec + 255) / 256, 3);
-        for (unsigned block = 0; block < g1 && ok; ++block) ok = emu::run_block(block, g1, 256, [&]() { rec_build_kernel<T>(P, R); });
-        for (unsigned block = 0; block < 2 && ok; ++block) ok = emu::run_block(block, 2, NTHREADS, [&]() { rec_blocks_kernel<T>(P, R, lt, pt); });
-    } else
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
         ok = emu::run_block(block, 2, NTHREADS, [&]() {
-            if (which == PRODUCT) scan_kernel<T, false, false>(P, lt, pt, tmap);
-            else if (which == ONEHOT) scan_kernel<T, true, false>(P, lt, pt, tmap);
-            else if (which == BLOCK_MERGE) scan_block_kernel<T, true>(P, lt, pt, tmap);
-            else if (which == BLOCK_SIMPLE) scan_block_kernel<T, false>(P, lt, pt, tmap);
-            else if (which == LEVEL_MERGE) scan_level_kernel<T, true>(P, lt, pt, tmap);
-            else if (which == META) scan_meta_kernel<T>(P, lt, pt, tmap);
-            else scan_level_kernel<T, false>(P, lt, pt, tmap);
+            scan_kernel<T, false>(P, lt, pt, tmap);
         });
     }
     LabelTab gotL; PairTab gotP;
@@ -199,27 +174,14 @@ static void print_stats() {
     const int ncell = (int)((double)nf * nm * nbuf / 21500.0 + 0.5);
     printf("tissue-like volume %d x %d x %d, %d cells; operations per voxel\n", nf, nm, nbuf, ncell);
     printf("%-28s %9s %9s %9s %9s %9s %9s\n", "kernel", "atom.smem", "atom.glob", "redux/w", "ballot/w", "shfl/w", "bar/blk");
-    unsigned long long level_stat[16] = {};
     for (int w = 0; w < NWHICH; ++w) {
         emu::g_stats.clear();
-        memset(g_user_stat, 0, sizeof g_user_stat);
         const int bad = run_case<uint16_t>((Which)w, nf, nm, nbuf, 0, nbuf, 0, ncell, 1, 12345u);
         const double nv = (double)nf * nm * nbuf;
         const emu::Stats& s = emu::g_stats;
         printf("%-28s %9.4f %9.4f %9.4f %9.4f %9.4f %9.5f%s\n", which_name[w], s.atom_shared / nv, s.atom_global / nv, s.redux / nv,
                s.ballot / nv, s.shfl / nv, s.syncthreads / nv, bad ? "  (MISMATCH)" : "");
-        if (w == LEVEL_MERGE) memcpy(level_stat, g_user_stat, sizeof level_stat);
     }
-    {
-        const unsigned long long* m = g_user_stat;      // the last kernel run: scan_meta_kernel
-        printf("record kernel: %llu bricks not one label, %llu blocks: %llu one label, %llu listed in %llu warp rounds; label steps: %llu warp-level "
-               "for %llu lanes; fallback blocks %llu (BAD %llu); 3+-label octs %llu\n", m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9]);
-    }
-    const unsigned long long* u = level_stat;
-    printf("level kernel, dynamic counts: %llu bricks not one label, %llu blocks: %llu one label (%.1f %%), list 2: %llu blocks in %llu warp "
-           "rounds (%.1f lanes), list 3: %llu blocks in %llu warp rounds (%.1f lanes), extension steps: %llu warp-level for %llu "
-           "blocks, fallback: %llu blocks; merge loop rounds: labels %llu, pairs %llu\n", u[0], u[1], u[2], 100.0 * u[2] / u[1],
-           u[3], u[4], (double)u[3] / u[4], u[5], u[6], (double)u[5] / (u[6] ? u[6] : 1), u[7], u[8], u[9], u[10], u[11]);
 }
 
 int main(int argc, char** argv) {

@@ -1,12 +1,11 @@
-"""The scan kernels themselves, run on the CPU (tests/host/emu/cuda_emu.h: every CUDA thread is a fiber, warp and block
+"""The scan kernel itself, run on the CPU (tests/host/emu/cuda_emu.h: every CUDA thread is a fiber, warp and block
 collectives are rendezvous points, atomics are plain) against a direct pass over the voxels.
 
-Covers the source of the product kernel scan_kernel<T, false, false> for uint16 and uint32 (march, worklists, per-voxel
-pair phases, flush, slab ownership, ragged bricks), its one-hot instantiation, the experimental block kernels and the
-level kernels (ta_scan_level.cuh), each with and without warp merges -- on the scalar staging path and on the TMA staging
-path with the box copy itself emulated (zero fill outside the buffer, re-clamping of edge tiles, the shifted tile of the
-level kernel).  g++ only.
-The GPU parity tests stay the authority for the compiled kernels; this one finds logic errors without a GPU.
+Covers the source of the product kernel scan_kernel<T, false> for uint16 and uint32 (march, worklists, per-voxel pair
+phases, flush, slab ownership, ragged bricks) on the scalar staging path and on the TMA staging path with the box copy
+itself emulated (zero fill outside the buffer, re-clamping of edge tiles; a box origin that is not 16-byte aligned
+aborts, as the hardware faults on it).  g++ only.
+The GPU parity tests stay the authority for the compiled kernel; this one finds logic errors without a GPU.
 """
 import os
 import shutil

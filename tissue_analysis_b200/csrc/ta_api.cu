@@ -13,12 +13,6 @@
 #include "ta_common.cuh"
 #include "ta_kernels.cuh"
 #include "ta_scan.cuh"
-#ifdef TA_WITH_BLOCK_KERNEL           // experimental, not part of the product build: TA_NVCC_EXTRA=-DTA_WITH_BLOCK_KERNEL
-#include "ta_scan_block.cuh"
-#include "ta_scan_level.cuh"
-#endif
-#include "ta_scan_meta.cuh"
-#include "ta_scan_rec.cuh"
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -61,8 +55,6 @@ struct ta_ctx {
     cudaEvent_t ev[6] = {};
     cudaStream_t copy_stream = nullptr;          // H2D chunks of ta_run_pass_host
     std::vector<cudaEvent_t> chunk_ev;
-    uint32_t* rec_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // record scratch of the two-kernel scan (a, b, q, e, e2)
-    size_t rec_have[5] = {0, 0, 0, 0, 0};
     float scan_ms = 0, pass_ms = 0, h2d_ms = 0;
     uint64_t launches = 0;
 };
@@ -97,16 +89,15 @@ template <typename P> static int ensure(ta_ctx* ctx, P** ptr, size_t* have, size
     return TA_OK;
 }
 
-// The scan kernel's instantiations: label width x pair path (per-voxel | one-hot, flag 0x1000) x phase clocks
-// (TA_PHASE_TIMING=1).  The product path is (width, per-voxel, no clocks).
+// The scan kernel's instantiations: label width, and -- only in a -DTA_WITH_PHASE_TIMING build -- the phase clocks
+// (TA_PHASE_TIMING=1).  The product library carries the two kernels it launches and nothing else.
 typedef void (*scan_kernel_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
-static scan_kernel_fn scan_kernel_variant(int elem, bool onehot, bool timing) {
-    if (elem == 2) {
-        if (onehot) return timing ? ta::scan_kernel<uint16_t, true, true> : ta::scan_kernel<uint16_t, true, false>;
-        return timing ? ta::scan_kernel<uint16_t, false, true> : ta::scan_kernel<uint16_t, false, false>;
-    }
-    if (onehot) return timing ? ta::scan_kernel<uint32_t, true, true> : ta::scan_kernel<uint32_t, true, false>;
-    return timing ? ta::scan_kernel<uint32_t, false, true> : ta::scan_kernel<uint32_t, false, false>;
+static scan_kernel_fn scan_kernel_variant(int elem, bool timing) {
+#ifdef TA_WITH_PHASE_TIMING
+    if (timing) return elem == 2 ? ta::scan_kernel<uint16_t, true> : ta::scan_kernel<uint32_t, true>;
+#endif
+    (void)timing;
+    return elem == 2 ? ta::scan_kernel<uint16_t, false> : ta::scan_kernel<uint32_t, false>;
 }
 
 extern "C" {
@@ -149,11 +140,10 @@ int ta_ctx_create(ta_ctx** out, int device) {
     TA_CUDA(cudaMalloc((void**)&ctx->status, 8 * sizeof(uint32_t)));
     ctx->counters = ctx->status + 4;
     for (int e = 0; e < 2; ++e)
-        for (int oh = 0; oh < 2; ++oh)
-            for (int tm = 0; tm < 2; ++tm)
-                TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, oh != 0, tm != 0),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
+        for (int tm = 0; tm < 2; ++tm)
+            TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, tm != 0),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
     *out = ctx;
     return TA_OK;
 }
@@ -169,7 +159,6 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
-    for (auto& rb : ctx->rec_buf) cudaFree(rb);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->diag_host) cudaFreeHost(ctx->diag_host);
@@ -356,75 +345,8 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     if (total == 0) return TA_OK;
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
-    const bool onehot = (P.flags & 0x1000u) && !(P.flags & 0x800u);
-    if (P.flags & 0x80000u) {
-        // the two-kernel record scan (ta_scan_rec.cuh): records of planes [own_lo - 1, own_hi], then one warp per brick
-        ta::RecBuf R{};
-        R.noct = (int)((ctx->nf + 7) / 8);
-        R.plane0 = (int)std::max<long long>(own_lo - 1, 0);
-        R.nplanes = (int)(std::min<long long>(own_hi + 1, ctx->ns) - R.plane0);
-        const size_t nrec = (size_t)R.nplanes * (size_t)ctx->nm * (size_t)R.noct;
-        if (nrec >= (1ull << 31)) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass of the record scan");
-        const int nbuf = ctx->elem == 2 ? 3 : 5;
-        const int which[5] = {0, 2, 3, 1, 4};                 // uint16 uses a, q, e
-        for (int k = 0; k < nbuf; ++k) {
-            int rc = ensure(ctx, &ctx->rec_buf[which[k]], &ctx->rec_have[which[k]], nrec);
-            if (rc) return rc;
-        }
-        R.a = ctx->rec_buf[0]; R.b = ctx->rec_buf[1]; R.q = ctx->rec_buf[2]; R.e = ctx->rec_buf[3]; R.e2 = ctx->rec_buf[4];
-        P.nbf = (int)((ctx->nf + ta::RB_BF - 1) / ta::RB_BF);
-        const size_t rtotal = (size_t)P.nbf * P.nbm * P.nbs;
-        const size_t nchunks = (size_t)R.nplanes * (size_t)ctx->nm * (size_t)((R.noct + 31) / 32);      // one warp per 32 octs of a row
-        const int g1 = (int)std::min<size_t>((nchunks + 7) / 8, (size_t)ctx->num_sms * 16);
-        const int g2 = (int)std::min<size_t>((rtotal + ta::RB_WARPS - 1) / ta::RB_WARPS, (size_t)ctx->num_sms * TA_REC_MINB);
-        if (ctx->elem == 2) {
-            ta::rec_build_kernel<uint16_t><<<g1, 256, 0, st>>>(P, R);
-            ta::rec_blocks_kernel<uint16_t><<<g2, ta::NTHREADS, 0, st>>>(P, R, ctx->lt, ctx->pt);
-        } else {
-            ta::rec_build_kernel<uint32_t><<<g1, 256, 0, st>>>(P, R);
-            ta::rec_blocks_kernel<uint32_t><<<g2, ta::NTHREADS, 0, st>>>(P, R, ctx->lt, ctx->pt);
-        }
-        ctx->launches += 2;
-        TA_CUDA(cudaGetLastError());
-        return TA_OK;
-    }
-    if (P.flags & 0x40000u) {
-        // the record kernel (ta_scan_meta.cuh)
-        typedef void (*meta_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
-        meta_fn fn = ctx->elem == 2 ? (meta_fn)ta::scan_meta_kernel<uint16_t> : (meta_fn)ta::scan_meta_kernel<uint32_t>;
-        const size_t msmem = ctx->elem == 2 ? ta::scan_meta_smem_bytes<uint16_t>() : ta::scan_meta_smem_bytes<uint32_t>();
-        TA_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-        const int mgrid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * TA_META_MINB);
-        fn<<<mgrid, ta::NTHREADS, msmem, st>>>(P, ctx->lt, ctx->pt, tmap);
-        ctx->launches++;
-        TA_CUDA(cudaGetLastError());
-        return TA_OK;
-    }
-#ifdef TA_WITH_BLOCK_KERNEL
-    if (P.flags & 0x4000u) {
-        // experimental block-bitmask kernel (ta_scan_block.cuh): only on request, configured on first use so that the
-        // product path never depends on it
-        typedef void (*block_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
-        const bool merge = !(P.flags & 0x8000u);
-        block_fn fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_block_kernel<uint16_t, true> : (block_fn)ta::scan_block_kernel<uint16_t, false>)
-                                           : (merge ? (block_fn)ta::scan_block_kernel<uint32_t, true> : (block_fn)ta::scan_block_kernel<uint32_t, false>);
-        size_t bsmem = ctx->elem == 2 ? ta::scan_block_smem_bytes<uint16_t>() : ta::scan_block_smem_bytes<uint32_t>();
-        if (P.flags & 0x10000u) {          // level formulation (ta_scan_level.cuh)
-            fn = ctx->elem == 2 ? (merge ? (block_fn)ta::scan_level_kernel<uint16_t, true> : (block_fn)ta::scan_level_kernel<uint16_t, false>)
-                                : (merge ? (block_fn)ta::scan_level_kernel<uint32_t, true> : (block_fn)ta::scan_level_kernel<uint32_t, false>);
-            bsmem = ctx->elem == 2 ? ta::scan_level_smem_bytes<uint16_t>() : ta::scan_level_smem_bytes<uint32_t>();
-        }
-        TA_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-        fn<<<grid, ta::NTHREADS, bsmem, st>>>(P, ctx->lt, ctx->pt, tmap);
-        ctx->launches++;
-        TA_CUDA(cudaGetLastError());
-        return TA_OK;
-    }
-#else
-    if (P.flags & 0x4000u) return fail(ctx, TA_ERR_BAD_ARG, "the block kernel is not compiled in (-DTA_WITH_BLOCK_KERNEL)");
-#endif
     const size_t smem = ctx->elem == 2 ? ta::scan_smem_bytes<uint16_t>() : ta::scan_smem_bytes<uint32_t>();
-    scan_kernel_variant(ctx->elem, onehot, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
+    scan_kernel_variant(ctx->elem, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     return TA_OK;
@@ -518,28 +440,17 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     }
     P.diag = ctx->diag_dev;
     P.phase_cycles = nullptr;
+#ifdef TA_WITH_PHASE_TIMING
     const bool phase_timing = getenv("TA_PHASE_TIMING") != nullptr;
+#else
+    const bool phase_timing = false;         // the product library has no kernel with phase clocks
+#endif
     if (phase_timing) {
         if (!ctx->phase_cycles) TA_CUDA(cudaMalloc((void**)&ctx->phase_cycles, 16 * sizeof(u64)));
         TA_CUDA(cudaMemsetAsync(ctx->phase_cycles, 0, 16 * sizeof(u64), st));
         P.phase_cycles = ctx->phase_cycles;
     }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
-#if defined(TA_WITH_BLOCK_KERNEL) && defined(TA_DEFAULT_LEVEL)
-    // experiment build: the level kernel unless a pass names another one (0x800 forces the product kernel)
-    if (!(P.flags & (0x800u | 0x1000u | 0x4000u))) P.flags |= 0x4000u | 0x10000u;
-#endif
-    if (const char* pp = getenv("TA_PAIR_PATH")) {       // experiments: "voxel" / "onehot" / "block" / "level" for every brick
-        if (!strcmp(pp, "voxel")) P.flags |= 0x800u;
-        else if (!strcmp(pp, "onehot")) P.flags |= 0x1000u;
-        else if (!strcmp(pp, "block")) P.flags |= 0x4000u;
-        else if (!strcmp(pp, "block_simple")) P.flags |= 0x4000u | 0x8000u;
-        else if (!strcmp(pp, "level")) P.flags |= 0x4000u | 0x10000u;
-        else if (!strcmp(pp, "level_simple")) P.flags |= 0x4000u | 0x8000u | 0x10000u;
-        else if (!strcmp(pp, "level_pf")) P.flags |= 0x4000u | 0x10000u | 0x20000u;
-        else if (!strcmp(pp, "meta")) P.flags |= 0x40000u;
-        else if (!strcmp(pp, "rec")) P.flags |= 0x80000u;
-    }
     TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {
         for (int k = 0; k < ranges->n; ++k) {
@@ -796,7 +707,7 @@ int ta_inertia_table(ta_ctx* ctx, double* evals, double* evecs) {
     cudaStream_t st = ctx->stream;
     size_t n = ctx->lt.nrows;
     if (ctx->eig_alloc_rows < n) {
-        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
+        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
         ctx->d_evals = ctx->d_evecs = nullptr; ctx->eig_alloc_rows = 0;
         TA_CUDA(cudaMalloc((void**)&ctx->d_evals, n * 3 * sizeof(double)));
         TA_CUDA(cudaMalloc((void**)&ctx->d_evecs, n * 9 * sizeof(double)));

@@ -26,16 +26,6 @@
 //      worklist and are handled with a register dedup of up to 4 labels (exact rescan beyond that).
 //   F  flush the per-brick label table (u32 brick-local sums -> shifted u64 global REDs) and pair table.
 //
-// One-hot pair path (instantiation OH = true, flag 0x1000; an experiment kept testable, not the default -- it is exact
-// but slower than C2 / D / D2 on every measured configuration):
-//   R  after the march the tile is rewritten in place: label -> one-hot word (1 << id) of a brick-local id.  Ids come
-//      from NID-slot tables (NID = bits of a label word), one per quarter of the row for uint16 so that 16 ids suffice;
-//      the two lanes either side of a quarter boundary are kept in both encodings (edge array).
-//   S  per listed segment, SIMD on the packed lanes: the OR of the 18 neighbour words is the SET of labels around
-//      each voxel (the de-duplication of the wall18 definition is the OR itself); `& ~own` leaves the other labels.
-//      Counts per (own id, other id) are sums of one bit column; they go to a direct-indexed table of packed 16-bit
-//      counters [wall18 | +f] [+m | +s] after a warp merge.  No per-voxel work, no junction special case.
-//   A quarter with more labels than ids (noise-like data): the brick is staged again and takes C2 / D / D2.
 #pragma once
 #include "ta_common.cuh"
 
@@ -167,10 +157,6 @@ template <typename T> struct BrickShared {
     unsigned short* junclist;          // [VOXLIST_CAP]
     unsigned int* ctr;                 // [0] next brick, [1] nseg, [2..3] nvox ping-pong, [4..5] njunc ping-pong,
                                        // [6..7] brick index ping-pong, [9] one-hot id table overflow
-    uint32_t* idk;                     // [NQ * NID = 64] one-hot id tables: label of id (slot index), TA_EMPTY32 when free
-    uint32_t* ohc;                     // [OH_CTR_WORDS] one-hot pair counters (quarter, own id, other id) x 2 words;
-                                       // aliases voxlist + junclist (per-voxel path only)
-    void* edg;                         // one-hot edge array (see OneHot); aliases pt_val + pt_key (per-voxel path only)
 };
 
 // ---- global flush of one label's brick-local sums -----------------------------------------------------------
@@ -497,290 +483,9 @@ __device__ __noinline__ int neighbour_offset(int k) {
     return 0;
 }
 
-// ---- one-hot pair path ------------------------------------------------------------------------------------------------
-// The segment arithmetic is host-compilable (TA_HD) so that tests/host/oh_host_check.cu can run exactly this code on the
-// CPU against a brute-force count; the kernel is the only product caller.
-#ifdef __CUDA_ARCH__
-#define TA_HD __device__ __forceinline__
-#else
-#define TA_HD __host__ __device__ inline
-#endif
-TA_HD uint32_t ta_funnel_r16(uint32_t lo, uint32_t hi) {          // (hi:lo) >> 16
-#ifdef __CUDA_ARCH__
-    return __funnelshift_r(lo, hi, 16);
-#else
-    return (hi << 16) | (lo >> 16);
-#endif
-}
-TA_HD uint32_t ta_vminu2(uint32_t a, uint32_t b) {
-#ifdef __CUDA_ARCH__
-    return __vminu2(a, b);
-#else
-    const uint32_t l = (a & 0xFFFFu) < (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
-    const uint32_t h = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
-    return l | (h << 16);
-#endif
-}
-TA_HD int ta_popc(uint32_t x) {
-#ifdef __CUDA_ARCH__
-    return __popc(x);
-#else
-    return __builtin_popcount(x);
-#endif
-}
-TA_HD int ta_ffs(uint32_t x) {
-#ifdef __CUDA_ARCH__
-    return __ffs(x);
-#else
-    return __builtin_ffs((int)x);
-#endif
-}
-
-// Brick-local label ids.  A tile row is cut into NQ groups of QS = NFS / NQ segments ("quarters" for uint16); every
-// quarter has its own NID-slot open-addressing table (id = slot index, one-hot word = 1 << id), so that NID = the bits
-// of a label word is enough for cells down to a few voxels across.  A voxel is encoded with the table of its quarter.
-// The two lanes on either side of a quarter boundary are needed by the stencil of the segment across the boundary, in
-// THAT segment's encoding: the edge array holds them (edg[(row * (NQ - 1) + (b - 1)) * 2 + side], boundary b = 1 ..
-// NQ - 1 between quarters b - 1 and b; side 0: last lane of quarter b - 1 in table b, side 1: first lane of quarter b
-// in table b - 1).
-template <typename T> struct OneHot;
-
-template <> struct OneHot<uint16_t> {
-    static constexpr int NID = 16, LOG_NID = 4, NQ = 4;
-    static constexpr uint32_t LANE1 = 0x00010001u;                 // bit 0 of every lane
-    static TA_HD uint32_t splat(uint32_t oh) { return oh * 0x00010001u; }
-    static TA_HD uint32_t fold(uint32_t x) { return (x | (x >> 16)) & 0xFFFFu; }     // ids in a word
-    static TA_HD uint32_t full(uint32_t lanebits) { return lanebits * 0xFFFFu; }     // LANE1 bits -> whole-lane masks
-    static TA_HD uint32_t lanesum(uint32_t t) { return (t + (t >> 16)) & 0xFFFFu; }  // sum of the lanes of a word
-    // 0xFFFF in every lane of c that equals the lane of pat
-    static TA_HD uint32_t eqmask(uint32_t c, uint32_t pat) {
-        return (ta_vminu2(c ^ pat, 0x00010001u) ^ 0x00010001u) * 0xFFFFu;
-    }
-    // whole-lane mask of lanes [j0, j1) restricted to word w
-    static TA_HD uint32_t lane_range(int w, int j0, int j1) {
-        return ((2 * w >= j0 && 2 * w < j1) ? 0xFFFFu : 0u) | ((2 * w + 1 >= j0 && 2 * w + 1 < j1) ? 0xFFFF0000u : 0u);
-    }
-    static TA_HD uint32_t run_breaks(const uint4& C) {             // bit j <=> lane j differs from lane j + 1 (j < 7)
-        const uint32_t d0 = C.x ^ ta_funnel_r16(C.x, C.y), d1 = C.y ^ ta_funnel_r16(C.y, C.z),
-                       d2 = C.z ^ ta_funnel_r16(C.z, C.w), d3 = (C.w ^ (C.w >> 16)) & 0xFFFFu;
-        const uint32_t one = 0x00010001u;
-        const uint32_t tt = ta_vminu2(d0, one) | (ta_vminu2(d1, one) << 2) | (ta_vminu2(d2, one) << 4) |
-                            (ta_vminu2(d3, one) << 6);
-        return ((tt & 0x55u) | ((tt >> 15) & 0xAAu)) & 0x7Fu;
-    }
-};
-template <> struct OneHot<uint32_t> {
-    static constexpr int NID = 32, LOG_NID = 5, NQ = 1;
-    static constexpr uint32_t LANE1 = 1u;
-    static TA_HD uint32_t splat(uint32_t oh) { return oh; }
-    static TA_HD uint32_t fold(uint32_t x) { return x; }
-    static TA_HD uint32_t full(uint32_t lanebits) { return 0u - lanebits; }
-    static TA_HD uint32_t lanesum(uint32_t t) { return t; }
-    static TA_HD uint32_t eqmask(uint32_t c, uint32_t pat) { return c == pat ? 0xFFFFFFFFu : 0u; }
-    static TA_HD uint32_t lane_range(int w, int j0, int j1) { return (w >= j0 && w < j1) ? 0xFFFFFFFFu : 0u; }
-    static TA_HD uint32_t run_breaks(const uint4& C) {
-        return (C.x != C.y ? 1u : 0u) | (C.y != C.z ? 2u : 0u) | (C.z != C.w ? 4u : 0u);
-    }
-};
-constexpr int OH_CTR_WORDS = 2048;      // NQ * NID * NID * 2 for both label widths
-
-// find-or-insert label L in one quarter's table; the slot index is the id.  -1: table full.
-template <typename T>
-TA_HD int oh_insert(uint32_t* idk, uint32_t L) {
-    constexpr int NID = OneHot<T>::NID;
-    uint32_t slot = (L * 0x9E3779B1u) >> (32 - OneHot<T>::LOG_NID);
-    for (int probe = 0; probe < NID; ++probe) {
-#ifdef __CUDA_ARCH__
-        const uint32_t k = *((volatile uint32_t*)&idk[slot]);
-        if (k == L) return (int)slot;
-        if (k == TA_EMPTY32) {
-            const uint32_t old = atomicCAS(&idk[slot], TA_EMPTY32, L);
-            if (old == TA_EMPTY32 || old == L) return (int)slot;
-        }
-#else
-        if (idk[slot] == L) return (int)slot;
-        if (idk[slot] == TA_EMPTY32) { idk[slot] = L; return (int)slot; }
-#endif
-        slot = (slot + 1) & (NID - 1);
-    }
-    return -1;
-}
-
-// Phase R for one segment (row r, segment fs) of the tile: labels -> one-hot words of the quarter's ids, in place, plus
-// the encodings of its boundary lanes that the neighbouring quarter / the f-halo need.  Only the segment's own lanes
-// (and, for the first / last segment of a row, the f-halo lane beside it) are read, so all segments can be rewritten
-// concurrently.  `code`: the uniformity code of phase B.  false: some table is full (the tile is then unusable for
-// both pair paths and has to be staged again).
-template <typename T>
-TA_HD bool oh_relabel_segment(uint4* tile, T* edg, uint32_t* idk, int r, int fs, uint32_t code, uint32_t& lastL,
-                              uint32_t& lastQ, uint32_t& lastOH) {
-    constexpr int SEG = Vox<T>::SEG;
-    constexpr int NID = OneHot<T>::NID, NQ = OneHot<T>::NQ, QS = NFS / NQ;
-    constexpr int ROWE = ROWV * SEG;
-    const uint32_t q = (uint32_t)(fs / QS);
-    bool ok = true;
-    auto enc = [&](uint32_t qq, uint32_t L) -> uint32_t {          // one-hot of L in quarter qq (one-entry cache)
-        if (L == lastL && qq == lastQ) return lastOH;
-        const int slot = oh_insert<T>(idk + qq * NID, L);
-        if (slot < 0) { ok = false; return 0u; }
-        lastL = L; lastQ = qq; lastOH = 1u << slot;
-        return lastOH;
-    };
-    uint4* seg = tile + r * ROWV + fs + 1;
-    T* rp = reinterpret_cast<T*>(tile) + r * ROWE + (fs + 1) * SEG;
-    uint32_t first, last;                                           // labels of lane 0 and lane SEG - 1
-    if (code != Vox<T>::MIXED) {
-        const uint32_t w = OneHot<T>::splat(enc(q, code));
-        first = last = code;
-        if (fs == 0) rp[-1] = (T)lastOH;                            // code != MIXED: the f-halo lanes carry the same label
-        if (fs == NFS - 1) rp[SEG] = (T)lastOH;
-        *seg = make_uint4(w, w, w, w);
-    } else {
-        const uint4 v = *seg;
-        uint32_t brk = OneHot<T>::run_breaks(v);
-        uint32_t out[4] = {0u, 0u, 0u, 0u};
-        first = rp[0]; last = rp[SEG - 1];
-        const uint32_t hl = (fs == 0) ? (uint32_t)rp[-1] : 0u, hr = (fs == NFS - 1) ? (uint32_t)rp[SEG] : 0u;
-        int j0 = 0;
-        while (j0 < SEG) {
-            const uint32_t rest = brk >> j0;
-            const int j1 = rest ? j0 + ta_ffs(rest) : SEG;
-            const uint32_t w = OneHot<T>::splat(enc(q, rp[j0]));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] |= w & OneHot<T>::lane_range(k, j0, j1);
-            j0 = j1;
-        }
-        if (fs == 0) rp[-1] = (T)enc(q, hl);
-        if (fs == NFS - 1) rp[SEG] = (T)enc(q, hr);
-        *seg = make_uint4(out[0], out[1], out[2], out[3]);
-    }
-    if (NQ > 1) {
-        const int b0 = fs / QS, pos = fs % QS;
-        if (pos == 0 && b0 > 0) edg[(r * (NQ - 1) + (b0 - 1)) * 2 + 1] = (T)enc(q - 1, first);
-        if (pos == QS - 1 && b0 < NQ - 1) edg[(r * (NQ - 1) + b0) * 2 + 0] = (T)enc(q + 1, last);
-    }
-    return ok;
-}
-
-// One listed segment (row r of the tile, segment fs) of the one-hot tile: C = own words; oth = labels in the
-// 18-neighbourhood other than the own one; xf / xm / xs = the +f / +m / +s neighbour's word where it differs from the
-// own one (else 0).  The lanes beside the segment come from the tile or, across a quarter boundary, from the edge array.
-template <typename T>
-TA_HD void oh_stencil(const uint4* tile, const T* edg, int r, int fs, uint32_t C[4], uint32_t oth[4], uint32_t xf[4],
-                      uint32_t xm[4], uint32_t xs[4]) {
-    constexpr int SEG = Vox<T>::SEG;
-    constexpr int NQ = OneHot<T>::NQ, QS = NFS / NQ;
-    constexpr int ROWE = ROWV * SEG, PLANEE = (BM + 2) * ROWE;
-    constexpr int EROW = (NQ - 1) * 2, EPLANE = (BM + 2) * EROW;
-    const int t = r * ROWV + fs + 1;
-    const uint4 c = tile[t];
-    const uint4 m0 = tile[t - ROWV], m1 = tile[t + ROWV], s0 = tile[t - PLANEV], s1 = tile[t + PLANEV];
-    const uint4 d0 = tile[t - PLANEV - ROWV], d1 = tile[t - PLANEV + ROWV], d2 = tile[t + PLANEV - ROWV],
-                d3 = tile[t + PLANEV + ROWV];
-    const T* e = reinterpret_cast<const T*>(tile + t);
-    const T* pl = e - 1;
-    const T* pr = e + SEG;
-    int lrow = ROWE, lplane = PLANEE, rrow = ROWE, rplane = PLANEE;
-    if (NQ > 1) {
-        const int b0 = fs / QS, pos = fs % QS;
-        if (pos == 0 && b0 > 0) { pl = edg + (r * (NQ - 1) + (b0 - 1)) * 2 + 0; lrow = EROW; lplane = EPLANE; }
-        if (pos == QS - 1 && b0 < NQ - 1) { pr = edg + (r * (NQ - 1) + b0) * 2 + 1; rrow = EROW; rplane = EPLANE; }
-    }
-    const uint32_t cR = pr[0];
-    const uint32_t yL = (uint32_t)pl[0] | pl[-lrow] | pl[lrow] | pl[-lplane] | pl[lplane];
-    const uint32_t yR = cR | pr[-rrow] | pr[rrow] | pr[-rplane] | pr[rplane];
-    C[0] = c.x; C[1] = c.y; C[2] = c.z; C[3] = c.w;
-    const uint32_t X[4] = {m0.x | m1.x | s0.x | s1.x, m0.y | m1.y | s0.y | s1.y, m0.z | m1.z | s0.z | s1.z,
-                           m0.w | m1.w | s0.w | s1.w};
-    const uint32_t D[4] = {d0.x | d1.x | d2.x | d3.x, d0.y | d1.y | d2.y | d3.y, d0.z | d1.z | d2.z | d3.z,
-                           d0.w | d1.w | d2.w | d3.w};
-    const uint32_t Y[4] = {C[0] | X[0], C[1] | X[1], C[2] | X[2], C[3] | X[3]};   // rows whose f-shifts count
-    uint32_t nxt[4];                                                             // centre row shifted by +f
-    if (SEG == 8) {
-        const uint32_t h0 = ta_funnel_r16(yL << 16, Y[0]), h1 = ta_funnel_r16(Y[0], Y[1]),
-                       h2 = ta_funnel_r16(Y[1], Y[2]), h3 = ta_funnel_r16(Y[2], Y[3]),
-                       h4 = ta_funnel_r16(Y[3], yR);
-        oth[0] = (h0 | h1 | X[0] | D[0]) & ~C[0];
-        oth[1] = (h1 | h2 | X[1] | D[1]) & ~C[1];
-        oth[2] = (h2 | h3 | X[2] | D[2]) & ~C[2];
-        oth[3] = (h3 | h4 | X[3] | D[3]) & ~C[3];
-        nxt[0] = ta_funnel_r16(C[0], C[1]); nxt[1] = ta_funnel_r16(C[1], C[2]);
-        nxt[2] = ta_funnel_r16(C[2], C[3]); nxt[3] = ta_funnel_r16(C[3], cR);
-    } else {
-        oth[0] = (yL | Y[1] | X[0] | D[0]) & ~C[0];
-        oth[1] = (Y[0] | Y[2] | X[1] | D[1]) & ~C[1];
-        oth[2] = (Y[1] | Y[3] | X[2] | D[2]) & ~C[2];
-        oth[3] = (Y[2] | yR | X[3] | D[3]) & ~C[3];
-        nxt[0] = C[1]; nxt[1] = C[2]; nxt[2] = C[3]; nxt[3] = cR;
-    }
-    xf[0] = nxt[0] & ~C[0]; xf[1] = nxt[1] & ~C[1]; xf[2] = nxt[2] & ~C[2]; xf[3] = nxt[3] & ~C[3];
-    xm[0] = m1.x & ~C[0]; xm[1] = m1.y & ~C[1]; xm[2] = m1.z & ~C[2]; xm[3] = m1.w & ~C[3];
-    xs[0] = s1.x & ~C[0]; xs[1] = s1.y & ~C[1]; xs[2] = s1.z & ~C[2]; xs[3] = s1.w & ~C[3];
-}
-
-// number of lanes (of the four words) whose bit j is set
-template <typename T>
-TA_HD uint32_t oh_column_count(const uint32_t o[4], uint32_t j) {
-    constexpr uint32_t L1 = OneHot<T>::LANE1;
-    return OneHot<T>::lanesum(((o[0] >> j) & L1) + ((o[1] >> j) & L1) + ((o[2] >> j) & L1) + ((o[3] >> j) & L1));
-}
-
-// Every (own id i, other id j) contribution of one listed segment, `left` voxels of it inside the volume:
-// emit((quarter * NID + i) * NID + j, [wall18 | +f faces], [+m faces | +s faces]) as seen from the voxels of label i.
-// The loop runs over the OTHER labels j (one or two per wall segment); the lanes that see j almost always carry one
-// own label, so there is no loop over own labels on the common path.
-template <typename T, typename Emit>
-TA_HD void oh_segment_pairs(const uint4* tile, const T* edg, int r, int fs, int left, uint32_t keep0, bool do_p6,
-                            Emit&& emit) {
-    constexpr int SEG = Vox<T>::SEG;
-    constexpr int NID = OneHot<T>::NID, QS = NFS / OneHot<T>::NQ;
-    constexpr uint32_t L1 = OneHot<T>::LANE1;
-    uint32_t C[4], oth[4], xf[4], xm[4], xs[4];
-    oh_stencil<T>(tile, edg, r, fs, C, oth, xf, xm, xs);
-    if (left < SEG) {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t vm = OneHot<T>::lane_range(w, 0, left);
-            C[w] &= vm; oth[w] &= vm; xf[w] &= vm; xm[w] &= vm; xs[w] &= vm;
-        }
-    }
-    uint32_t J = OneHot<T>::fold(oth[0] | oth[1] | oth[2] | oth[3]);
-    const uint32_t kbase = (uint32_t)(fs / QS) * NID;
-    while (J) {
-        const uint32_t j = ta_ffs(J) - 1;
-        J &= J - 1u;
-        // lanes that have label j around them, as whole-lane masks
-        const uint32_t l0 = OneHot<T>::full((oth[0] >> j) & L1), l1 = OneHot<T>::full((oth[1] >> j) & L1),
-                       l2 = OneHot<T>::full((oth[2] >> j) & L1), l3 = OneHot<T>::full((oth[3] >> j) & L1);
-        uint32_t own = OneHot<T>::fold((C[0] & l0) | (C[1] & l1) | (C[2] & l2) | (C[3] & l3));
-        if ((own & (own - 1u)) == 0u) {
-            const uint32_t i = ta_ffs(own) - 1;
-            const uint32_t c0 = (oh_column_count<T>(oth, j) | (oh_column_count<T>(xf, j) << 16)) & keep0;
-            const uint32_t c1 = do_p6 ? (oh_column_count<T>(xm, j) | (oh_column_count<T>(xs, j) << 16)) : 0u;
-            emit((kbase + i) * NID + j, c0, c1);
-        } else {
-            while (own) {                                           // lanes of several own labels see j (rare)
-                const uint32_t i = ta_ffs(own) - 1;
-                own &= own - 1u;
-                const uint32_t pat = OneHot<T>::splat(1u << i);
-                uint32_t o[4], f[4], mm[4], ss[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t M = OneHot<T>::eqmask(C[w], pat);
-                    o[w] = oth[w] & M; f[w] = xf[w] & M; mm[w] = xm[w] & M; ss[w] = xs[w] & M;
-                }
-                const uint32_t c0 = (oh_column_count<T>(o, j) | (oh_column_count<T>(f, j) << 16)) & keep0;
-                const uint32_t c1 = do_p6 ? (oh_column_count<T>(mm, j) | (oh_column_count<T>(ss, j) << 16)) : 0u;
-                emit((kbase + i) * NID + j, c0, c1);
-            }
-        }
-    }
-}
-
-// OH: compile the one-hot pair path (phases R + S) in.  The product launches OH = false (per-voxel pair path only, the
-// faster one on every measured configuration) unless flag 0x1000 asks for the one-hot path.
-// TIMING: compile the per-phase clocks in (profiling aid, TA_PHASE_TIMING=1).  The product kernel carries none of it.
-template <typename T, bool OH, bool TIMING>
+// TIMING: compile the per-phase clocks in (profiling aid of a -DTA_WITH_PHASE_TIMING build, TA_PHASE_TIMING=1).  The
+// product kernel carries none of it.
+template <typename T, bool TIMING>
 __global__ void __launch_bounds__(NTHREADS, 3)
 scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::Code Code;
@@ -800,19 +505,10 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
     sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
     sh.ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
-    sh.idk = reinterpret_cast<uint32_t*>(sh.ctr + 16);
-    sh.codes = reinterpret_cast<Code*>(sh.idk + 64);
+    sh.codes = reinterpret_cast<Code*>(sh.ctr + 16 + 64);
     sh.seglist = reinterpret_cast<unsigned short*>(sh.codes + TILE_ROWS * NFS);
     sh.voxlist = sh.seglist + SEGLIST_CAP;
     sh.junclist = sh.voxlist + VOXLIST_CAP;
-    sh.ohc = reinterpret_cast<uint32_t*>(sh.voxlist);
-    sh.edg = sh.pt_val;
-    constexpr int NID = OneHot<T>::NID, NQ = OneHot<T>::NQ;
-    static_assert(NQ * NID * NID * 2 == OH_CTR_WORDS && OH_CTR_WORDS * 4 <= 2 * VOXLIST_CAP * 2,
-                  "one-hot counters must fit the two voxel worklists");
-    static_assert(NQ * NID <= 64, "id tables");
-    static_assert(TILE_ROWS * (NQ - 1) * 2 * sizeof(T) <= PT_SLOTS * PT_WORDS * 4 + PT_SLOTS * sizeof(PKey),
-                  "edge array must fit the per-brick pair table");
     const T* tileT = reinterpret_cast<const T*>(sh.tile);
 
     const int tid = threadIdx.x;
@@ -821,8 +517,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
     const bool do_pairs = do_p6 || do_w18;
-    // Pair path: per-voxel (C2 / D / D2) or, in the OH instantiation, one-hot (R + S).  Both are exact.
-    const bool oh_enabled = OH && do_pairs && !(P.flags & 0x800u);
     const int nf = (int)P.nf, nm = (int)P.nm, ns = (int)P.ns;
 
     // reset the per-brick tables once; the flush at the end of each brick re-arms them
@@ -862,7 +556,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             sh.ctr[6 + ((iter + 1u) & 1u)] = atomicAdd(P.brick_counter, 1u);
             sh.ctr[1] = 0u; sh.ctr[2] = 0u; sh.ctr[3] = 0u; sh.ctr[4] = 0u; sh.ctr[5] = 0u; sh.ctr[9] = 0u;
         }
-        if (tid < 64) sh.idk[tid] = TA_EMPTY32;
         TA_TICK(0);
         const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
         const int F0 = bf * BF, M0 = bm * BM, S0 = (int)P.own_lo + bs * BS;
@@ -1102,80 +795,8 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         __syncthreads();
         TA_TICK(3);
 
-        // ---- one-hot pair path: phases R + S -----------------------------------------------------------------------------
-        bool use_oh = oh_enabled && (sh.ctr[1] != 0u);      // uniform over the CTA (ctr[1] is final since the barrier)
-        if (use_oh) {
-            const int nseg = (int)sh.ctr[1];
-            T* edg = reinterpret_cast<T*>(sh.edg);
-            for (int i = tid; i < OH_CTR_WORDS; i += NTHREADS) sh.ohc[i] = 0u;
-            // R: rewrite the tile in place, label -> one-hot word of its id in the quarter's table
-            {
-                uint32_t lastL = TA_EMPTY32, lastQ = 0u, lastOH = 0u;
-                bool ok = true;
-                for (int i = tid; i < TILE_ROWS * NFS; i += NTHREADS)
-                    ok = oh_relabel_segment<T>(sh.tile, edg, sh.idk, i / NFS, i % NFS, sh.codes[i], lastL, lastQ, lastOH) && ok;
-                if (!ok) sh.ctr[9] = 1u;
-            }
-            __syncthreads();
-            TA_TICK(8);
-            if (sh.ctr[9] != 0u) {
-                // a quarter holds more than NID labels (noise-like data): the tile is half rewritten, stage it again and
-                // take the per-voxel path.  The edge array lies in the per-brick pair table: re-arm that.
-                use_oh = false;
-                for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
-                for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
-                stage_tile();
-                __syncthreads();
-            }
-        }
-        if (TIMING && tid == 0 && do_pairs && P.phase_cycles) atomicAdd(&P.phase_cycles[use_oh ? 12 : 13], 1ull);   // bricks per path
-        if (use_oh) {
-            const int nseg = (int)sh.ctr[1];
-            const T* edg = reinterpret_cast<const T*>(sh.edg);
-            // S: listed segments.  Per (quarter, own id i, other id j): [wall18 | +f faces] [+m faces | +s faces] as seen
-            // from the voxels of label i.
-            const uint32_t keep0 = (do_w18 ? 0xFFFFu : 0u) | (do_p6 ? 0xFFFF0000u : 0u);
-            for (int base = 0; base < nseg; base += NTHREADS) {
-                const int idx = base + tid;
-                uint32_t key0 = TA_EMPTY32, a0 = 0u, a1 = 0u;
-                if (idx < nseg) {
-                    const uint32_t id = sh.seglist[idx];
-                    const int fs = id % NFS, m = (id / NFS) % BM, s = id / (NFS * BM);
-                    oh_segment_pairs<T>(sh.tile, edg, (s + 1) * (BM + 2) + (m + 1), fs, nf - (F0 + fs * SEG), keep0, do_p6,
-                        [&](uint32_t key, uint32_t c0, uint32_t c1) {
-                            if (key0 == TA_EMPTY32) { key0 = key; a0 = c0; a1 = c1; }    // first one: through the warp merge
-                            else {
-                                if (c0) atomicAdd(&sh.ohc[2 * key], c0);
-                                if (c1) atomicAdd(&sh.ohc[2 * key + 1], c1);
-                            }
-                        });
-                }
-                // one shared-counter update per distinct (own, other) in the warp: uniform loop, full-mask redux
-                {
-                    unsigned pending = __ballot_sync(0xffffffffu, key0 != TA_EMPTY32);
-                    uint32_t t0 = 0u, t1 = 0u;
-                    bool am_leader = false;
-                    while (pending) {
-                        const int leader = __ffs(pending) - 1;
-                        const uint32_t kk = __shfl_sync(0xffffffffu, key0, leader);
-                        const bool mine = (key0 == kk);
-                        const uint32_t r0 = __reduce_add_sync(0xffffffffu, mine ? a0 : 0u);
-                        const uint32_t r1 = __reduce_add_sync(0xffffffffu, mine ? a1 : 0u);
-                        if (lane == leader) { t0 = r0; t1 = r1; am_leader = true; }
-                        pending &= ~__ballot_sync(0xffffffffu, mine);
-                    }
-                    if (am_leader) {
-                        if (t0) atomicAdd(&sh.ohc[2 * key0], t0);
-                        if (t1) atomicAdd(&sh.ohc[2 * key0 + 1], t1);
-                    }
-                }
-            }
-            __syncthreads();
-            TA_TICK(9);
-        }
-
-        // ---- phases C2 + D in rounds of NTHREADS listed segments (bricks with more than NID labels) ------------------
-        if (do_pairs && !use_oh) {
+        // ---- phases C2 + D in rounds of NTHREADS listed segments ---------------------------------------------------------
+        if (do_pairs) {
             const int nseg = (int)sh.ctr[1];
             for (int base = 0, round = 0; base < nseg; base += NTHREADS, ++round) {
                 unsigned int* nvox = &sh.ctr[2 + (round & 1)];
@@ -1374,7 +995,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 sh.lt_key[i] = TA_EMPTY32;
             }
             for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
-                if (use_oh) break;             // the per-brick pair table held the one-hot edge array: re-armed below
                 PKey key = sh.pt_key[i];
                 if (key == Vox<T>::PEMPTY) continue;
                 uint32_t* d = &sh.pt_val[i * PT_WORDS];
@@ -1387,35 +1007,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
 #pragma unroll
                 for (int w = 0; w < PT_WORDS; ++w) d[w] = 0u;
                 sh.pt_key[i] = Vox<T>::PEMPTY;
-            }
-            if (use_oh) {
-                if (NQ > 1) {
-                    for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
-                    for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
-                }
-                // one-hot counters: entries (q, i, j) and (q, j, i) belong to the same label pair
-                for (int e = tid; e < NQ * NID * NID; e += NTHREADS) {
-                    const int q = e / (NID * NID), i = (e / NID) % NID, j = e % NID;
-                    if (i >= j) continue;
-                    const uint32_t* cij = &sh.ohc[2 * ((q * NID + i) * NID + j)];
-                    const uint32_t* cji = &sh.ohc[2 * ((q * NID + j) * NID + i)];
-                    const uint32_t p0 = cij[0], p1 = cij[1], q0 = cji[0], q1 = cji[1];
-                    if (!(p0 | p1 | q0 | q1)) continue;
-                    const uint32_t La = sh.idk[q * NID + i], Lb = sh.idk[q * NID + j];
-                    const int slot = ta_pair_slot(pt, ta_pair_key(La, Lb));
-                    if (slot < 0) continue;
-                    uint32_t* v = &pt.vals[(size_t)slot * TA_PAIR_STRIDE];
-                    // a face seen from its lower-index voxel: slot 2a when that voxel carries the smaller label
-                    const int lo = La < Lb ? 0 : 1;
-                    const uint32_t w18 = (p0 & 0xFFFFu) + (q0 & 0xFFFFu);
-                    if (w18) atomicAdd(&v[6], w18);
-                    if (p0 >> 16) atomicAdd(&v[0 + lo], p0 >> 16);
-                    if (q0 >> 16) atomicAdd(&v[1 - lo], q0 >> 16);
-                    if (p1 & 0xFFFFu) atomicAdd(&v[2 + lo], p1 & 0xFFFFu);
-                    if (q1 & 0xFFFFu) atomicAdd(&v[3 - lo], q1 & 0xFFFFu);
-                    if (p1 >> 16) atomicAdd(&v[4 + lo], p1 >> 16);
-                    if (q1 >> 16) atomicAdd(&v[5 - lo], q1 >> 16);
-                }
             }
         }
         __syncthreads();
