@@ -5,15 +5,21 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one full feature pass (moments + bbox, 6-face counts, 18-connected wall-voxel counts, pair-table
-compaction + sort, inertia eigen-solve for every label) over one synthetic Voronoi tissue.
+compaction, inertia eigen-solve for every label) over one synthetic Voronoi tissue.
   N = 1   workload C3: 1024^3 uint16, 50 000 seeds, dome, background 1 (north_star's target configuration).
-  N > 1   the same volume z-slab sharded over N ranks (halo exchange + all_reduce + all_gather inside the
-          timed step): total work fixed -> "scaling": "strong".
+  N > 1   the same volume z-slab sharded over N ranks (halo exchange + all_reduce + all_gather + merge inside the
+          timed step): total work fixed -> "scaling": "strong".  Outside the timed region rank 0 scans the whole volume
+          alone and compares a digest of the merged tables with it ("parity"); a mismatch ends the run with exit code 3.
 `value`   device-resident volume, tables left on the device (CUDA events on the launching stream).
-`e2e`     host (pinned) volume -> C ABI: H2D copy + pass + D2H of both tables, every step.
-`--impl reference`  the CPU restatement of the reference's own per-label loops (oracle/sia_loops.py; the
-          reference is Python 2 + openalea and cannot run here) on bounded crops of the same volume, one
-          process per host core.
+`e2e`     host (pinned) volume -> tables in host memory, every step: N = 1 through ta_run_pass_host (chunked H2D
+          overlapped with the scan) + ta_fetch_*; N > 1 every rank uploads its slab, the sharded step runs including the
+          cross-rank merge, rank 0 fetches the merged tables.
+`api_e2e` (N = 1) what a user of the drop-in class waits for: pageable numpy volume -> SpatialImageAnalysis3D ->
+          graph_arrays / the reference's dict-returning methods, wall clock.
+`--impl reference`  the reference's OWN SpatialImageAnalysis3D (oracle/_ref/vplants_ref, the mechanical py3 rewrite that
+          oracle/make_ref.py makes of /root/reference; oracle/sia_loops.py if that module was not built) on bounded
+          crops of the same workload, one process per host core.  The crops are generated on the CPU: this arm loads
+          neither the product library nor CUDA.
 """
 import argparse
 import json
@@ -109,23 +115,43 @@ def _crop_origin(shape_zyx, edge, k):
     return z0, y0, x0
 
 
+def _reference_factory():
+    """-> (make(crop_xyz, voxelsize) -> analysis object, kind).  The reference itself when oracle/_ref holds it."""
+    try:
+        from oracle import make_ref, ref_stubs
+        ref = make_ref.load()
+    except Exception:
+        ref = None
+    if ref is not None:
+        def make(crop, voxelsize):
+            return ref.SpatialImageAnalysis3D(ref_stubs.SpatialImage(crop, voxelsize=voxelsize), background=1)
+        return make, "reference"
+    from oracle.sia_loops import LoopOracle
+
+    def make(crop, voxelsize):
+        return LoopOracle(crop, background=1, voxelsize=voxelsize)
+    return make, "port"
+
+
 def _reference_pass(crop_xyz, voxelsize):
-    """The reference's feature pass, per-label loops and all (oracle/sia_loops.py), as graph_from_image drives it
+    """The reference's feature pass, per-label loops and all, as graph_from_image drives it
     (temporal_graph_from_image.py:109-212): labels, neighbors, boundingbox, volume, center_of_mass, background
-    neighbours / L1, stack margins, inertia_axis, wall_areas, wall voxel counts per pair."""
+    neighbours / L1, stack margins, inertia_axis, wall_areas, wall voxels per pair."""
     import io
     import contextlib
     import warnings
-    from oracle.sia_loops import LoopOracle
+    make, _ = _reference_factory()
     with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
         warnings.simplefilter("ignore")
-        o = LoopOracle(crop_xyz, background=1, voxelsize=voxelsize)
+        o = make(crop_xyz, voxelsize)
         labels = o.labels()
+        if len(labels) == 0:              # a crop of pure background: the reference's inertia_axis indexes an empty list
+            return 0
         nb = o.neighbors()
         o.boundingbox()
         o.volume()
         o.center_of_mass()
-        if 1 in o._neighbors and len(nb[1]):
+        if 1 in nb and len(nb[1]):
             o.cell_first_layer()
         o.labels_at_stack_margins()
         o.inertia_axis()
@@ -135,45 +161,69 @@ def _reference_pass(crop_xyz, voxelsize):
 
 
 def _reference_worker(args):
-    vol_path, shape_zyx, dtype, edge, k, voxelsize = args
-    vol = np.load(vol_path, mmap_mode="r")
+    cfg_name, vol_path, edge, k = args
+    cfg = CONFIGS[cfg_name]
+    X, Y, Z = cfg["shape"]
+    shape_zyx = (Z, Y, X)
     z0, y0, x0 = _crop_origin(shape_zyx, edge, k)
-    crop = np.ascontiguousarray(vol[z0:z0 + edge, y0:y0 + edge, x0:x0 + edge]).transpose(2, 1, 0)
+    e = [min(edge, s) for s in shape_zyx]
+    if vol_path:
+        vol = np.load(vol_path, mmap_mode="r")
+        crop = np.ascontiguousarray(vol[z0:z0 + e[0], y0:y0 + e[1], x0:x0 + e[2]])
+    else:
+        # CPU generator, this box only (bit-identical to the device generator: tests/test_gpu_parity.py)
+        from tissue_analysis_b200.synth import voronoi_numpy_box
+        crop = voronoi_numpy_box(shape_zyx, cfg["ncell"], cfg["seed"], (z0, y0, x0), (z0 + e[0], y0 + e[1], x0 + e[2]),
+                                 cfg["weights"][::-1], cfg["dome"], np.dtype(cfg["dtype"]))
+    crop = crop.transpose(2, 1, 0)
     t0 = time.perf_counter()
-    nl = _reference_pass(crop, voxelsize)
+    nl = _reference_pass(crop, cfg["voxelsize"])
     return crop.size, time.perf_counter() - t0, nl
 
 
-def run_reference_sample(vol_zyx, voxelsize, edge, nproc, steps=1, warmup=0):
-    """-> (Gvoxel/s, seconds per step, description).  Each step: `nproc` processes, one crop each."""
+def run_reference_sample(cfg_name, edge, nproc, steps=1, warmup=0, vol_zyx=None):
+    """-> (Gvoxel/s, seconds per step, description, kind).  Each step: `nproc` processes, one crop each; the timed part of
+    a worker is the feature pass alone (crop generation / loading is outside it)."""
     import multiprocessing as mp
     import tempfile
-    tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
-    tmp.close()
-    np.save(tmp.name, vol_zyx)
+    path = None
+    if vol_zyx is not None:
+        tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
+        tmp.close()
+        np.save(tmp.name, vol_zyx)
+        path = tmp.name
+    kind = _reference_factory()[1]
     ctx = mp.get_context("fork")
-    times, vox = [], 0
+    rates = []
     try:
         with ctx.Pool(nproc) as pool:
             for it in range(warmup + steps):
-                jobs = [(tmp.name, vol_zyx.shape, str(vol_zyx.dtype), edge, it * nproc + k, voxelsize)
-                        for k in range(nproc)]
-                t0 = time.perf_counter()
+                jobs = [(cfg_name, path, edge, it * nproc + k) for k in range(nproc)]
                 res = pool.map(_reference_worker, jobs)
-                dt = time.perf_counter() - t0
                 if it >= warmup:
-                    times.append(dt)
-                    vox = sum(r[0] for r in res)
+                    # the processes run side by side: the step takes as long as its slowest pass
+                    rates.append((sum(r[0] for r in res), max(r[1] for r in res)))
     finally:
-        os.unlink(tmp.name)
-    sec = float(np.mean(times))
-    desc = ("%d crops of %d^3 voxels of the workload volume per step (one per process, %d processes), full feature "
-            "pass by oracle/sia_loops.py (py3 restatement of the reference's scipy.ndimage per-label loops)"
-            % (nproc, edge, nproc))
-    return vox / sec / 1e9, sec, desc
+        if path:
+            os.unlink(path)
+    vox = float(np.mean([r[0] for r in rates]))
+    sec = float(np.mean([r[1] for r in rates]))
+    desc = ("%d crops of %d^3 voxels of the workload volume per step (one per process, %d processes), full feature pass by %s"
+            % (nproc, edge, nproc, "the reference's own SpatialImageAnalysis3D (oracle/_ref, py3 rewrite by oracle/make_ref.py)"
+               if kind == "reference" else "oracle/sia_loops.py (py3 restatement of the reference's per-label loops)"))
+    return vox / sec / 1e9, sec, desc, kind
 
 
 # ------------------------------------------------------------------------------------------------ main
+def tables_digest(count, s1, s2, bbox, lo, hi, faces, wall):
+    """Order-independent fingerprint of a pair of result tables (the pair rows are sorted by (lo, hi) already)."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in (count, s1, s2, bbox, lo, hi, faces, wall):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,7 +234,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="edge of the CPU baseline crops (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip api_e2e and the C2 / C4 scan times (N = 1)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the merged == single-GPU check")
     ap.add_argument("--equal-planes", action="store_true", help="N > 1: slabs of equal height instead of equal work")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: scan the interior planes during the halo exchange")
+    ap.add_argument("--sync-merge", action="store_true", help="N > 1: the synchronous merge in every step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -201,34 +255,25 @@ def main():
         args.config, X, Y, Z, cfg["dtype"], cfg["ncell"], "dome + background 1" if cfg["dome"] else "no background",
         cfg["seed"])
 
-    import torch
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: the whole run (steps + warmup) should end within a few minutes at ~0.3 Mvoxel/s/process
+        # bounded sample: the whole run (steps + warmup) should end within a few minutes at ~0.3 Mvoxel/s/process.  No CUDA,
+        # no product library in this process: the crops come from the CPU generator.
         edge = args.cpu_sample or (128 if args.steps + args.warmup <= 16 else 96 if args.steps + args.warmup <= 40 else 64)
-        if torch.cuda.is_available():
-            from tissue_analysis_b200.synth import voronoi_device
-            torch.cuda.set_device(0)
-            vol = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"],
-                                 cfg["dtype"]).cpu().numpy()
-        else:   # no GPU: a reduced stand-in volume generated on the CPU (same generator definition)
-            from tissue_analysis_b200.synth import voronoi_numpy
-            shape_zyx = tuple(min(s, 160) for s in shape_zyx)
-            vol = voronoi_numpy(shape_zyx, max(cfg["ncell"] * int(np.prod(shape_zyx)) // nvox, 8), cfg["seed"],
-                                cfg["weights"][::-1], cfg["dome"], np.dtype(cfg["dtype"]))
-        gv, sec, desc = run_reference_sample(vol, cfg["voxelsize"], edge, ncores, args.steps, args.warmup)
+        gv, sec, desc, kind = run_reference_sample(args.config, edge, ncores, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": gv, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u16" if elem == 2 else "u32",
                 "data": "synthetic", "config": {"workload": workload, "sample": desc},
-                "cpu_baseline": {"value": gv, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc},
+                "cpu_baseline": {"value": gv, "unit": UNIT, "cores": ncores, "kind": kind, "sample": desc},
                 "e2e": {"value": gv, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
 
     # ---------------------------------------------------------------------------------------------- our arm
+    import torch
     assert torch.cuda.is_available(), "bench.py --impl ours needs a B200 (there is no CPU fallback)"
     import torch.distributed as dist
     from tissue_analysis_b200 import _native
@@ -242,7 +287,8 @@ def main():
     bounds = None
     if world > 1 and cfg["dome"] and not args.equal_planes:
         # Partition step (outside the timed region, as a loader would do it once per volume): plane boundaries of equal
-        # estimated work instead of equal height -- a dome leaves the end slabs mostly background.
+        # estimated work instead of equal height -- a dome leaves the end slabs mostly background.  Multiples of 8 planes:
+        # the scan works in bricks of 8.
         from tissue_analysis_b200.distributed import partition_planes, partition_planes_weighted, plane_work_weights
         b0 = partition_planes(shape_zyx[0], world)
         part = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"],
@@ -256,7 +302,7 @@ def main():
         dist.all_gather_into_tensor(allw, mine)
         allw = allw.cpu().numpy()
         weights = np.concatenate([allw[r * cap:r * cap + (b0[r + 1] - b0[r])] for r in range(world)])
-        bounds = partition_planes_weighted(weights, world)
+        bounds = partition_planes_weighted(weights, world, align=8)
     scan = SlabScan(shape_zyx, torch.uint16 if elem == 2 else torch.uint32, rank=rank, world=world, bounds=bounds)
     gen = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"],
                          zslice=(scan.g_lo, scan.g_hi))
@@ -266,7 +312,8 @@ def main():
     hint_labels = cfg["ncell"] + 1 if elem == 4 else 0
 
     def step():
-        scan.run(flags=_native.PASS_ALL, max_label_hint=hint_labels, inertia=True)
+        scan.run(flags=_native.PASS_ALL, max_label_hint=hint_labels, inertia=True, overlap=args.overlap,
+                 deferred=not args.sync_merge)
 
     def barrier():
         if world > 1:
@@ -280,16 +327,21 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = scan.ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms = []
     ev0.record()
     for _ in range(args.steps):
         step()
-        scan_ms.append(scan.ctx.last_timing()["scan_ms"])
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = scan.ctx.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    # the scan kernel's own time: CUDA events of the library around its launches, read back after each of a few extra
+    # steps (reading them inside the timed loop would put a host synchronisation into every step)
+    scan_ms = []
+    for _ in range(3):
+        step()
+        scan_ms.append(scan.ctx.last_timing()["scan_ms"])
+    barrier()
     t = torch.tensor([ms, float(np.mean(scan_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,51 +360,125 @@ def main():
                 "traffic": ncu_traffic_bytes(args.config, world), "kernel": "ta::scan_kernel", "kernel_ms": scan_ms_avg,
                 "kernel_ms_per_rank": scan_ms_per_rank, "algorithmic_bytes_per_voxel": elem, "peak_source": peak_src}
 
-    # ---- e2e: host volume through the C ABI (H2D + pass + D2H of the tables), rank-local slab --------------
+    # ---- parity of the sharded result: merged tables == one GPU scanning the whole volume (outside the timed region) ------
+    parity = None
+    if world > 1 and not args.no_parity:
+        step()
+        if rank == 0:
+            merged = tables_digest(*scan.ctx.label_table(), *scan.ctx.pair_table())
+            n_pairs = int(scan.ctx.pair_table()[0].size)
+            whole = voronoi_device(shape_zyx, cfg["ncell"], cfg["seed"], cfg["weights"][::-1], cfg["dome"], cfg["dtype"])
+            c1 = _native.Context(local_rank)
+            c1.bind_device(whole.data_ptr(), elem, X, Y, Z, keepalive=whole)
+            c1.run_pass(_native.PASS_ALL, hint_labels)
+            single = tables_digest(*c1.label_table(), *c1.pair_table())
+            c1.close()
+            del whole
+            parity = {"merged_equals_single": merged == single, "pairs": n_pairs, "sha256": merged[:16],
+                      "check": "rank 0 scans the whole volume alone; sha256 over the label table and the sorted pair table"}
+        barrier()
+
+    # ---- e2e: host volume -> tables in host memory ---------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = torch.empty(tuple(scan.buf.shape), dtype=scan.buf.dtype).pin_memory()
-        host.copy_(scan.buf)
-        harr = host.numpy()
-        ctx2 = _native.Context(local_rank)
-        ns_b, nm_b, nf_b = harr.shape
+        host = torch.empty(tuple(scan.owned().shape), dtype=scan.buf.dtype).pin_memory()
+        host.copy_(scan.owned())
+        n_e2e = max(2, min(args.steps, 5))
+        if world == 1:
+            harr = host.numpy()
+            ctx2 = _native.Context(local_rank)
 
-        def e2e_step():
-            ctx2.run_pass_host(harr, _native.PASS_ALL, hint_labels,
-                               slab=(scan.own_lo, scan.own_hi, scan.g_lo - scan.own_lo))
-            lt = ctx2.label_table()
-            pt = ctx2.pair_table()
-            return lt, pt
-
+            def e2e_step():
+                ctx2.run_pass_host(harr, _native.PASS_ALL, hint_labels)
+                return ctx2.label_table(), ctx2.pair_table()
+            note = "pinned host volume -> ta_run_pass_host (chunked H2D overlapped with the scan) + ta_fetch_*_table (D2H)"
+        else:
+            def e2e_step():
+                scan.owned().copy_(host, non_blocking=True)
+                step()
+                if rank == 0:
+                    return scan.ctx.label_table(), scan.ctx.pair_table()
+                return None, None
+            note = ("every rank: pinned host slab -> device (H2D), sharded step with halo exchange and cross-rank merge; "
+                    "rank 0: ta_fetch_*_table of the merged tables (D2H)")
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(2, min(args.steps, 5))
         for _ in range(n_e2e):
             lt, pt = e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
-        d2h = sum(a.nbytes for a in lt) + sum(a.nbytes for a in pt)
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        d2h = (sum(a.nbytes for a in lt) + sum(a.nbytes for a in pt)) if lt is not None else 0
+        tt = torch.tensor([dt, float(host.numel() * host.element_size()), float(d2h)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": nvox / float(tt[0]) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(harr.nbytes),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
-               "note": "pinned host volume -> ta_run_pass_host (chunked H2D overlapped with the scan) + "
-                       "ta_fetch_*_table (D2H); per-rank slab, no cross-rank merge"}
-        ctx2.close()
+            mx = tt[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            tt[0] = mx[0]
+        e2e = {"value": nvox / float(tt[0]) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(tt[1]),
+               "d2h_bytes_per_step": int(tt[2]), "ms_per_step": float(tt[0]) * 1e3, "note": note}
+        if world == 1:
+            ctx2.close()
+
+    # ---- N = 1 extras: the drop-in class end to end, the other single-GPU configurations ------------------------------------
+    api_e2e, extra = None, None
+    if world == 1 and not args.no_extra:
+        import warnings
+        from tissue_analysis_b200 import SpatialImage, SpatialImageAnalysis3D
+        from tissue_analysis_b200.temporal_graph_from_image import graph_arrays
+        vol_np = scan.buf.cpu().numpy()                  # pageable host memory, (z, y, x)
+        img = SpatialImage(vol_np.transpose(2, 1, 0), voxelsize=cfg["voxelsize"])     # x fastest, as openalea's images
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            an = SpatialImageAnalysis3D(img, background=1, device=local_rank)
+            ga = graph_arrays(an)
+            t_arrays = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            nl = an.nb_labels()
+            an.volume(); an.boundingbox(); an.center_of_mass(); an.neighbors(); an.wall_areas()
+            an.cell_first_layer(); an.labels_at_stack_margins(); an.inertia_axis()
+            t_dicts = time.perf_counter() - t0
+        api_e2e = {"graph_arrays_s": t_arrays, "value": nvox / t_arrays / 1e9, "unit": UNIT,
+                   "dict_methods_s": t_dicts, "labels": int(nl),
+                   "note": "pageable numpy volume -> SpatialImageAnalysis3D (H2D + scan + D2H) -> graph_arrays (CSR + property "
+                           "arrays); dict_methods_s: then volume, boundingbox, center_of_mass, neighbors, wall_areas, "
+                           "cell_first_layer, labels_at_stack_margins, inertia_axis as the reference's dicts (tables cached)"}
+        del an, ga, img, vol_np
+        extra = {}
+        for name in ("C2", "C4"):
+            if name == args.config:
+                continue
+            c = CONFIGS[name]
+            cx, cy, cz = c["shape"]
+            cel = 2 if c["dtype"] == "uint16" else 4
+            free = torch.cuda.mem_get_info()[0]
+            if cx * cy * cz * cel * 1.3 > free:
+                extra[name] = "skipped: not enough free memory"
+                continue
+            v = voronoi_device((cz, cy, cx), c["ncell"], c["seed"], c["weights"][::-1], c["dome"], c["dtype"])
+            cx2 = _native.Context(local_rank)
+            cx2.bind_device(v.data_ptr(), cel, cx, cy, cz, keepalive=v)
+            tms = []
+            for _ in range(3):
+                cx2.run_pass(_native.PASS_ALL, c["ncell"] + 1 if cel == 4 else 0)
+                tms.append(cx2.last_timing()["scan_ms"])
+            extra[name] = {"scan_ms": float(np.min(tms)), "Gvoxel_per_s": cx * cy * cz / float(np.min(tms)) / 1e6,
+                           "roofline_frac": cx * cy * cz * cel / (float(np.min(tms)) * 1e-3) / 1e9 / peak}
+            cx2.close()
+            del v
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         edge = args.cpu_sample or 128
-        vol = scan.buf.cpu().numpy()
-        gv, sec, desc = run_reference_sample(vol, cfg["voxelsize"], edge, ncores, steps=1, warmup=0)
-        cpu_baseline = {"value": gv, "unit": UNIT, "cores": ncores, "kind": "port", "sample": desc,
-                        "seconds": sec}
+        gv, sec, desc, kind = run_reference_sample(args.config, edge, ncores, steps=1, warmup=0,
+                                                   vol_zyx=scan.buf.cpu().numpy())
+        cpu_baseline = {"value": gv, "unit": UNIT, "cores": ncores, "kind": kind, "sample": desc, "seconds": sec}
 
     if rank == 0 and scan.stage_ms:
         sys.stderr.write("[stage ms per step] " + ", ".join("%s %.3f" % (k, v / args.steps)
                                                             for k, v in scan.stage_ms.items()) + "\n")
+    rc = 0
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -360,13 +486,26 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload, "sharding": "z-slabs x%d%s" % (world, (", plane boundaries of equal estimated work %s" % list(bounds)) if bounds else ""),
                            "l2": "input (%.1f GiB) larger than L2, no flush needed" % (nvox * elem / 2 ** 30),
-                           "step": "halo exchange + scan + table compaction/sort + cross-rank merge + inertia eig"},
+                           "step": "halo exchange + scan + record packing + cross-rank merge + inertia eig" if world > 1
+                                   else "scan + table compaction / sort + inertia eig",
+                           "merge": None if world == 1 else ("synchronous" if args.sync_merge else "deferred: no host synchronisation inside a step")},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks}
+        if parity is not None:
+            line["parity"] = parity
+            if not parity["merged_equals_single"]:
+                rc = 3
+        if api_e2e is not None:
+            line["api_e2e"] = api_e2e
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
+        flag = torch.tensor([rc], dtype=torch.int32, device="cuda")
+        dist.broadcast(flag, 0)
+        rc = int(flag.item())
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

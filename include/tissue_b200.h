@@ -48,6 +48,11 @@ enum {
 /* Leave the pair records in hash order (no sort by (lo, hi)): for passes whose records only feed
  * ta_merge_pair_records on the ranks of a sharded run, which sorts the merged table anyway. */
 #define TA_PASS_UNSORTED 0x2000u
+/* No host synchronisation inside ta_run_pass (the sharded driver's steady state): everything is queued on the stream, the
+ * pair records are packed on the device behind a header row {count} (ta_pair_records_deferred; pair_capacity_hint = rows of
+ * that buffer) and the status flags -- pair / record overflow, label range -- are checked by the first call that hands
+ * results to the host (ta_*_size, ta_fetch_*, ta_pair_records_device), which returns the error then. */
+#define TA_PASS_DEFERRED 0x4000u
 /* Measurement switches, never needed for results (every combination fills identical tables, tests/test_gpu_parity.py):
  * 0x1000 launches the scan kernel's one-hot pair-counting instantiation, 0x800 forces the default per-voxel one;
  * 0x100 / 0x200 / 0x400 stop the kernel after staging / after the uniformity codes / before the table flush. */
@@ -121,6 +126,13 @@ int ta_label_table_device(ta_ctx* ctx, void** count, void** s1, void** s2, void*
 int ta_pair_records_device(ta_ctx* ctx, void** records, uint64_t* n);
 /* Replace the pair table by the sum-merge of `n` packed device records (gathered from all ranks). */
 int ta_merge_pair_records(ta_ctx* ctx, const void* device_records, uint64_t n);
+/* The same for a TA_PASS_DEFERRED pass, without host synchronisation.  ta_pair_records_deferred: this rank's record
+ * buffer, uint32[1 + cap_rows][9] on the device -- row 0 = {count, 0, ...}, then `count` records in hash order -- ready
+ * for a fixed-size all_gather.  ta_merge_pair_records_deferred: `gathered` = the buffers of all `world` ranks back to
+ * back; the pair table becomes their sum-merge.  Counts never reach the host; sorting and the status check happen at
+ * the first fetch. */
+int ta_pair_records_deferred(ta_ctx* ctx, void** records, uint64_t* cap_rows);
+int ta_merge_pair_records_deferred(ta_ctx* ctx, const void* gathered, uint64_t cap_rows, int world);
 
 /* Batched inertia axes (replaces compute_covariance_matrix SIA:137-150 + eigen_values_vectors SIA:152-167).
  * For each listed label: covariance = central second moments / max(3, count) from the exact integer sums

@@ -147,7 +147,10 @@ def load():
     parent = os.path.dirname(OUT_DIR)
     if parent not in sys.path:
         sys.path.insert(0, parent)
-    return importlib.import_module("vplants_ref.spatial_image_analysis")
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):          # "PlantGL is not installed ..." (SIA:32)
+        return importlib.import_module("vplants_ref.spatial_image_analysis")
 
 
 if __name__ == "__main__":

@@ -22,12 +22,14 @@ TA_ERR_NO_TABLES = -6
 
 PASS_MOMENTS, PASS_PAIRS6, PASS_WALL18, PASS_ALL = 1, 2, 4, 7
 PASS_UNSORTED = 0x2000   # pair records stay in hash order (input of merge_pair_records only)
+PASS_DEFERRED = 0x4000   # no host synchronisation inside the pass; flags and counts are read at the first fetch
 
 # every symbol include/tissue_b200.h declares (tests/test_cabi_symbols.py checks header <-> library)
 EXPORTS = [
     "ta_version", "ta_ctx_create", "ta_ctx_destroy", "ta_last_error", "ta_set_stream", "ta_bind_volume",
     "ta_set_slab", "ta_run_pass", "ta_run_pass_host", "ta_run_pass_ranges", "ta_label_table_size", "ta_fetch_label_table", "ta_pair_table_size",
     "ta_fetch_pair_table", "ta_label_table_device", "ta_pair_records_device", "ta_merge_pair_records",
+    "ta_pair_records_deferred", "ta_merge_pair_records_deferred",
     "ta_inertia_from_moments", "ta_inertia_table", "ta_inertia_eig", "ta_wall_voxel_coords", "ta_voxel_first_layer",
     "ta_hollow_out_cells", "ta_cell_shell18", "ta_map_labels", "ta_last_timing", "ta_launch_count", "ta_synth_voronoi",
 ]
@@ -71,6 +73,8 @@ def load():
     lib.ta_label_table_device.argtypes = [vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(u64)]
     lib.ta_pair_records_device.argtypes = [vp, P(vp), P(u64)]
     lib.ta_merge_pair_records.argtypes = [vp, vp, u64]
+    lib.ta_pair_records_deferred.argtypes = [vp, P(vp), P(u64)]
+    lib.ta_merge_pair_records_deferred.argtypes = [vp, vp, u64, ci]
     lib.ta_inertia_from_moments.argtypes = [vp, vp, u64, vp, vp]
     lib.ta_inertia_table.argtypes = [vp, vp, vp]
     lib.ta_inertia_eig.argtypes = [vp, vp, u64, vp, vp]
@@ -214,6 +218,16 @@ class Context(object):
 
     def merge_pair_records(self, dev_ptr, n):
         self._check(self.lib.ta_merge_pair_records(self.h, C.c_void_p(dev_ptr or 0), n))
+
+    def pair_records_deferred(self):
+        """(device pointer, cap_rows) of the record buffer of a PASS_DEFERRED pass: uint32[1 + cap_rows][9]."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.lib.ta_pair_records_deferred(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def merge_pair_records_deferred(self, dev_ptr, cap_rows, world):
+        self._check(self.lib.ta_merge_pair_records_deferred(self.h, C.c_void_p(dev_ptr), C.c_uint64(cap_rows), int(world)))
 
     # ---- derived ---------------------------------------------------------------------------------------------
     def inertia_from_moments(self, labels=None, n=None):

@@ -45,6 +45,8 @@ struct ta_ctx {
     size_t records_alloc = 0;
     uint64_t nrecords = 0;
     bool have_tables = false;
+    bool pending = false;             // deferred pass / merge: records, their count and the status flags are still on the device
+    uint64_t deferred_cap = 0;        // rows of the deferred record buffer (without the header row)
     double* d_evals = nullptr;
     double* d_evecs = nullptr;
     size_t eig_alloc_rows = 0;
@@ -230,10 +232,7 @@ int ta_set_slab(ta_ctx* ctx, int64_t own_lo, int64_t own_hi, int64_t slow_offset
     return TA_OK;
 }
 
-// compaction + sort + gather of the pair hash into ctx->records
-static int build_records(ta_ctx* ctx, bool sorted = true) {
-    cudaStream_t st = ctx->stream;
-    size_t cap = (size_t)ctx->pt.cap_mask + 1;
+static int ensure_sort_buffers(ta_ctx* ctx, size_t cap) {
     if (ctx->sort_alloc < cap) {
         for (int i = 0; i < 2; ++i) {
             if (ctx->sort_keys[i]) TA_CUDA(cudaFree(ctx->sort_keys[i]));
@@ -247,6 +246,15 @@ static int build_records(ta_ctx* ctx, bool sorted = true) {
         }
         ctx->sort_alloc = cap;
     }
+    return TA_OK;
+}
+
+// compaction + sort + gather of the pair hash into ctx->records
+static int build_records(ta_ctx* ctx, bool sorted = true) {
+    cudaStream_t st = ctx->stream;
+    size_t cap = (size_t)ctx->pt.cap_mask + 1;
+    int rcs = ensure_sort_buffers(ctx, cap);
+    if (rcs) return rcs;
     TA_CUDA(cudaMemsetAsync(&ctx->counters[1], 0, sizeof(unsigned int), st));
     int blocks = (int)std::min<size_t>((cap + 255) / 256, (size_t)ctx->num_sms * 8);
     ta::compact_pairs_kernel<<<blocks, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], &ctx->counters[1]);
@@ -284,6 +292,44 @@ static int build_records(ta_ctx* ctx, bool sorted = true) {
                                                               ctx->records);
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+// Deferred pass: the records go to ctx->records on the device -- header row {count}, then the rows, hash order -- without
+// the host ever learning the count.  No synchronisation.
+static int pack_records_deferred(ta_ctx* ctx, uint64_t cap_rows) {
+    cudaStream_t st = ctx->stream;
+    const size_t cap = (size_t)ctx->pt.cap_mask + 1;
+    int rc = ensure_sort_buffers(ctx, cap);
+    if (rc) return rc;
+    rc = ensure(ctx, &ctx->records, &ctx->records_alloc, (size_t)(cap_rows + 1) * ta::REC_WORDS);
+    if (rc) return rc;
+    TA_CUDA(cudaMemsetAsync(&ctx->counters[1], 0, sizeof(unsigned int), st));
+    const int blocks = (int)std::min<size_t>((cap + 255) / 256, (size_t)ctx->num_sms * 8);
+    ta::compact_pairs_kernel<<<blocks, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], &ctx->counters[1]);
+    ta::gather_records_deferred_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(ctx->pt, ctx->sort_keys[0], ctx->sort_vals[0], &ctx->counters[1],
+                                                                        (unsigned int)cap_rows, ctx->records);
+    ctx->launches += 2;
+    TA_CUDA(cudaGetLastError());
+    ctx->deferred_cap = cap_rows;
+    return TA_OK;
+}
+
+// What a deferred pass / merge left for later: the one host synchronisation (status flags, record count) and the sorted
+// records.  Called by everything that hands results to the host.
+static int resolve_pending(ta_ctx* ctx) {
+    if (!ctx->pending) return TA_OK;
+    ctx->pending = false;
+    int rc = build_records(ctx);
+    if (rc) { ctx->have_tables = false; return rc; }
+    const uint32_t* status = ctx->host_flags;
+    if (status[0] || status[3]) {
+        ctx->have_tables = false;
+        return fail(ctx, TA_ERR_PAIR_OVERFLOW, status[0] ? "pair table overflow (deferred pass): retry with a larger pair_capacity_hint"
+                                                         : "more pair records than the deferred record buffer holds: retry with more rows");
+    }
+    if (status[1]) { ctx->have_tables = false; return fail(ctx, TA_ERR_LABEL_RANGE, "a label exceeds the label table (max_label_hint too small)"); }
+    if (status[2] && ctx->diag_host && ctx->diag_host[0]) { ctx->have_tables = false; return fail(ctx, TA_ERR_CUDA, "scan kernel: a tile copy did not complete"); }
     return TA_OK;
 }
 
@@ -510,6 +556,18 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[12], cyc[13]);
     }
 
+    if (flags & TA_PASS_DEFERRED) {
+        // no host synchronisation: records packed on the device, flags checked at the first fetch (resolve_pending)
+        const uint64_t cap_rows = pair_capacity_hint ? pair_capacity_hint : std::min<uint64_t>((uint64_t)ctx->pt.cap_mask + 1, 1ull << 20);
+        rc = pack_records_deferred(ctx, cap_rows);
+        if (rc) return rc;
+        TA_CUDA(cudaEventRecord(ctx->ev[3], st));
+        ctx->timing_pending = true;
+        ctx->pending = true;
+        ctx->have_tables = true;
+        return TA_OK;
+    }
+    ctx->pending = false;
     rc = build_records(ctx, !(flags & TA_PASS_UNSORTED));
     if (rc) return rc;
     TA_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -586,6 +644,7 @@ int ta_run_pass_host(ta_ctx* ctx, const void* host_data, int elem_bytes, int64_t
 int ta_label_table_size(ta_ctx* ctx, uint64_t* n) {
     if (!ctx || !n) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
     if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    { int rcp = resolve_pending(ctx); if (rcp) return rcp; }
     *n = ctx->lt.nrows;
     return TA_OK;
 }
@@ -593,6 +652,7 @@ int ta_label_table_size(ta_ctx* ctx, uint64_t* n) {
 int ta_fetch_label_table(ta_ctx* ctx, uint64_t* count, uint64_t* s1, uint64_t* s2, int32_t* bbox) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    { int rcp = resolve_pending(ctx); if (rcp) return rcp; }
     TA_CUDA(cudaSetDevice(ctx->device));
     size_t n = ctx->lt.nrows;
     cudaStream_t st = ctx->stream;
@@ -613,6 +673,7 @@ int ta_fetch_label_table(ta_ctx* ctx, uint64_t* count, uint64_t* s1, uint64_t* s
 int ta_pair_table_size(ta_ctx* ctx, uint64_t* n) {
     if (!ctx || !n) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
     if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    { int rcp = resolve_pending(ctx); if (rcp) return rcp; }
     *n = ctx->nrecords;
     return TA_OK;
 }
@@ -620,6 +681,7 @@ int ta_pair_table_size(ta_ctx* ctx, uint64_t* n) {
 int ta_fetch_pair_table(ta_ctx* ctx, uint32_t* lo, uint32_t* hi, uint32_t* faces, uint32_t* wall18) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    { int rcp = resolve_pending(ctx); if (rcp) return rcp; }
     TA_CUDA(cudaSetDevice(ctx->device));
     size_t n = ctx->nrecords;
     if (n == 0) return TA_OK;
@@ -651,6 +713,7 @@ int ta_label_table_device(ta_ctx* ctx, void** count, void** s1, void** s2, void*
 int ta_pair_records_device(ta_ctx* ctx, void** records, uint64_t* n) {
     if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
     if (!ctx->have_tables) return fail(ctx, TA_ERR_NO_TABLES, "no tables: call ta_run_pass first");
+    { int rcp = resolve_pending(ctx); if (rcp) return rcp; }
     if (records) *records = ctx->records;
     if (n) *n = ctx->nrecords;
     return TA_OK;
@@ -673,6 +736,33 @@ int ta_merge_pair_records(ta_ctx* ctx, const void* device_records, uint64_t n) {
     if (rc) return rc;
     const uint32_t* status = ctx->host_flags;
     if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow in merge");
+    ctx->have_tables = true;
+    return TA_OK;
+}
+
+int ta_pair_records_deferred(ta_ctx* ctx, void** records, uint64_t* cap_rows) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!ctx->have_tables || !ctx->pending) return fail(ctx, TA_ERR_NO_TABLES, "no deferred pass: call ta_run_pass with TA_PASS_DEFERRED first");
+    if (records) *records = ctx->records;
+    if (cap_rows) *cap_rows = ctx->deferred_cap;
+    return TA_OK;
+}
+
+int ta_merge_pair_records_deferred(ta_ctx* ctx, const void* gathered, uint64_t cap_rows, int world) {
+    if (!ctx) return fail(nullptr, TA_ERR_BAD_ARG, "null context");
+    if (!gathered || world <= 0 || cap_rows == 0) return fail(ctx, TA_ERR_BAD_ARG, "ta_merge_pair_records_deferred: bad arguments");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t cap = std::max<size_t>(next_pow2((size_t)cap_rows * (size_t)world * 2), 1024);
+    // the status flags of the local pass stay (checked at the first fetch); only the table is emptied
+    int rc = ensure_pair_table(ctx, cap);
+    if (rc) return rc;
+    const size_t total = (size_t)cap_rows * (size_t)world;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16);
+    ta::merge_records_deferred_kernel<<<blocks, 256, 0, st>>>(ctx->pt, (const uint32_t*)gathered, (unsigned int)cap_rows, world);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    ctx->pending = true;
     ctx->have_tables = true;
     return TA_OK;
 }

@@ -50,6 +50,45 @@ __global__ void gather_records_kernel(PairTable pt, const u64* keys, const uint3
     for (int f = 0; f < 7; ++f) r[2 + f] = v[f];
 }
 
+// The same without knowing n on the host (deferred pass): n comes from device memory, the records start at row 1 and row 0
+// is a header {rows written, 0, ...}.  More than `cap_rows` records: the overflow flag status[3] and a clipped header.
+__global__ void gather_records_deferred_kernel(PairTable pt, const u64* keys, const uint32_t* slots, const unsigned int* n_dev,
+                                               unsigned int cap_rows, uint32_t* rec) {
+    const unsigned int n_all = *n_dev, n = n_all < cap_rows ? n_all : cap_rows;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rec[0] = n;
+#pragma unroll
+        for (int f = 1; f < REC_WORDS; ++f) rec[f] = 0u;
+        if (n_all > cap_rows) atomicExch(&pt.status[3], 1u);
+    }
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 k = keys[i];
+        const uint32_t* v = &pt.vals[(size_t)slots[i] * TA_PAIR_STRIDE];
+        uint32_t* r = &rec[(size_t)(i + 1) * REC_WORDS];
+        r[0] = (uint32_t)(k >> 32);
+        r[1] = (uint32_t)k;
+#pragma unroll
+        for (int f = 0; f < 7; ++f) r[2 + f] = v[f];
+    }
+}
+
+// sum-merge the gathered records of all ranks ([world][1 + cap_rows][REC_WORDS], header row first) into a cleared hash
+__global__ void merge_records_deferred_kernel(PairTable pt, const uint32_t* all, unsigned int cap_rows, int world) {
+    const size_t total = (size_t)world * cap_rows;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t rank = i / cap_rows, j = i - rank * cap_rows;
+        const uint32_t* base = all + rank * (size_t)(cap_rows + 1) * REC_WORDS;
+        if (j >= base[0]) continue;
+        const uint32_t* r = base + (j + 1) * REC_WORDS;
+        const u64 key = ((u64)r[0] << 32) | r[1];
+        const int slot = ta_pair_slot(pt, key);
+        if (slot < 0) continue;
+#pragma unroll
+        for (int f = 0; f < 7; ++f)
+            if (r[2 + f]) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + f], r[2 + f]);
+    }
+}
+
 // sum-merge packed records (from all ranks) into a cleared hash
 __global__ void merge_records_kernel(PairTable pt, const uint32_t* rec, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

@@ -10,8 +10,12 @@ plus one halo plane on each side:
   2. local pass        ownership rules of ``ta_set_slab``: a face belongs to the rank owning its lower voxel, an
                        18-connected wall voxel to the rank owning the voxel
   3. label table       all_reduce SUM of the exact u64 sums, MIN / MAX of the bounding boxes
-  4. pair table        all_gather of the packed records (variable length -> sizes first) and a device hash
-                       sum-merge (``ta_merge_pair_records``) on every rank
+  4. pair table        all_gather of the packed records and a device hash sum-merge on every rank.  First step: sizes
+                       first (one host synchronisation), ``ta_merge_pair_records``.  Steady state (``run`` again on a
+                       volume of the same kind): NO host synchronisation anywhere in the step -- the pass is queued with
+                       ``TA_PASS_DEFERRED``, every rank contributes a fixed-size record buffer whose header row carries
+                       its count, ``ta_merge_pair_records_deferred`` reads the counts on the device, and sorting, the
+                       record count and the overflow flags wait for the first fetch.
 
 The collective helpers below act on plain tensors, so the world_size-2 ``gloo`` tests drive them on the CPU with
 oracle tables; on GPUs they act directly on the library's device buffers (zero copy).
@@ -28,9 +32,14 @@ def partition_planes(n_slow, world):
     return [(n_slow * r) // world for r in range(world + 1)]
 
 
-def partition_planes_weighted(weights, world):
+def partition_planes_weighted(weights, world, align=1):
     """Contiguous plane ranges of (nearly) equal total weight: rank r owns [b[r], b[r+1]).  ``weights``: one
-    non-negative work estimate per plane (see ``plane_work_weights``).  Every rank gets at least one plane."""
+    non-negative work estimate per plane (see ``plane_work_weights``).  Every rank gets at least one plane.
+    ``align``: boundaries are multiples of it (the scan works in bricks of 8 planes: a slab whose height is a multiple
+    of 8 has no ragged last brick layer)."""
+    if align > 1 and len(weights) % align == 0 and len(weights) // align >= world:
+        w = np.asarray(weights, dtype=np.float64).reshape(-1, align).sum(axis=1)
+        return [align * v for v in partition_planes_weighted(w, world)]
     w = np.asarray(weights, dtype=np.float64)
     n = w.size
     assert n >= world
@@ -87,12 +96,15 @@ def allreduce_label_tables(count, s1, s2, bmin, bmax):
     dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
 
 
-def allgather_pair_records(records, world):
-    """records: int32[n, 9] (this rank's packed pair rows) -> int32[sum n_r, 9] on every rank."""
+def allgather_pair_records(records, world, sizes_out=None):
+    """records: int32[n, 9] (this rank's packed pair rows) -> int32[sum n_r, 9] on every rank.  ``sizes_out``: a list that
+    receives the ranks' row counts."""
     n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
     sizes = torch.zeros(world, dtype=torch.int64, device=records.device)
     dist.all_gather_into_tensor(sizes, n)
     sizes = sizes.tolist()                       # one host synchronisation for all ranks' sizes
+    if sizes_out is not None:
+        sizes_out[:] = sizes
     cap = max(max(sizes), 1)
     padded = torch.zeros((cap, REC_WORDS), dtype=records.dtype, device=records.device)
     padded[:records.shape[0]] = records
@@ -136,6 +148,9 @@ class SlabScan(object):
         self._native = _native
         self.stage_ms, self._t0 = {}, 0.0
         self._halo_stream = self._halo_event = None
+        self._rec_cap = 0          # rows of the deferred record buffer: set by the first (synchronous) step
+        self._sizes_box = []
+        self._gathered = None
 
     def owned(self):
         """View of the owned planes (fill it by upload or by the device generator)."""
@@ -153,9 +168,16 @@ class SlabScan(object):
             self.stage_ms[name] = self.stage_ms.get(name, 0.0) + (now - self._t0) * 1e3
         self._t0 = now
 
-    def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False):
+    def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False, overlap=False, deferred=True):
+        """One sharded step.  ``overlap``: scan the interior planes while the halo planes are still in flight (three
+        launches) instead of one launch behind the exchange.  ``deferred``: after a first synchronous step has sized the
+        record buffer, run without any host synchronisation (see the module docstring)."""
         ns, nm, nf = self.buf.shape
         self._tick(None)
+        use_deferred = bool(deferred and self.world > 1 and self._rec_cap)
+        if use_deferred:
+            flags |= self._native.PASS_DEFERRED
+            pair_capacity_hint = self._rec_cap
         if self.elem == 4 and not max_label_hint and self.world > 1:
             # every rank must size its dense label table identically before the all_reduce
             mx = self.owned().view(torch.int32).max().to(torch.int64).reshape(1)
@@ -179,15 +201,24 @@ class SlabScan(object):
                 exchange_halo_planes(self.buf, self.own_lo, self.own_hi, self.rank, self.world)
                 self._halo_event.record(self._halo_stream)
             lo, hi = self.own_lo, self.own_hi
-            first = (lo, min(lo + 1, hi)) if self.has_lo else (lo, lo)
-            last = (max(hi - 1, first[1]), hi) if self.has_hi else (hi, hi)
             ev = self._halo_event.cuda_event
             # the local records only feed the merge, which sorts: skip the local sort
-            self.ctx.run_pass_ranges([(first[1], last[0]), first, last], [None, ev, ev],
-                                     flags | self._native.PASS_UNSORTED, max_label_hint, pair_capacity_hint)
+            if overlap:
+                first = (lo, min(lo + 1, hi)) if self.has_lo else (lo, lo)
+                last = (max(hi - 1, first[1]), hi) if self.has_hi else (hi, hi)
+                self.ctx.run_pass_ranges([(first[1], last[0]), first, last], [None, ev, ev],
+                                         flags | self._native.PASS_UNSORTED, max_label_hint, pair_capacity_hint)
+            else:
+                # one launch behind the exchange: a boundary plane scanned on its own stages a whole ten-plane tile per
+                # brick for one plane of work, and two extra launches cost more than 2 MiB over NVLink
+                self.ctx.run_pass_ranges([(lo, hi)], [ev], flags | self._native.PASS_UNSORTED, max_label_hint,
+                                         pair_capacity_hint)
         self._tick("pass")
         if self.world > 1:
-            self.merge()
+            if use_deferred:
+                self.merge_deferred()
+            else:
+                self.merge()
         if inertia:
             self.ctx.inertia_table(fetch=False)
         self._tick("inertia")
@@ -216,9 +247,35 @@ class SlabScan(object):
             mine = device_tensor(p_rec, (n_rec, REC_WORDS), "<i4")
         else:
             mine = torch.zeros((0, REC_WORDS), dtype=torch.int32, device=self.device)
-        allrec = allgather_pair_records(mine, self.world).contiguous()
+        allrec = allgather_pair_records(mine, self.world, sizes_out=self._sizes_box).contiguous()
+        # size the deferred record buffer of the following steps: the largest rank, with head room
+        self._rec_cap = max(1024, int(1.5 * max(self._sizes_box)) + 64)
         self._tick("allgather")
         self.ctx.merge_pair_records(allrec.data_ptr(), allrec.shape[0])     # same stream; synchronises internally
+        self._tick("pair merge")
+
+    def _allreduce_labels(self):
+        (p_count, p_s1, p_s2, p_bmin, p_bmax), n = self.ctx.label_table_device()
+        assert p_s1 == p_count + 8 * n and p_s2 == p_s1 + 24 * n and p_bmax == p_bmin + 12 * n
+        dist.all_reduce(device_tensor(p_count, (n * 10,), "<i8"), op=dist.ReduceOp.SUM)
+        box = device_tensor(p_bmin, (n * 6,), "<i4")
+        box[n * 3:].neg_()                       # MAX(x) = -MIN(-x): one collective for both halves of the boxes
+        dist.all_reduce(box, op=dist.ReduceOp.MIN)
+        box[n * 3:].neg_()
+
+    def merge_deferred(self):
+        """The merge of a PASS_DEFERRED step: two all_reduces, one fixed-size all_gather, one merge kernel; the host
+        never waits."""
+        self._allreduce_labels()
+        self._tick("allreduce")
+        p_rec, cap = self.ctx.pair_records_deferred()
+        rows = (cap + 1) * REC_WORDS
+        mine = device_tensor(p_rec, (rows,), "<i4")
+        if self._gathered is None or self._gathered.numel() != self.world * rows:
+            self._gathered = torch.empty(self.world * rows, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(self._gathered, mine)
+        self._tick("allgather")
+        self.ctx.merge_pair_records_deferred(self._gathered.data_ptr(), cap, self.world)
         self._tick("pair merge")
 
     def tables(self, ax_of_mem=(2, 1, 0)):

@@ -80,6 +80,30 @@ def voronoi_numpy(shape, ncell, seed, weights=(1, 1, 1), dome=False, dtype=np.ui
     return out
 
 
+def voronoi_numpy_box(shape, ncell, seed, lo, hi, weights=(1, 1, 1), dome=False, dtype=np.uint16, k=8):
+    """The box [lo, hi) (API axis order) of the volume ``voronoi_numpy(shape, ...)`` would make, without making the rest:
+    what a CPU-only process needs of a 1024^3 workload (bench.py's reference arm)."""
+    from scipy.spatial import cKDTree
+    seeds = voronoi_seeds(shape, ncell, seed).astype(np.int64)
+    w = np.asarray(weights, np.int64)
+    tree = cKDTree((seeds * w).astype(np.float64))
+    ext = tuple(int(h - l) for l, h in zip(lo, hi))
+    out = np.empty(ext, dtype)
+    k = min(k, ncell)
+    ys, zs = np.meshgrid(np.arange(lo[1], hi[1], dtype=np.int64), np.arange(lo[2], hi[2], dtype=np.int64), indexing="ij")
+    for i, x in enumerate(range(lo[0], hi[0])):
+        pts = np.stack([np.full(ys.size, 16 * x + 8, np.int64), 16 * ys.ravel() + 8, 16 * zs.ravel() + 8], axis=1) * w
+        _, cand = tree.query(pts.astype(np.float64), k=k)
+        cand = cand.reshape(len(pts), k)
+        d = ((pts[:, None, :] - seeds[cand] * w) ** 2).sum(axis=2)
+        best = d.min(axis=1, keepdims=True)
+        idx = np.where(d == best, cand, np.iinfo(np.int64).max).min(axis=1)
+        out[i] = (idx + 2).reshape(ext[1], ext[2]).astype(dtype)
+    if dome:
+        out[dome_mask(shape, (lo[0], hi[0]))[:, lo[1]:hi[1], lo[2]:hi[2]]] = 1
+    return out
+
+
 def voronoi_device(shape, ncell, seed, weights=(1, 1, 1), dome=False, dtype="uint16", ctx=None, zslice=None,
                    device=None):
     """CUDA generator -> torch tensor (C-contiguous, API order = (slow, mid, fast)) on the current device.
