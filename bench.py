@@ -327,10 +327,10 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = scan.ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    ev0.record(scan.stream)                    # the stream the steps are queued on
     for _ in range(args.steps):
         step()
-    ev1.record()
+    ev1.record(scan.stream)
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = scan.ctx.launch_count() - launches0
@@ -394,7 +394,8 @@ def main():
             note = "pinned host volume -> ta_run_pass_host (chunked H2D overlapped with the scan) + ta_fetch_*_table (D2H)"
         else:
             def e2e_step():
-                scan.owned().copy_(host, non_blocking=True)
+                with torch.cuda.stream(scan.stream):
+                    scan.owned().copy_(host, non_blocking=True)
                 step()
                 if rank == 0:
                     return scan.ctx.label_table(), scan.ctx.pair_table()

@@ -28,6 +28,14 @@ def main():
         torch.cuda.synchronize()
         scan.run(inertia=True)
         merged = scan.tables()
+        first = (scan.ctx.label_table(), scan.ctx.pair_table())
+        # the following steps run deferred (no host synchronisation; record counts stay on the device) -- with the scan of
+        # the interior planes overlapped with the halo exchange, and without: the same tables as the first, synchronous step
+        for overlap in (True, False):
+            assert scan._rec_cap > 0
+            scan.run(inertia=True, overlap=overlap, deferred=True)
+            again = (scan.ctx.label_table(), scan.ctx.pair_table())
+            ok = ok and all(np.array_equal(a, b) for a, b in zip(first[0] + first[1], again[0] + again[1]))
         # single-GPU truth on every rank
         whole = voronoi_device(shape, ncell, seed, (1, 1, 1), True, dt)
         ctx = _native.Context(local)

@@ -281,9 +281,8 @@ def test_mutators_and_property_image_on_the_gpu():
 
 @pytest.mark.parametrize("shape", [(5, 3, 2), (17, 16, 8), (129, 17, 9), (131, 5, 3), (260, 40, 21)])
 @pytest.mark.parametrize("dtype,nlab", [(np.uint16, 9), (np.uint16, 16), (np.uint16, 23), (np.uint32, 30), (np.uint32, 40)])
-def test_noise_within_the_one_hot_id_budget(shape, dtype, nlab):
-    """Noise on the one-hot pair path of the scan kernel: junctions of many labels, ragged rows, sparse label values.
-    With more labels than ids in a quarter (23 / 40) the brick is staged again and takes the per-voxel path."""
+def test_noise_with_tens_of_labels(shape, dtype, nlab):
+    """Noise volumes: junctions of many labels in every neighbourhood, ragged rows, sparse label values."""
     rng = np.random.default_rng(sum(shape) + nlab)
     names = rng.choice(np.arange(2, 60000), size=nlab, replace=False)
     arr = names[rng.integers(0, nlab, size=shape[::-1])].astype(dtype)
@@ -293,7 +292,7 @@ def test_noise_within_the_one_hot_id_budget(shape, dtype, nlab):
     view, ax = memory_layout(img)
     ctx = _native.Context()
     ctx.bind_host(np.ascontiguousarray(view))
-    ctx.run_pass(_native.PASS_ALL | 0x1000)              # one-hot pair path for uint16 too
+    ctx.run_pass(_native.PASS_ALL)
     count, s1, s2, bbox = ctx.label_table()
     lo, hi, faces, wall = ctx.pair_table()
     ctx.close()
@@ -302,23 +301,45 @@ def test_noise_within_the_one_hot_id_budget(shape, dtype, nlab):
 
 
 @pytest.mark.parametrize("dtype", [np.uint16, np.uint32])
-def test_one_hot_pair_path_equals_per_voxel_pair_path(dtype):
-    """Flag 0x800 forces phases C2 / D / D2 (per-voxel neighbour tests) for every brick, 0x1000 the one-hot phases
-    R / S wherever a brick has few enough labels.  Same tables bit for bit, and both equal the oracle."""
+def test_deferred_pass_and_merge_equal_the_synchronous_pass(dtype):
+    """TA_PASS_DEFERRED (the sharded driver's steady state: no host synchronisation, record counts stay on the device):
+    the packed record buffer, merged back as if it had been gathered from `world` ranks, gives the tables of the plain
+    pass -- once (world = 1) and doubled (the same buffer twice: every pair counter exactly twice as large)."""
+    import torch
     from tissue_analysis_b200 import _native
     from tissue_analysis_b200.engine import memory_layout
     img = tissue_image((150, 70, 33), 260, seed=21, dome=True, dtype=dtype)
-    view, _ = memory_layout(img)
-    out = []
-    for extra in (0x1000, 0x800):
-        ctx = _native.Context()
-        ctx.bind_host(np.ascontiguousarray(view))
-        ctx.run_pass(_native.PASS_ALL | extra)
-        out.append((ctx.label_table(), ctx.pair_table()))
-        ctx.close()
-    for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
-        assert np.array_equal(a, b)
-    assert_tables_equal(SpatialImageAnalysis3D(img, background=1)._tables(), oracle_tables(np.asarray(img)))
+    view = np.ascontiguousarray(memory_layout(img)[0])
+    hint = 400 if dtype == np.uint32 else 0
+    ctx = _native.Context()
+    stream = torch.cuda.Stream()                # as the sharded driver does: one (non-default) stream shared with torch
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)
+    ctx.bind_host(view)
+    ctx.run_pass(_native.PASS_ALL, hint)
+    want = ctx.label_table() + ctx.pair_table()
+    npairs = want[4].size
+    for world in (1, 2):
+        ctx.run_pass(_native.PASS_ALL | _native.PASS_UNSORTED | _native.PASS_DEFERRED, hint, npairs + 100)
+        ptr, cap = ctx.pair_records_deferred()
+        assert cap == npairs + 100
+        rows = (cap + 1) * 9
+        from tissue_analysis_b200.distributed import device_tensor
+        mine = device_tensor(ptr, (rows,), "<i4")
+        assert int(mine[0]) == npairs                      # the header row carries the count
+        gathered = torch.cat([mine] * world).contiguous()
+        ctx.merge_pair_records_deferred(gathered.data_ptr(), cap, world)
+        got = ctx.label_table() + ctx.pair_table()
+        for a, b in zip(got[:4], want[:4]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(got[4], want[4]) and np.array_equal(got[5], want[5])
+        assert np.array_equal(got[6], world * want[6]) and np.array_equal(got[7], world * want[7])
+    # too few rows for the records: the error arrives with the first fetch
+    ctx.run_pass(_native.PASS_ALL | _native.PASS_DEFERRED, hint, max(npairs // 2, 1))
+    with pytest.raises(_native.NativeError):
+        ctx.pair_table()
+    ctx.close()
+    torch.cuda.set_stream(torch.cuda.default_stream())
 
 
 @pytest.mark.parametrize("chunk", [0, 2, 3, 8, 1000])
@@ -370,8 +391,8 @@ def test_pass_in_plane_ranges_equals_one_pass():
 
 
 def test_kernel_variants_give_the_same_tables(monkeypatch, capfd):
-    """Every instantiation of the scan kernel -- phase clocks on (TA_PHASE_TIMING=1), TMA or cp.async staging
-    (TA_NO_TMA=1), per-voxel or one-hot pair path -- fills identical tables."""
+    """TMA staging and cp.async staging (TA_NO_TMA=1) fill identical tables.  (TA_PHASE_TIMING only has an effect in a
+    -DTA_WITH_PHASE_TIMING build; the product library ignores it.)"""
     from tissue_analysis_b200 import _native
     from tissue_analysis_b200.engine import memory_layout
     img = tissue_image((160, 48, 27), 120, seed=31, dome=True)
@@ -386,8 +407,8 @@ def test_kernel_variants_give_the_same_tables(monkeypatch, capfd):
         return out
 
     want = tables()
-    for env in ({"TA_PHASE_TIMING": "1"}, {"TA_NO_TMA": "1"}, {"TA_PHASE_TIMING": "1", "TA_NO_TMA": "1"}):
-        for flags in (0, 0x1000):
+    for env in ({"TA_PHASE_TIMING": "1"}, {"TA_NO_TMA": "1"}):
+        for flags in (0,):
             with monkeypatch.context() as m:
                 for k, v in env.items():
                     m.setenv(k, v)

@@ -497,11 +497,14 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         P.phase_cycles = ctx->phase_cycles;
     }
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
-    TA_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if (!(ranges && ranges->n == 1 && ranges->wait_events && ranges->wait_events[0])) TA_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (ranges) {
         for (int k = 0; k < ranges->n; ++k) {
-            if (ranges->wait_events && ranges->wait_events[k])
+            if (ranges->wait_events && ranges->wait_events[k]) {
                 TA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ranges->wait_events[k], 0));
+                // one range behind one event (the halo exchange): the wait is not scan time
+                if (ranges->n == 1) TA_CUDA(cudaEventRecord(ctx->ev[1], st));
+            }
             rc = launch_scan(ctx, P, tmap, ranges->lo_hi[2 * k], ranges->lo_hi[2 * k + 1]);
             if (rc) return rc;
         }

@@ -144,7 +144,11 @@ class SlabScan(object):
         self.buf = torch.zeros((self.own_hi + (1 if self.has_hi else 0), nm, nf), dtype=dtype, device=self.device)
         self.elem = self.buf.element_size()
         self.ctx = _native.Context(self.device.index)
-        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # One stream for the library's kernels AND the collectives (torch orders a collective against the stream that is
+        # current when it is issued).  torch's default stream has handle 0, which ta_set_stream reads as "the context's own
+        # stream": the deferred step, which never synchronises with the host, would then race with the collectives.
+        self.stream = torch.cuda.Stream(self.device)
+        self.ctx.set_stream(self.stream.cuda_stream)
         self._native = _native
         self.stage_ms, self._t0 = {}, 0.0
         self._halo_stream = self._halo_event = None
@@ -171,7 +175,13 @@ class SlabScan(object):
     def run(self, flags=7, max_label_hint=0, pair_capacity_hint=0, inertia=False, overlap=False, deferred=True):
         """One sharded step.  ``overlap``: scan the interior planes while the halo planes are still in flight (three
         launches) instead of one launch behind the exchange.  ``deferred``: after a first synchronous step has sized the
-        record buffer, run without any host synchronisation (see the module docstring)."""
+        record buffer, run without any host synchronisation (see the module docstring).  Everything is queued on
+        ``self.stream``."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self._run(flags, max_label_hint, pair_capacity_hint, inertia, overlap, deferred)
+
+    def _run(self, flags, max_label_hint, pair_capacity_hint, inertia, overlap, deferred):
         ns, nm, nf = self.buf.shape
         self._tick(None)
         use_deferred = bool(deferred and self.world > 1 and self._rec_cap)
