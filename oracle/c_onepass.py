@@ -1,4 +1,4 @@
-"""ctypes loader of the C oracle (oracle/c/onepass.c -> oracle/_ref/libta_oracle.so).  Test infrastructure only."""
+"""ctypes loader of the C oracle (oracle/c/onepass.c -> oracle/_build/libta_oracle.so).  Test infrastructure only."""
 import ctypes as C
 import os
 import subprocess
@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_ref", "libta_oracle.so")
+_SO = os.path.join(_HERE, "_build", "libta_oracle.so")
 
 
 def _lib():
