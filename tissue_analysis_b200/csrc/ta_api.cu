@@ -45,6 +45,8 @@ struct ta_ctx {
     size_t records_alloc = 0;
     uint64_t nrecords = 0;
     bool have_tables = false;
+    uint32_t* fetch_scratch = nullptr;   // device scratch of the fetch functions (interleaved boxes, split pair columns)
+    size_t fetch_scratch_have = 0;
     bool pending = false;             // deferred pass / merge: records, their count and the status flags are still on the device
     uint64_t deferred_cap = 0;        // rows of the deferred record buffer (without the header row)
     double* d_evals = nullptr;
@@ -134,6 +136,7 @@ int ta_ctx_create(ta_ctx** out, int device) {
     TA_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(nullptr, TA_ERR_CUDA, "device is not sm_100 class (Blackwell) hardware");
     ctx = new ta_ctx();
+    struct CtxGuard { ta_ctx* c; ~CtxGuard() { if (c) ta_ctx_destroy(c); } } guard{ctx};    // an early return below frees it
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     TA_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
@@ -146,6 +149,7 @@ int ta_ctx_create(ta_ctx** out, int device) {
             TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, tm != 0),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
+    guard.c = nullptr;
     *out = ctx;
     return TA_OK;
 }
@@ -160,7 +164,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     cudaFree(ctx->status);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
-    cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles);
+    cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles); cudaFree(ctx->fetch_scratch);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->diag_host) cudaFreeHost(ctx->diag_host);
@@ -329,7 +333,13 @@ static int resolve_pending(ta_ctx* ctx) {
                                                          : "more pair records than the deferred record buffer holds: retry with more rows");
     }
     if (status[1]) { ctx->have_tables = false; return fail(ctx, TA_ERR_LABEL_RANGE, "a label exceeds the label table (max_label_hint too small)"); }
-    if (status[2] && ctx->diag_host && ctx->diag_host[0]) { ctx->have_tables = false; return fail(ctx, TA_ERR_CUDA, "scan kernel: a tile copy did not complete"); }
+    if (ctx->diag_host && ctx->diag_host[0]) {
+        ctx->have_tables = false;
+        int rcd = fail(ctx, TA_ERR_CUDA, "scan kernel: a CTA gave up waiting for its brick");
+        ta_last_error(ctx);
+        ctx->diag_host[0] = 0;
+        return rcd;
+    }
     return TA_OK;
 }
 
@@ -576,6 +586,12 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     TA_CUDA(cudaEventRecord(ctx->ev[3], st));
     const uint32_t* status = ctx->host_flags;      // read back inside build_records, after the scan kernel
     ctx->timing_pending = true;                     // events are resolved lazily by ta_last_timing
+    if (ctx->diag_host && ctx->diag_host[0]) {      // a CTA gave up waiting for a tile copy and left (ta_scan.cuh, phase A)
+        int rcd = fail(ctx, TA_ERR_CUDA, "scan kernel: a CTA gave up waiting for its brick");
+        ta_last_error(ctx);                         // appends the diagnostic while it is still there
+        ctx->diag_host[0] = 0;
+        return rcd;
+    }
     if (phase_timing) fprintf(stderr, "[ta] moment-slot evictions: %u (%.3f per segment column)\n", status[2],
                               (double)status[2] / ((double)total * ta::NTHREADS));
     if (status[0]) return fail(ctx, TA_ERR_PAIR_OVERFLOW, "pair table overflow: retry with a larger pair_capacity_hint");
@@ -659,17 +675,19 @@ int ta_fetch_label_table(ta_ctx* ctx, uint64_t* count, uint64_t* s1, uint64_t* s
     TA_CUDA(cudaSetDevice(ctx->device));
     size_t n = ctx->lt.nrows;
     cudaStream_t st = ctx->stream;
+    // the layouts the caller wants are made on the device; the host side is four copies and ONE synchronisation
+    if (bbox) {
+        int rc = ensure(ctx, &ctx->fetch_scratch, &ctx->fetch_scratch_have, n * 6);
+        if (rc) return rc;
+        ta::interleave_boxes_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(ctx->lt.bmin, ctx->lt.bmax, n, (int*)ctx->fetch_scratch);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+    }
     if (count) TA_CUDA(cudaMemcpyAsync(count, ctx->lt.count, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
     if (s1) TA_CUDA(cudaMemcpyAsync(s1, ctx->lt.s1, n * 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     if (s2) TA_CUDA(cudaMemcpyAsync(s2, ctx->lt.s2, n * 6 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (bbox) TA_CUDA(cudaMemcpyAsync(bbox, ctx->fetch_scratch, n * 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
-    if (bbox) {
-        std::vector<int> lo(n * 3), hi(n * 3);
-        TA_CUDA(cudaMemcpy(lo.data(), ctx->lt.bmin, n * 3 * sizeof(int), cudaMemcpyDeviceToHost));
-        TA_CUDA(cudaMemcpy(hi.data(), ctx->lt.bmax, n * 3 * sizeof(int), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; ++i)
-            for (int a = 0; a < 3; ++a) { bbox[i * 6 + a] = lo[i * 3 + a]; bbox[i * 6 + 3 + a] = hi[i * 3 + a]; }
-    }
     return TA_OK;
 }
 
@@ -688,16 +706,18 @@ int ta_fetch_pair_table(ta_ctx* ctx, uint32_t* lo, uint32_t* hi, uint32_t* faces
     TA_CUDA(cudaSetDevice(ctx->device));
     size_t n = ctx->nrecords;
     if (n == 0) return TA_OK;
-    std::vector<uint32_t> rec(n * ta::REC_WORDS);
-    TA_CUDA(cudaMemcpyAsync(rec.data(), ctx->records, rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    TA_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t* r = &rec[i * ta::REC_WORDS];
-        if (lo) lo[i] = r[0];
-        if (hi) hi[i] = r[1];
-        if (faces) for (int f = 0; f < 6; ++f) faces[i * 6 + f] = r[2 + f];
-        if (wall18) wall18[i] = r[8];
-    }
+    cudaStream_t st = ctx->stream;
+    int rc = ensure(ctx, &ctx->fetch_scratch, &ctx->fetch_scratch_have, n * ta::REC_WORDS);
+    if (rc) return rc;
+    ta::split_records_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(ctx->records, n, ctx->fetch_scratch);
+    ctx->launches++;
+    TA_CUDA(cudaGetLastError());
+    const uint32_t* d = ctx->fetch_scratch;
+    if (lo) TA_CUDA(cudaMemcpyAsync(lo, d, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (hi) TA_CUDA(cudaMemcpyAsync(hi, d + n, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (faces) TA_CUDA(cudaMemcpyAsync(faces, d + 2 * n, n * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (wall18) TA_CUDA(cudaMemcpyAsync(wall18, d + 8 * n, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
     return TA_OK;
 }
 
@@ -777,19 +797,25 @@ int ta_inertia_from_moments(ta_ctx* ctx, const uint32_t* labels, uint64_t n, dou
     if (!evals || !evecs) return fail(ctx, TA_ERR_BAD_ARG, "null output");
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    uint32_t* dl = nullptr; double *dv = nullptr, *dw = nullptr;
-    TA_CUDA(cudaMalloc((void**)&dw, n * 3 * sizeof(double)));
-    TA_CUDA(cudaMalloc((void**)&dv, n * 9 * sizeof(double)));
-    if (labels) {
-        TA_CUDA(cudaMalloc((void**)&dl, n * sizeof(uint32_t)));
-        TA_CUDA(cudaMemcpyAsync(dl, labels, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // results go to the context's eigen buffers (kept between calls), the label list to a scoped temporary
+    if (ctx->eig_alloc_rows < n) {
+        cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs);
+        ctx->d_evals = ctx->d_evecs = nullptr; ctx->eig_alloc_rows = 0;
+        TA_CUDA(cudaMalloc((void**)&ctx->d_evals, n * 3 * sizeof(double)));
+        TA_CUDA(cudaMalloc((void**)&ctx->d_evecs, n * 9 * sizeof(double)));
+        ctx->eig_alloc_rows = n;
     }
-    ta::inertia_from_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->lt, dl, n, dw, dv);
+    double *dw = ctx->d_evals, *dv = ctx->d_evecs;
+    TaDevBuf dl;
+    if (labels) {
+        TA_CUDA(cudaMalloc(&dl.p, n * sizeof(uint32_t)));
+        TA_CUDA(cudaMemcpyAsync(dl.p, labels, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    ta::inertia_from_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->lt, dl.as<uint32_t>(), n, dw, dv);
     ctx->launches++;
     TA_CUDA(cudaMemcpyAsync(evals, dw, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaMemcpyAsync(evecs, dv, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dl); cudaFree(dv); cudaFree(dw);
     return TA_OK;
 }
 
@@ -822,17 +848,16 @@ int ta_inertia_eig(ta_ctx* ctx, const double* cov, uint64_t n, double* evals, do
     if (!cov || !evals || !evecs) return fail(ctx, TA_ERR_BAD_ARG, "null argument");
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    double *dc = nullptr, *dv = nullptr, *dw = nullptr;
-    TA_CUDA(cudaMalloc((void**)&dc, n * 6 * sizeof(double)));
-    TA_CUDA(cudaMalloc((void**)&dw, n * 3 * sizeof(double)));
-    TA_CUDA(cudaMalloc((void**)&dv, n * 9 * sizeof(double)));
-    TA_CUDA(cudaMemcpyAsync(dc, cov, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-    ta::inertia_eig_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dc, n, dw, dv);
+    TaDevBuf dc, dw, dv;
+    TA_CUDA(cudaMalloc(&dc.p, n * 6 * sizeof(double)));
+    TA_CUDA(cudaMalloc(&dw.p, n * 3 * sizeof(double)));
+    TA_CUDA(cudaMalloc(&dv.p, n * 9 * sizeof(double)));
+    TA_CUDA(cudaMemcpyAsync(dc.p, cov, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    ta::inertia_eig_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dc.as<double>(), n, dw.as<double>(), dv.as<double>());
     ctx->launches++;
-    TA_CUDA(cudaMemcpyAsync(evals, dw, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TA_CUDA(cudaMemcpyAsync(evecs, dv, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaMemcpyAsync(evals, dw.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaMemcpyAsync(evecs, dv.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dc); cudaFree(dv); cudaFree(dw);
     return TA_OK;
 }
 
@@ -882,10 +907,11 @@ int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)ctx->nf * ctx->nm * ctx->ns;
-    void *d_lut = nullptr, *d_out = nullptr;
-    TA_CUDA(cudaMalloc(&d_lut, n_lut * lut_elem_bytes));
+    TaDevBuf lut_buf, out_buf;
+    TA_CUDA(cudaMalloc(&lut_buf.p, n_lut * lut_elem_bytes));
+    TA_CUDA(cudaMalloc(&out_buf.p, n * lut_elem_bytes));
+    void *d_lut = lut_buf.p, *d_out = out_buf.p;
     TA_CUDA(cudaMemcpyAsync(d_lut, lut_host, n_lut * lut_elem_bytes, cudaMemcpyHostToDevice, st));
-    TA_CUDA(cudaMalloc(&d_out, n * lut_elem_bytes));
     const int grid = ctx->num_sms * 16;
     if (ctx->elem == 2 && lut_elem_bytes == 2)
         ta::map_labels_kernel<uint16_t, uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)ctx->vol, (uint16_t*)d_out, (const uint16_t*)d_lut, n_lut, (uint16_t)fill, n);
@@ -903,7 +929,6 @@ int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_
     }
     if (out_host) TA_CUDA(cudaMemcpyAsync(out_host, d_out, n * lut_elem_bytes, cudaMemcpyDeviceToHost, st));
     TA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_lut); cudaFree(d_out);
     return TA_OK;
 }
 
@@ -968,10 +993,11 @@ int ta_synth_voronoi(ta_ctx* ctx, void* device_out, int elem_bytes, int64_t n_fa
     for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (uint32_t i = 0; i < ncell; ++i) order[fill[binof[i]]++] = (int)i;
-    int *d_start = nullptr, *d_order = nullptr, *d_seeds = nullptr;
-    TA_CUDA(cudaMalloc((void**)&d_start, (nb + 1) * sizeof(int)));
-    TA_CUDA(cudaMalloc((void**)&d_order, ncell * sizeof(int)));
-    TA_CUDA(cudaMalloc((void**)&d_seeds, (size_t)ncell * 3 * sizeof(int)));
+    TaDevBuf b_start, b_order, b_seeds;
+    TA_CUDA(cudaMalloc(&b_start.p, (nb + 1) * sizeof(int)));
+    TA_CUDA(cudaMalloc(&b_order.p, ncell * sizeof(int)));
+    TA_CUDA(cudaMalloc(&b_seeds.p, (size_t)ncell * 3 * sizeof(int)));
+    int *d_start = b_start.as<int>(), *d_order = b_order.as<int>(), *d_seeds = b_seeds.as<int>();
     TA_CUDA(cudaMemcpyAsync(d_start, start.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     TA_CUDA(cudaMemcpyAsync(d_order, order.data(), ncell * sizeof(int), cudaMemcpyHostToDevice, st));
     TA_CUDA(cudaMemcpyAsync(d_seeds, seeds_host, (size_t)ncell * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -983,7 +1009,6 @@ int ta_synth_voronoi(ta_ctx* ctx, void* device_out, int elem_bytes, int64_t n_fa
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     TA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_start); cudaFree(d_order); cudaFree(d_seeds);
     return TA_OK;
 }
 

@@ -10,6 +10,16 @@
 
 typedef unsigned long long u64;
 
+// Host side: a temporary device buffer that is freed when its scope ends, on the error paths too (TA_CUDA returns early).
+struct TaDevBuf {
+    void* p = nullptr;
+    TaDevBuf() {}
+    TaDevBuf(const TaDevBuf&) = delete;
+    TaDevBuf& operator=(const TaDevBuf&) = delete;
+    ~TaDevBuf() { if (p) cudaFree(p); }
+    template <typename U> U* as() const { return static_cast<U*>(p); }
+};
+
 // inline PTX goes through this macro so that the CPU emulation of the kernels (tests/host/emu) can compile them with g++
 #ifndef TA_PTX
 #define TA_PTX(...) asm volatile(__VA_ARGS__)

@@ -89,6 +89,26 @@ __global__ void merge_records_deferred_kernel(PairTable pt, const uint32_t* all,
     }
 }
 
+// fetch layouts, made on the device so that the host side is plain copies into the caller's arrays
+__global__ void interleave_boxes_kernel(const int* __restrict__ bmin, const int* __restrict__ bmax, size_t n, int* __restrict__ bbox) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n * 3; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / 3, a = i - row * 3;
+        bbox[row * 6 + a] = bmin[i];
+        bbox[row * 6 + 3 + a] = bmax[i];
+    }
+}
+// packed records [n][9] -> lo[n] | hi[n] | faces[n][6] | wall18[n] in one scratch block
+__global__ void split_records_kernel(const uint32_t* __restrict__ rec, size_t n, uint32_t* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t* r = rec + i * REC_WORDS;
+        out[i] = r[0];
+        out[n + i] = r[1];
+#pragma unroll
+        for (int f = 0; f < 6; ++f) out[2 * n + i * 6 + f] = r[2 + f];
+        out[8 * n + i] = r[8];
+    }
+}
+
 // sum-merge packed records (from all ranks) into a cleared hash
 __global__ void merge_records_kernel(PairTable pt, const uint32_t* rec, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

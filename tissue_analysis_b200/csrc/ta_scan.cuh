@@ -107,6 +107,7 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     if (!done) ta_emu_yield();
     return done;
 }
+inline u64 ta_globaltimer() { return 0ull; }
 inline void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     EmuTmap m;
     memcpy(&m, map, sizeof m);
@@ -136,6 +137,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
     return done != 0u;
+}
+__device__ __forceinline__ u64 ta_globaltimer() {       // nanoseconds
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void tma_load_box_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     TA_PTX("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -575,19 +581,31 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             // spin in try_wait can starve the one lane the barrier is waiting for (seen as a lost copy with
             // TA_PHASE_TIMING=1).  Converge the warp first.
             __syncwarp();
+            // A lost copy must not hang the box.  The limit is wall time (5 s of %globaltimer, looked at every 4096
+            // polls), not a poll count -- a time-sliced or debugged GPU polls for a long time without anything being wrong
+            // -- and the failure is REPORTED, not trapped: every thread of the CTA waits on this barrier, so every thread
+            // sees the time-out and leaves the kernel; the host finds the diagnostic (P.diag, host-mapped) after the
+            // pass, returns TA_ERR_CUDA with its text and the context stays usable (no sticky error).
             unsigned spins = 0;
+            u64 t_first = 0ull;
+            bool lost = false;
             while (!mbar_try_wait(tma_bar, tma_parity)) {
-                if (++spins > (1u << 18)) {                  // ~1 s: a lost copy must not hang the box; fail loudly
-                    if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
-                        P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
-                        P.diag[2] = ((u64)iter << 32) | (u64)brick;
-                        P.diag[3] = ((u64)tma_parity << 32) | (u64)sh.ctr[6 + ((iter + 1u) & 1u)];
-                        P.diag[4] = *reinterpret_cast<volatile u64*>(tma_bar);
-                        P.diag[5] = ((u64)(uint32_t)(F0 - SEG) << 32) | ((u64)(uint32_t)(M0 - 1) << 16) | (u64)(uint32_t)(S0 - 1);
-                        __threadfence_system();
-                    }
-                    __trap();
+                if ((++spins & 0xFFFu) == 0u) {
+                    const u64 now = ta_globaltimer();
+                    if (t_first == 0ull) t_first = now;
+                    else if (now - t_first > 5000000000ull) { lost = true; break; }
                 }
+            }
+            if (lost) {
+                if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
+                    P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
+                    P.diag[2] = ((u64)iter << 32) | (u64)brick;
+                    P.diag[3] = ((u64)tma_parity << 32) | (u64)sh.ctr[6 + ((iter + 1u) & 1u)];
+                    P.diag[4] = *reinterpret_cast<volatile u64*>(tma_bar);
+                    P.diag[5] = ((u64)(uint32_t)(F0 - SEG) << 32) | ((u64)(uint32_t)(M0 - 1) << 16) | (u64)(uint32_t)(S0 - 1);
+                    __threadfence_system();
+                }
+                return;
             }
             tma_parity ^= 1u;
             // Elements outside the buffer arrive as zeros; the tile wants them clamped (replicated edge voxels).  Only

@@ -113,10 +113,10 @@ inline int wall_voxel_coords_impl(const void* vol, int elem, long long nf, long 
     }
     const size_t nk = skeys.size();
     VolDims D{nf, nm, ns, own_lo, own_hi, slow_offset};
-    u64 *d_keys = nullptr, *d_counts = nullptr, *d_cursor = nullptr;
-    TA2_CUDA(cudaMalloc((void**)&d_keys, nk * sizeof(u64)));
-    TA2_CUDA(cudaMalloc((void**)&d_counts, (nk + 1) * sizeof(u64)));
-    d_cursor = d_counts + nk;
+    TaDevBuf b_keys, b_counts, b_rec0, b_rec1, b_off, b_xyz, b_tmp;        // freed on every way out
+    TA2_CUDA(cudaMalloc(&b_keys.p, nk * sizeof(u64)));
+    TA2_CUDA(cudaMalloc(&b_counts.p, (nk + 1) * sizeof(u64)));
+    u64 *d_keys = b_keys.as<u64>(), *d_counts = b_counts.as<u64>(), *d_cursor = d_counts + nk;
     TA2_CUDA(cudaMemcpyAsync(d_keys, skeys.data(), nk * sizeof(u64), cudaMemcpyHostToDevice, st));
     TA2_CUDA(cudaMemsetAsync(d_counts, 0, (nk + 1) * sizeof(u64), st));
     const int grid = num_sms * 16;
@@ -133,23 +133,23 @@ inline int wall_voxel_coords_impl(const void* vol, int elem, long long nf, long 
     TA2_CUDA(cudaMemcpyAsync(kcount.data(), d_counts, nk * sizeof(u64), cudaMemcpyDeviceToHost, st));
     TA2_CUDA(cudaStreamSynchronize(st));
     for (size_t i = 0; i < npairs; ++i) counts[i] = kcount[rank_of[i]];
-    if (!xyz) { cudaFree(d_keys); cudaFree(d_counts); return TA_OK; }
+    if (!xyz) return TA_OK;
 
     // unique-key blocks in rank order on the device; caller blocks follow the caller's pair order
     std::vector<u64> koff(nk + 1, 0);
     for (size_t r = 0; r < nk; ++r) koff[r + 1] = koff[r] + kcount[r];
     const u64 total = koff[nk];
     int rc = TA_OK;
-    u64 *d_rec[2] = {nullptr, nullptr}, *d_off = nullptr;
-    long long* d_xyz = nullptr;
-    void* d_tmp = nullptr;
     if (total > 0) {
         if ((double)nk * (double)lin_span > 9.0e18) { *err = "too many pairs x voxels for one coordinate pass"; rc = TA_ERR_BAD_ARG; }
         if (!rc) {
-            TA2_CUDA(cudaMalloc((void**)&d_rec[0], total * sizeof(u64)));
-            TA2_CUDA(cudaMalloc((void**)&d_rec[1], total * sizeof(u64)));
-            TA2_CUDA(cudaMalloc((void**)&d_off, (nk + 1) * sizeof(u64)));
-            TA2_CUDA(cudaMalloc((void**)&d_xyz, total * 3 * sizeof(long long)));
+            TA2_CUDA(cudaMalloc(&b_rec0.p, total * sizeof(u64)));
+            TA2_CUDA(cudaMalloc(&b_rec1.p, total * sizeof(u64)));
+            TA2_CUDA(cudaMalloc(&b_off.p, (nk + 1) * sizeof(u64)));
+            TA2_CUDA(cudaMalloc(&b_xyz.p, total * 3 * sizeof(long long)));
+            u64* d_rec[2] = {b_rec0.as<u64>(), b_rec1.as<u64>()};
+            u64* d_off = b_off.as<u64>();
+            long long* d_xyz = b_xyz.as<long long>();
             TA2_CUDA(cudaMemcpyAsync(d_off, koff.data(), (nk + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
             if (elem == 2)
                 wall_voxels_kernel<uint16_t, 1><<<grid, 256, 0, st>>>((const uint16_t*)vol, D, d_keys, (long long)nk,
@@ -160,8 +160,8 @@ inline int wall_voxel_coords_impl(const void* vol, int elem, long long nf, long 
             (*launches)++;
             size_t need = 0;
             TA2_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, d_rec[0], d_rec[1], (long long)total, 0, 64, st));
-            TA2_CUDA(cudaMalloc(&d_tmp, need));
-            TA2_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_rec[0], d_rec[1], (long long)total, 0, 64, st));
+            TA2_CUDA(cudaMalloc(&b_tmp.p, need));
+            TA2_CUDA(cub::DeviceRadixSort::SortKeys(b_tmp.p, need, d_rec[0], d_rec[1], (long long)total, 0, 64, st));
             decode_wall_voxels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_rec[1], total, lin_span, nf, nm,
                                                                                        d_off, d_counts, d_xyz);
             (*launches)++;
@@ -176,8 +176,6 @@ inline int wall_voxel_coords_impl(const void* vol, int elem, long long nf, long 
             }
         }
     }
-    cudaFree(d_keys); cudaFree(d_counts); cudaFree(d_rec[0]); cudaFree(d_rec[1]); cudaFree(d_off);
-    cudaFree(d_xyz); cudaFree(d_tmp);
     return rc;
 }
 
@@ -257,8 +255,9 @@ __global__ void stencil_image_kernel(const T* __restrict__ vol, T* __restrict__ 
 inline int stencil_image_impl(const void* vol, int elem, long long nf, long long nm, long long ns, int kind,
                               void* out_host, cudaStream_t st, int num_sms, uint64_t* launches, std::string* err) {
     const size_t bytes = (size_t)nf * nm * ns * elem;
-    void* d_out = nullptr;
-    TA2_CUDA(cudaMalloc(&d_out, bytes));
+    TaDevBuf out_buf;
+    TA2_CUDA(cudaMalloc(&out_buf.p, bytes));
+    void* d_out = out_buf.p;
     VolDims D{nf, nm, ns, 0, ns, 0};
     const int grid = num_sms * 16;
     if (elem == 2) {
@@ -275,7 +274,6 @@ inline int stencil_image_impl(const void* vol, int elem, long long nf, long long
     (*launches)++;
     TA2_CUDA(cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
     TA2_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_out);
     return TA_OK;
 }
 
@@ -283,8 +281,9 @@ inline int voxel_first_layer_impl(const void* vol, int elem, long long nf, long 
                                   uint32_t background, int keep_background, void* out_host, cudaStream_t st,
                                   int num_sms, uint64_t* launches, std::string* err) {
     const size_t bytes = (size_t)nf * nm * ns * elem;
-    void* d_out = nullptr;
-    TA2_CUDA(cudaMalloc(&d_out, bytes));
+    TaDevBuf out_buf;
+    TA2_CUDA(cudaMalloc(&out_buf.p, bytes));
+    void* d_out = out_buf.p;
     VolDims D{nf, nm, ns, 0, ns, 0};
     if (elem == 2)
         voxel_first_layer_kernel<uint16_t><<<num_sms * 16, 256, 0, st>>>((const uint16_t*)vol, (uint16_t*)d_out, D,
@@ -295,7 +294,6 @@ inline int voxel_first_layer_impl(const void* vol, int elem, long long nf, long 
     (*launches)++;
     TA2_CUDA(cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
     TA2_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_out);
     return TA_OK;
 }
 
