@@ -10,8 +10,9 @@ static unsigned long long g_user_stat[16];
 #define TA_STAT(which, n) (g_user_stat[which] += (unsigned long long)(n))
 
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_scan_mask.cuh"
 
-namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; }
+namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; namespace mk { alignas(128) unsigned char smem_raw[160 * 1024]; } }
 void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
 
 using namespace ta;
@@ -51,8 +52,8 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
-enum Which { PRODUCT, NWHICH };
-static const char* which_name[] = {"scan_kernel<T,false>"};
+enum Which { PRODUCT, MASK, NWHICH };
+static const char* which_name[] = {"scan_kernel<T,false>", "mk::mask_kernel<T>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -103,18 +104,21 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     P.vol = vol.data(); P.nf = nf; P.nm = nm; P.ns = nbuf; P.own_lo = own_lo; P.own_hi = own_hi; P.slow_offset = slow_offset;
     const int seg = 16 / (int)sizeof(T);
     P.nbf = (nf + NFS * seg - 1) / (NFS * seg); P.nbm = (nm + BM - 1) / BM; P.nbs = (own_hi - own_lo + BS - 1) / BS;
+    if (which == MASK) { P.nbf = (nf + mk::RW - 1) / mk::RW; P.nbm = (nm + mk::OM - 1) / mk::OM; P.nbs = (own_hi - own_lo + mk::ZB - 1) / mk::ZB; }
     P.flags = 7u; P.vec_ok = 0; P.use_tma = use_tma; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     {
         // what ta_api.cu encodes for the kernels: the bound buffer, one box = tile (brick + halo)
         ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), ROWV * seg, BM + 2, BS + 2};
+        if (which == MASK) { em.box0 = mk::Geo<T>::TRE; em.box1 = mk::TM; em.box2 = mk::TP; }
         static_assert(sizeof(ta::EmuTmap) <= sizeof(CUtensorMap), "the emulated map lives in the bytes of the real one");
         memcpy(&tmap, &em, sizeof em);
     }
     bool ok = true;
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
-        ok = emu::run_block(block, 2, NTHREADS, [&]() {
+        if (which == MASK) ok = emu::run_block(block, 2, mk::NTHREADS, [&]() { mk::mask_kernel<T>(P, lt, pt, tmap); });
+        else ok = emu::run_block(block, 2, NTHREADS, [&]() {
             scan_kernel<T, false>(P, lt, pt, tmap);
         });
     }

@@ -13,6 +13,7 @@
 #include "ta_common.cuh"
 #include "ta_kernels.cuh"
 #include "ta_scan.cuh"
+#include "ta_scan_mask.cuh"
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -96,6 +97,16 @@ template <typename P> static int ensure(ta_ctx* ctx, P** ptr, size_t* have, size
 // The scan kernel's instantiations: label width, and -- only in a -DTA_WITH_PHASE_TIMING build -- the phase clocks
 // (TA_PHASE_TIMING=1).  The product library carries the two kernels it launches and nothing else.
 typedef void (*scan_kernel_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
+// TA_SCAN_KERNEL=brick selects the round-1 worklist kernel (scan_kernel, ta_scan.cuh); the default is the bit-mask kernel
+// (mk::mask_kernel, ta_scan_mask.cuh).  Both fill the same tables.
+static bool use_mask_kernel() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TA_SCAN_KERNEL"); v = (e && !strcmp(e, "brick")) ? 0 : 1; }
+    return v == 1;
+}
+static scan_kernel_fn mask_kernel_variant(int elem) {
+    return elem == 2 ? ta::mk::mask_kernel<uint16_t> : ta::mk::mask_kernel<uint32_t>;
+}
 static scan_kernel_fn scan_kernel_variant(int elem, bool timing) {
 #ifdef TA_WITH_PHASE_TIMING
     if (timing) return elem == 2 ? ta::scan_kernel<uint16_t, true> : ta::scan_kernel<uint32_t, true>;
@@ -149,6 +160,10 @@ int ta_ctx_create(ta_ctx** out, int device) {
             TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, tm != 0),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
+    TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ta::mk::smem_bytes<uint16_t>()));
+    TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(4), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ta::mk::smem_bytes<uint32_t>()));
     guard.c = nullptr;
     *out = ctx;
     return TA_OK;
@@ -366,7 +381,7 @@ typedef CUresult (*ta_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map, int rowv = ta::ROWV) {
+static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map, bool mask_geometry) {
     static ta_encode_tiled_fn encode = nullptr;
     static bool looked = false;
     if (!looked) {
@@ -383,7 +398,8 @@ static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map, int rowv = ta::ROWV) {
     const int seg = 16 / ctx->elem;
     const cuuint64_t dims[3] = {(cuuint64_t)ctx->nf, (cuuint64_t)ctx->nm, (cuuint64_t)ctx->ns};
     const cuuint64_t strides[2] = {(cuuint64_t)ctx->nf * ctx->elem, (cuuint64_t)ctx->nf * ctx->nm * ctx->elem};
-    const cuuint32_t box[3] = {(cuuint32_t)(rowv * seg), (cuuint32_t)(ta::BM + 2), (cuuint32_t)(ta::BS + 2)};
+    cuuint32_t box[3] = {(cuuint32_t)(ta::ROWV * seg), (cuuint32_t)(ta::BM + 2), (cuuint32_t)(ta::BS + 2)};
+    if (mask_geometry) { box[0] = (cuuint32_t)(ta::mk::RW + 2 * seg); box[1] = (cuuint32_t)ta::mk::TM; box[2] = (cuuint32_t)ta::mk::TP; }
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, ctx->elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
                         const_cast<void*>(ctx->vol), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -395,11 +411,21 @@ static bool make_tile_map(ta_ctx* ctx, CUtensorMap* map, int rowv = ta::ROWV) {
 static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long long own_lo, long long own_hi) {
     cudaStream_t st = ctx->stream;
     P.own_lo = own_lo; P.own_hi = own_hi;
-    P.nbs = (int)((own_hi - own_lo + ta::BS - 1) / ta::BS);
+    const bool mask = use_mask_kernel();
+    P.nbs = (int)((own_hi - own_lo + ta::BS - 1) / ta::BS);         // BS == mk::ZB
     const size_t total = (size_t)P.nbf * P.nbm * P.nbs;
     if (total > 0xFFFFFFF0ull) return fail(ctx, TA_ERR_BAD_ARG, "volume too large for one pass");
     if (total == 0) return TA_OK;
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
+    if (mask) {
+        const int per_sm = ctx->elem == 2 ? 3 : 2;
+        const int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * per_sm);
+        const size_t smem = ctx->elem == 2 ? ta::mk::smem_bytes<uint16_t>() : ta::mk::smem_bytes<uint32_t>();
+        mask_kernel_variant(ctx->elem)<<<grid, ta::mk::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
+        ctx->launches++;
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const size_t smem = ctx->elem == 2 ? ta::scan_smem_bytes<uint16_t>() : ta::scan_smem_bytes<uint32_t>();
     scan_kernel_variant(ctx->elem, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
@@ -479,11 +505,15 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
     P.nbf = (int)((ctx->nf + BF - 1) / BF);
     P.nbm = (int)((ctx->nm + ta::BM - 1) / ta::BM);
     P.nbs = (int)((ctx->own_hi - ctx->own_lo + ta::BS - 1) / ta::BS);
+    if (use_mask_kernel()) {
+        P.nbf = (int)((ctx->nf + ta::mk::RW - 1) / ta::mk::RW);
+        P.nbm = (int)((ctx->nm + ta::mk::OM - 1) / ta::mk::OM);
+    }
     P.flags = flags;
     P.vec_ok = ((ctx->nf % seg) == 0) && (((uintptr_t)ctx->vol & 15) == 0);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    P.use_tma = (P.vec_ok && !getenv("TA_NO_TMA") && make_tile_map(ctx, &tmap)) ? 1 : 0;
+    P.use_tma = (P.vec_ok && !getenv("TA_NO_TMA") && make_tile_map(ctx, &tmap, use_mask_kernel())) ? 1 : 0;
     P.brick_counter = &ctx->counters[0];
     if (!ctx->diag_host) {
         if (cudaHostAlloc((void**)&ctx->diag_host, 8 * sizeof(u64), cudaHostAllocMapped) == cudaSuccess) {
