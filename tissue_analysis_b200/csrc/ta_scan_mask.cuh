@@ -4,23 +4,24 @@
 // words, warp-uniform, without worklists.
 //
 // Work unit: a brick of RW x OM x ZB = 32 x 30 x 8 voxels, staged with a one-voxel halo as ONE TMA box of
-// (32 + 2 segments of 16 bytes) x 32 rows x 10 planes.  One warp per tile plane, one lane per tile row (lanes 0 and 31 are
-// the halo rows, planes 0 and 9 the halo planes).
+// (32 + 2 segments of 16 bytes) x 32 rows x 10 planes = 320 tile rows of 32 (+ 2 halo) voxels.  A lane owns a row.
 //
-//   P1  plane warp p discovers the labels of its plane tile (34 x 32 voxels): the lane rows are held in registers; the
-//       leader of the still uncovered voxels names a label L, every lane compares its row with L (VIADDMNMX.U16x2: packed
-//       subtract + min 1, then one IMAD per word gathers the bits) and stores (own, halo) = 32 + 2 bits in shared memory:
-//       masks[p][slot][lane].  The labels of a plane sit in lists[p][slot], slot < K.  More than K labels in one plane
-//       tile (noise, never tissue): the whole brick takes the per-voxel path G below.
+//   P1  warp w takes a block of 16 rows x 2 planes of the tile (compact blocks see few labels: ~4 on C3, a whole plane
+//       sees ~7).  The lane rows are held in registers; the leader of the still uncovered voxels names a label L, the warp
+//       looks it up in the brick's label list (blab[K], lock-free append), every lane compares its row with L
+//       (VIADDMNMX.U16x2: packed subtract + min 1, then one IMAD per word gathers the bits) and stores
+//       masks[plane][slot][row] = (32 own bits, 2 halo bits).  Slots the block has not seen are stored as zero, and
+//       pres[plane][row] keeps the slots that are not.  More than K labels in one brick (noise, never tissue): the whole
+//       brick takes the per-voxel path G.
 //   --  barrier; the tile is dead now: thread 0 issues the NEXT brick's box copy, it lands under P2.
-//   P2  plane warp p (owned planes) for every label b of planes p-1, p, p+1:
-//         D_b = dilation of b by the 18-neighbourhood, restricted to row `lane` of plane p -- ORs of the nine row masks
-//               around, two shifts for the f direction; Bf / Bm / Bs = b as the +f / +m / +s neighbour;
-//         for every label a of plane p that meets D_b somewhere in the warp:
-//               wall18 += popc(M_a & D_b), faces += popc(M_a & Bf), popc(M_a & Bm), popc(M_a & Bs)    (a is the lower voxel)
-//               two full-mask redux per (a, b); the results wait in one lane each and go to the per-brick pair table in one
-//               SIMT pass.
-//       Moments: per label of the plane n = popc(M), closed forms for sum f, sum f^2 of a run of bits, 5 redux, bounds from
+//   P2  warp w < 8 takes a block of 15 owned rows x 2 owned planes.  For every label b present in the rows around the
+//       block (redux.or of the row presence words):
+//         D_b = dilation of b by the 18-neighbourhood, restricted to the lane's row -- ORs of the nine row masks around,
+//               two shifts for the f direction; Bf / Bm / Bs = b as the +f / +m / +s neighbour;
+//         the labels a of the block that meet D_b somewhere (16 masks in registers, one LOP3 + one predicated OR each,
+//         one redux.or) get wall18 += popc(M_a & D_b), faces += popc(M_a & Bf), popc(M_a & Bm), popc(M_a & Bs), two
+//         full-mask redux per (a, b); the results wait in one lane each and go to the per-brick pair table in one SIMT pass.
+//       Moments: per label of the block n = popc(M), closed forms for sum f, sum f^2 of a run of bits, 6 redux, bounds from
 //       redux.or / ballot, one lane per label updates the per-brick label table.
 //   G   (rare) every voxel of the brick against its 18 neighbours, straight from the tile.
 //   F   flush the per-brick tables (brick-local u32 sums -> shifted u64 global REDs; pair slots -> global hash).
@@ -38,7 +39,10 @@ constexpr int TM = 32;                    // tile rows = lanes
 constexpr int ZB = 8;                     // owned planes per brick
 constexpr int TP = ZB + 2;                // tile planes = warps
 constexpr int NTHREADS = TP * 32;
-constexpr int K = 14;                     // label slots per plane tile
+constexpr int K = 24;                     // label slots per brick
+constexpr int KB = 12;                    // labels of a P2 block held in registers at a time
+constexpr int NW2 = 8;                    // warps with a P2 block (15 rows x 2 planes each)
+constexpr int MPLANE = K * 32 + 16;       // mask words per tile plane; + 16: the two half-warps of a P2 block (planes q, q + 1) use different banks
 
 template <typename T> struct Geo {
     static constexpr int HV = 16 / (int)sizeof(T);       // halo elements per side (one 16-byte segment)
@@ -50,8 +54,8 @@ template <typename T> struct Geo {
 };
 
 template <typename T> constexpr size_t smem_bytes() {
-    return (size_t)Geo<T>::TILE_BYTES + (size_t)TP * K * 32 * 8 + (size_t)TP * 32 * 4 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 +
-           PT_SLOTS * PT_WORDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + 32 * 4 + 16 * 8 + 128;
+    return (size_t)Geo<T>::TILE_BYTES + (size_t)TP * MPLANE * 4 + (size_t)3 * TP * 32 * 4 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 +
+           PT_SLOTS * PT_WORDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + 96 * 4 + 16 * 8 + 128;
 }
 
 // ---- packed compares ---------------------------------------------------------------------------------------------------
@@ -154,24 +158,28 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     constexpr int HV = G::HV, TRE = G::TRE, NW = G::NW, ROWV = G::ROWV;
     constexpr int PLANEE = TM * TRE;
     constexpr uint32_t FULL = 0xffffffffu;
+    static_assert(K <= 32 && 5 * KB <= 64, "lane l looks at blab[l]; the slots of a round are packed 5 bits each");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
     uint4* tilev = reinterpret_cast<uint4*>(smem_raw);
-    uint2* masks = reinterpret_cast<uint2*>(smem_raw + G::TILE_BYTES);                  // [TP][K][32]
-    uint32_t* lists = reinterpret_cast<uint32_t*>(masks + TP * K * 32);                  // [TP][32]
+    uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + G::TILE_BYTES);            // [TP][MPLANE]: own bits of (slot, row)
+    uint32_t* pres = masks + TP * MPLANE;                                                // [TP][32]: slots with a bit in the row
+    uint32_t* hwl = pres + TP * 32;                                                      // [TP][32]: slots in the left halo voxel of the row
+    uint32_t* hwr = hwl + TP * 32;                                                       // [TP][32]: slots in the right halo voxel
     BrickShared<T> sh{};
-    sh.lt_key = lists + TP * 32;
+    sh.lt_key = hwr + TP * 32;
     sh.lt_val = sh.lt_key + LT_SLOTS;
     sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
     sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
-    // ctr: [0..1] brick index ping-pong, [2] overflow flag of the brick, [4..5] mbarrier, [8 + p] label count of plane p
+    // ctr: [0..1] brick index ping-pong, [2..3] overflow flag ping-pong, [4..5] mbarrier, [8..10] / [12..14] brick origin
+    // ping-pong, [16 .. 16 + 2 K) the brick's label list, ping-pong
     unsigned int* ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
-    Carry* carry = reinterpret_cast<Carry*>(ctr + 32);
+    Carry* carry = reinterpret_cast<Carry*>(ctr + 16 + 2 * K + (2 * K) % 2 + 16);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int p = tid >> 5;                     // tile plane of this warp
+    const int warp = tid >> 5;
     const T* vol = reinterpret_cast<const T*>(P.vol);
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
     const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
@@ -185,6 +193,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     }
     for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
     for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
+    if (tid < 2 * K) ctr[16 + tid] = TA_EMPTY32;
 
     uint64_t* tma_bar = reinterpret_cast<uint64_t*>(ctr + 4);
     uint32_t tma_parity = 0u;
@@ -195,35 +204,43 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             TA_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         carry->valid = 0u;
-        ctr[2] = 0u;
+        ctr[2] = 0u; ctr[3] = 0u;
     }
 
-    auto brick_origin = [&](unsigned int brick, int& F0, int& M0, int& S0) {
-        const int bf = brick % P.nbf, bm = (brick / P.nbf) % P.nbm, bs = brick / (P.nbf * P.nbm);
-        F0 = bf * RW; M0 = bm * OM; S0 = (int)P.own_lo + bs * ZB;
+    // thread 0: origin of a brick into its ping-pong slot (the divisions are made once per brick, not once per thread)
+    auto set_origin = [&](unsigned int brick, unsigned which) {
+        const unsigned bf = brick % (unsigned)P.nbf, rest = brick / (unsigned)P.nbf;
+        const unsigned bm = rest % (unsigned)P.nbm, bs = rest / (unsigned)P.nbm;
+        ctr[8 + 4 * which] = bf * RW; ctr[9 + 4 * which] = bm * OM; ctr[10 + 4 * which] = (unsigned)((int)P.own_lo + (int)bs * ZB);
     };
-    auto issue_box = [&](unsigned int brick) {          // thread 0, after a barrier that ended every read of the tile
-        int F0, M0, S0;
-        brick_origin(brick, F0, M0, S0);
+    auto issue_box = [&](unsigned which) {          // thread 0, after a barrier that ended every read of the tile
         TA_PTX("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(tma_bar, (uint32_t)G::TILE_BYTES);
-        tma_load_box_3d(tile, &tmap, tma_bar, F0 - HV, M0 - 1, S0 - 1);
+        tma_load_box_3d(tile, &tmap, tma_bar, (int)ctr[8 + 4 * which] - HV, (int)ctr[9 + 4 * which] - 1, (int)ctr[10 + 4 * which] - 1);
     };
 
     __syncthreads();
     if (tid == 0) {
         const unsigned int b0 = atomicAdd(P.brick_counter, 1u);
         ctr[0] = b0;
-        if (use_tma && b0 < total) issue_box(b0);
+        if (b0 < total) {
+            set_origin(b0, 0u);
+            if (use_tma) issue_box(0u);
+        }
     }
     __syncthreads();
 
     for (unsigned iter = 0;; ++iter) {
-        const unsigned int brick = ctr[iter & 1u];
+        const unsigned cur = iter & 1u, nxt = cur ^ 1u;
+        const unsigned int brick = ctr[cur];
         if (brick >= total) break;
-        if (tid == 0) ctr[(iter + 1u) & 1u] = atomicAdd(P.brick_counter, 1u);
-        int F0, M0, S0;
-        brick_origin(brick, F0, M0, S0);
+        uint32_t* blab = ctr + 16 + K * cur;
+        if (tid == 0) {
+            const unsigned int nb = atomicAdd(P.brick_counter, 1u);
+            ctr[nxt] = nb;
+            if (nb < total) set_origin(nb, nxt);
+        }
+        const int F0 = (int)ctr[8 + 4 * cur], M0 = (int)ctr[9 + 4 * cur], S0 = (int)ctr[10 + 4 * cur];
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
         const int nown = min(ZB, (int)P.own_hi - S0);          // owned planes of this brick: tile planes 1 .. nown
         const int fvalid_n = min(RW, nf - F0);
@@ -246,7 +263,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 if (P.diag && atomicAdd(&P.diag[0], 1ull) == 0ull) {
                     P.diag[1] = ((u64)blockIdx.x << 32) | (u64)tid;
                     P.diag[2] = ((u64)iter << 32) | (u64)brick;
-                    P.diag[3] = ((u64)tma_parity << 32) | (u64)ctr[(iter + 1u) & 1u];
+                    P.diag[3] = ((u64)tma_parity << 32) | (u64)ctr[nxt];
                     P.diag[4] = *reinterpret_cast<volatile u64*>(tma_bar);
                     P.diag[5] = ((u64)(uint32_t)(F0 - HV) << 32) | ((u64)(uint32_t)(M0 - 1) << 16) | (u64)(uint32_t)(S0 - 1);
                     __threadfence_system();
@@ -291,49 +308,73 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             __syncthreads();
         }
 
-        // ---- P1: labels and row masks of plane p ----------------------------------------------------------------------
+        // ---- P1: block of 16 rows x 2 planes: labels -> brick slots, row masks ------------------------------------------
         const uint32_t ref_label = tile[HV];               // plane 0, row 0, first owned column
-        bool one_label = true;                             // this plane: not needed, or all ref_label
-        if (p <= nown + 1) {
-            const T* row = tile + (p * TM + lane) * TRE;
-            uint32_t w[NW];
-            {
-                const uint4* rv = reinterpret_cast<const uint4*>(row + HV);
+        bool one_label = true;                             // this block: not needed, or all ref_label
+        {
+            const int q = 2 * (warp >> 1) + (lane >> 4);   // tile plane of the lane
+            const int r = 16 * (warp & 1) + (lane & 15);   // tile row of the lane
+            if (2 * (warp >> 1) <= nown + 1) {             // the block has a plane somebody needs (uniform per warp)
+                const T* row = tile + (q * TM + r) * TRE;
+                uint32_t w[NW];
+                {
+                    const uint4* rv = reinterpret_cast<const uint4*>(row + HV);
 #pragma unroll
-                for (int q = 0; q < NW / 4; ++q) {
-                    const uint4 v = rv[q];
-                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    for (int x = 0; x < NW / 4; ++x) {
+                        const uint4 v = rv[x];
+                        w[4 * x] = v.x; w[4 * x + 1] = v.y; w[4 * x + 2] = v.z; w[4 * x + 3] = v.w;
+                    }
                 }
+                const uint32_t hl = row[HV - 1], hr = row[HV + RW];
+                uint32_t* mrow = masks + q * MPLANE + r;
+                uint32_t cov = 0u, covh = 0u, mypres = 0u, myhl = 0u, myhr = 0u;
+                int k = 0;
+                bool all_ref = true;
+                for (;;) {
+                    const uint32_t unc = ~cov;
+                    uint32_t cand = hl;
+                    if (unc) cand = row[HV + __ffs(unc) - 1];
+                    else if (covh & 1u) cand = hr;
+                    const unsigned bal = __ballot_sync(FULL, (unc != 0u) || (covh != 3u));
+                    if (!bal) break;
+                    const uint32_t L = __shfl_sync(FULL, cand, __ffs(bal) - 1);
+                    // slot of L in the brick's list: lanes l and l + 16 look at entry l; append with a CAS on the first free entry
+                    int slot = -1;
+                    for (;;) {
+                        const uint32_t e = lane < K ? *((volatile uint32_t*)&blab[lane]) : TA_EMPTY32;
+                        const unsigned hit = __ballot_sync(FULL, e == L);
+                        if (hit) { slot = __ffs(hit) - 1; break; }
+                        const int n = __popc(__ballot_sync(FULL, e != TA_EMPTY32));
+                        if (n >= K) break;
+                        uint32_t old = 0u;
+                        if (lane == 0) old = atomicCAS(&blab[n], TA_EMPTY32, L);
+                        old = __shfl_sync(FULL, old, 0);
+                        if (old == TA_EMPTY32 || old == L) { slot = n; break; }
+                    }
+                    if (slot < 0) { if (lane == 0) ctr[2 + cur] = 1u; break; }
+                    const uint32_t M = RowMask<T>::eq(w, L);
+                    const uint32_t el = (hl == L) ? 1u : 0u, er = (hr == L) ? 1u : 0u;
+                    cov |= M; covh |= el | (er << 1);
+                    mrow[slot * 32] = M;
+                    myhl |= el << slot; myhr |= er << slot;
+                    if (M | el | er) mypres |= 1u << slot;
+                    all_ref = all_ref && (L == ref_label);
+                    ++k;
+                }
+#pragma unroll
+                for (int sl = 0; sl < K; ++sl)
+                    if (!((mypres >> sl) & 1u)) mrow[sl * 32] = 0u;
+                pres[q * 32 + r] = mypres;
+                hwl[q * 32 + r] = myhl; hwr[q * 32 + r] = myhr;
+                one_label = (k == 1) && all_ref;
             }
-            const uint32_t hl = row[HV - 1], hr = row[HV + RW];
-            uint32_t cov = 0u, covh = 0u, mylab = TA_EMPTY32;
-            int k = 0;
-            for (;;) {
-                const uint32_t unc = ~cov;
-                uint32_t cand = hl;
-                if (unc) cand = row[HV + __ffs(unc) - 1];
-                else if (covh & 1u) cand = hr;
-                const unsigned bal = __ballot_sync(FULL, (unc != 0u) || (covh != 3u));
-                if (!bal) break;
-                if (k == K) { if (lane == 0) ctr[2] = 1u; break; }
-                const uint32_t L = __shfl_sync(FULL, cand, __ffs(bal) - 1);
-                const uint32_t M = RowMask<T>::eq(w, L);
-                const uint32_t el = (hl == L) ? 1u : 0u, er = (hr == L) ? 1u : 0u;
-                cov |= M; covh |= el | (er << 1);
-                masks[(p * K + k) * 32 + lane] = make_uint2(M, el | (er << 31));
-                if (lane == k) mylab = L;
-                ++k;
-            }
-            lists[p * 32 + lane] = mylab;
-            if (lane == 0) ctr[8 + p] = (unsigned)k;
-            one_label = (k == 1) && (__shfl_sync(FULL, mylab, 0) == ref_label);
         }
         const bool uniform = __syncthreads_and(one_label) != 0;
-        const bool overflow = ctr[2] != 0u;
-        const unsigned int next_brick = ctr[(iter + 1u) & 1u];
+        const bool overflow = ctr[2 + cur] != 0u;
+        const unsigned int next_brick = ctr[nxt];
         bool box_issued = false;
         if (use_tma && !overflow && next_brick < total) {
-            if (tid == 0) issue_box(next_brick);
+            if (tid == 0) issue_box(nxt);
             box_issued = true;
         }
 
@@ -365,131 +406,141 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 }
             }
         } else if (!overflow) {
-            // ---- P2: owned plane p ---------------------------------------------------------------------------------------
-            if (p >= 1 && p <= nown) {
-                const bool own_row = (lane >= 1) && (lane <= OM) && (M0 + lane - 1 < nm);
+            // ---- P2: block of 15 owned rows x 2 owned planes ---------------------------------------------------------------
+            if (warp < NW2 && 1 + 2 * (warp >> 1) <= nown) {
+                const int wm = warp & 1, s0 = 2 * (warp >> 1);              // s0: brick-local plane of the lower half-warp
+                const int lm = lane & 15, ls = lane >> 4;
+                const bool own_row = (lm < 15) && (s0 + ls < nown) && (M0 + 15 * wm + lm < nm);
+                const int r = own_row ? 1 + 15 * wm + lm : 1;               // idle lanes look at a harmless row
+                const int q = own_row ? 1 + s0 + ls : 1;
                 const uint32_t fm = own_row ? fvalid : 0u;
-                const int kc = (int)ctr[8 + p], kd = (int)ctr[8 + p - 1], ku = (int)ctr[8 + p + 1];
-                const uint32_t Lc = lists[p * 32 + lane], Ld = lists[(p - 1) * 32 + lane], Lu = lists[(p + 1) * 32 + lane];
-                const uint2* mc = masks + (p * K) * 32;
-                const uint2* md = masks + ((p - 1) * K) * 32;
-                const uint2* mu = masks + ((p + 1) * K) * 32;
-                const int lm = max(lane - 1, 0), lp = min(lane + 1, 31);
-                const uint32_t sl = (uint32_t)(p - 1);                     // brick-local plane
+                const uint32_t ml = (uint32_t)(15 * wm + lm);               // brick-local row
+                const uint32_t* mbase = masks + q * MPLANE + r;             // + slot * 32; rows +-1, planes +- MPLANE
+                const uint32_t* hlb = hwl + q * 32 + r;
+                const uint32_t* hrb = hwr + q * 32 + r;
+                const uint32_t hrc1 = hrb[0];
+                // halo slots of the five rows with an f-shifted neighbour
+                const uint32_t hlall = hlb[-1] | hlb[0] | hlb[1] | hlb[-32] | hlb[32], hrall = hrb[-1] | hrc1 | hrb[1] | hrb[-32] | hrb[32];
+                const uint32_t* pbase = pres + q * 32 + r;
+                uint32_t pn = pbase[-33] | pbase[-32] | pbase[-31] | pbase[-1] | pbase[0] | pbase[1] | pbase[31] | pbase[32] | pbase[33];
+                const uint32_t PU = __reduce_or_sync(FULL, own_row ? pn : 0u);       // labels around the block
+                const uint32_t PC = __reduce_or_sync(FULL, own_row ? pbase[0] : 0u);  // labels in the block
 
                 if (do_mom) {
-                    uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, kx = 0, ky = 0;
-                    const uint32_t ml = (uint32_t)(lane - 1);              // brick-local row (owned lanes only matter)
-                    for (int i = 0; i < kc; ++i) {
-                        const uint32_t M = mc[i * 32 + lane].x & fm;
+                    uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, kx = 0, ky = 0, ks = 0;
+                    const uint32_t up = ls ? 0xFFFFFFFFu : 0u;
+                    int idx = 0;
+                    for (uint32_t rest = PC; rest; rest &= rest - 1u, ++idx) {
+                        const int i = __ffs(rest) - 1;
+                        const uint32_t M = mbase[i * 32] & fm;
                         const uint32_t n = (uint32_t)__popc(M);
                         uint32_t sf = 0u, sff = 0u;
                         if (M) bit_moments(M, n, sf, sff);
-                        const uint32_t r1 = __reduce_add_sync(FULL, n | (sf << 10));
-                        const uint32_t r2 = __reduce_add_sync(FULL, n * ml);
+                        const uint32_t nml = n * ml;
+                        const uint32_t r1 = __reduce_add_sync(FULL, n | (sf << 10));                 // n < 2^10, sum f < 2^15
+                        const uint32_t r2 = __reduce_add_sync(FULL, nml | ((sf & up) << 15));        // sum n m < 2^15, upper sum f < 2^14
                         const uint32_t r3 = __reduce_add_sync(FULL, sff);
-                        const uint32_t r4 = __reduce_add_sync(FULL, n * ml * ml);
+                        const uint32_t r4 = __reduce_add_sync(FULL, nml * ml);
                         const uint32_t r5 = __reduce_add_sync(FULL, sf * ml);
+                        const uint32_t r6 = __reduce_add_sync(FULL, (n & up) | ((nml & up) << 10));  // upper n < 2^9, upper sum n m < 2^14
                         const uint32_t rx = __reduce_or_sync(FULL, M);
                         const uint32_t ry = __ballot_sync(FULL, M != 0u);
-                        if (lane == i) { k1 = r1; k2 = r2; k3 = r3; k4 = r4; k5 = r5; kx = rx; ky = ry; }
+                        if (lane == idx) { k1 = r1; k2 = r2; k3 = r3; k4 = r4; k5 = r5; k6 = r6; kx = rx; ky = ry; ks = (uint32_t)i; }
                     }
-                    if (lane < kc && kx) {
-                        const uint32_t n = k1 & 0x3FFu, sf = k1 >> 10;
+                    if (lane < idx && kx) {
+                        const uint32_t n = k1 & 0x3FFu, sf = k1 >> 10, nm_ = k2 & 0x7FFFu, sf1 = k2 >> 15;
+                        const uint32_t n1 = k6 & 0x3FFu, nm1 = k6 >> 10;
+                        const uint32_t rows = (ky | (ky >> 16)) & 0x7FFFu;
+                        const uint32_t u0 = (uint32_t)s0;
                         uint32_t v[LT_FIELDS];
-                        v[0] = n; v[1] = sf; v[2] = k2; v[3] = n * sl; v[4] = k3; v[5] = k5; v[6] = sf * sl;
-                        v[7] = k4; v[8] = k2 * sl; v[9] = n * sl * sl;
-                        v[10] = (uint32_t)__ffs(kx) - 1u; v[11] = (uint32_t)__ffs(ky) - 2u; v[12] = sl;
-                        v[13] = 31u - (uint32_t)__clz(kx); v[14] = 30u - (uint32_t)__clz(ky); v[15] = sl;
-                        label_add<T>(sh, lt, pt.status, Lc, v, gF0, gM0, gS0);
+                        v[0] = n; v[1] = sf; v[2] = nm_; v[3] = u0 * n + n1;
+                        v[4] = k3; v[5] = k5; v[6] = u0 * sf + sf1;
+                        v[7] = k4; v[8] = u0 * nm_ + nm1; v[9] = u0 * u0 * n + (2u * u0 + 1u) * n1;
+                        v[10] = (uint32_t)__ffs(kx) - 1u; v[11] = 15u * wm + (uint32_t)__ffs(rows) - 1u; v[12] = (ky & 0xFFFFu) ? u0 : u0 + 1u;
+                        v[13] = 31u - (uint32_t)__clz(kx); v[14] = 15u * wm + 31u - (uint32_t)__clz(rows); v[15] = (ky >> 16) ? u0 + 1u : u0;
+                        label_add<T>(sh, lt, pt.status, blab[ks], v, gF0, gM0, gS0);
                     }
                 }
 
                 if (do_pairs) {
                     int nres = 0;
-                    uint32_t res_i = 0, res_b = 0, res_1 = 0, res_2 = 0;
+                    uint32_t res_a = 0, res_b = 0, res_1 = 0, res_2 = 0;
                     auto flush_results = [&]() {
                         if (lane < nres) {
-                            const uint32_t a = lists[p * 32 + res_i];
-                            const bool lo = a < res_b;
+                            const uint32_t a = blab[res_a], b = blab[res_b];
+                            const bool lo = a < b;
                             const uint32_t w18 = res_1 & 0xFFFFu, ff = res_1 >> 16, fmm = res_2 & 0xFFFFu, fss = res_2 >> 16;
                             uint32_t inc[PT_WORDS];
                             inc[0] = w18 | (lo ? ff << 16 : 0u);
                             inc[1] = (lo ? 0u : ff) | (lo ? fmm << 16 : 0u);
                             inc[2] = (lo ? 0u : fmm) | (lo ? fss << 16 : 0u);
                             inc[3] = lo ? 0u : fss;
-                            pair_add_packed<T>(sh, pt, Vox<T>::key(a, res_b), inc);
+                            pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
                         }
                         nres = 0;
                     };
-                    const int nb = kc + kd + ku;
-                    for (int jj = 0; jj < nb; ++jj) {
-                        const int src = jj < kc ? 0 : (jj < kc + kd ? 1 : 2);
-                        const int j = jj - (src == 0 ? 0 : (src == 1 ? kc : kc + kd));
-                        const uint32_t b = __shfl_sync(FULL, src == 0 ? Lc : (src == 1 ? Ld : Lu), j);
-                        const int ic = __ffs(__ballot_sync(FULL, Lc == b)) - 1;
-                        if (src >= 1 && ic >= 0) continue;
-                        const int id = __ffs(__ballot_sync(FULL, Ld == b)) - 1;
-                        if (src == 2 && id >= 0) continue;
-                        const int iu = __ffs(__ballot_sync(FULL, Lu == b)) - 1;
-                        uint32_t Mc0 = 0, Mc1 = 0, Mc2 = 0, Hc0 = 0, Hc1 = 0, Hc2 = 0;
-                        uint32_t Md0 = 0, Md1 = 0, Md2 = 0, Hd1 = 0, Mu0 = 0, Mu1 = 0, Mu2 = 0, Hu1 = 0;
-                        if (ic >= 0) {
-                            const uint2* q = mc + ic * 32;
-                            const uint2 x0 = q[lm], x1 = q[lane], x2 = q[lp];
-                            Mc0 = x0.x; Hc0 = x0.y; Mc1 = x1.x; Hc1 = x1.y; Mc2 = x2.x; Hc2 = x2.y;
+                    // rounds of up to KB labels of the block: their own-row masks in registers, their slots packed 5 bits each
+                    for (uint32_t pcr = PC; pcr;) {
+                        uint32_t Ma[KB];
+                        u64 slots = 0ull;
+#pragma unroll
+                        for (int j = 0; j < KB; ++j) {
+                            const int i = pcr ? __ffs(pcr) - 1 : 0;
+                            Ma[j] = pcr ? (mbase[i * 32] & fm) : 0u;
+                            slots |= (u64)i << (5 * j);
+                            pcr &= pcr - 1u;
                         }
-                        if (id >= 0) {
-                            const uint2* q = md + id * 32;
-                            const uint2 x1 = q[lane];
-                            Md0 = q[lm].x; Md1 = x1.x; Hd1 = x1.y; Md2 = q[lp].x;
-                        }
-                        if (iu >= 0) {
-                            const uint2* q = mu + iu * 32;
-                            const uint2 x1 = q[lane];
-                            Mu0 = q[lm].x; Mu1 = x1.x; Hu1 = x1.y; Mu2 = q[lp].x;
-                        }
-                        const uint32_t Y = Mc0 | Mc1 | Mc2 | Md0 | Md1 | Md2 | Mu0 | Mu1 | Mu2;
-                        const uint32_t Pm = Mc0 | Mc1 | Mc2 | Md1 | Mu1;
-                        const uint32_t PH = Hc0 | Hc1 | Hc2 | Hd1 | Hu1;
-                        const uint32_t Dn = (Y | (Pm << 1) | (Pm >> 1) | PH) & fm & ~Mc1;    // not-b voxels with a b in their N18
-                        if (!__ballot_sync(FULL, Dn != 0u)) continue;
-                        const uint32_t Bf = (Mc1 >> 1) | (Hc1 & 0x80000000u);                 // b is the +f neighbour
-                        for (int i = 0; i < kc; ++i) {
-                            if (i == ic) continue;
-                            const uint32_t Ma = mc[i * 32 + lane].x;
-                            const uint32_t t = Ma & Dn;
-                            if (!__ballot_sync(FULL, t != 0u)) continue;
-                            uint32_t c1 = do_w18 ? (uint32_t)__popc(t) : 0u, c2 = 0u;
-                            if (do_p6) {
-                                const uint32_t Mo = Ma & fm;
-                                c1 |= (uint32_t)__popc(Mo & Bf) << 16;
-                                c2 = (uint32_t)__popc(Mo & Mc2) | ((uint32_t)__popc(Mo & Mu1) << 16);
+                        for (uint32_t rest = PU; rest; rest &= rest - 1u) {
+                            const int b = __ffs(rest) - 1;
+                            const uint32_t* qb = mbase + b * 32;
+                            const uint32_t c0 = qb[-1], c1 = qb[0], c2 = qb[1];
+                            const uint32_t d0 = qb[-MPLANE - 1], d1 = qb[-MPLANE], d2 = qb[-MPLANE + 1];
+                            const uint32_t u0 = qb[MPLANE - 1], u1 = qb[MPLANE], u2 = qb[MPLANE + 1];
+                            const uint32_t Y = c0 | c1 | c2 | d0 | d1 | d2 | u0 | u1 | u2;
+                            const uint32_t Pm = c0 | c1 | c2 | d1 | u1;
+                            const uint32_t PH = ((hlall >> b) & 1u) | (((hrall >> b) & 1u) << 31);   // b in a left / right halo voxel of the five rows
+                            const uint32_t Dn = (Y | (Pm << 1) | (Pm >> 1) | PH) & fm & ~c1;          // not-b voxels with a b in their N18
+                            // labels of the round that meet Dn somewhere in the warp (b itself cannot: Dn excludes its voxels)
+                            uint32_t ts = 0u;
+#pragma unroll
+                            for (int j = 0; j < KB; ++j) if (Ma[j] & Dn) ts |= 1u << j;
+                            ts = __reduce_or_sync(FULL, ts);
+                            if (!ts) continue;
+                            const uint32_t Bf = (c1 >> 1) | (((hrc1 >> b) & 1u) << 31);                // b is the +f neighbour
+                            for (; ts; ts &= ts - 1u) {
+                                const int j = __ffs(ts) - 1;
+                                const int i = (int)((slots >> (5 * j)) & 31ull);
+                                const uint32_t Mo = mbase[i * 32] & fm;
+                                uint32_t cnt1 = do_w18 ? (uint32_t)__popc(Mo & Dn) : 0u, cnt2 = 0u;
+                                if (do_p6) {
+                                    cnt1 |= (uint32_t)__popc(Mo & Bf) << 16;
+                                    cnt2 = (uint32_t)__popc(Mo & c2) | ((uint32_t)__popc(Mo & u1) << 16);
+                                }
+                                const uint32_t r1 = __reduce_add_sync(FULL, cnt1);
+                                const uint32_t r2 = __reduce_add_sync(FULL, cnt2);
+                                if (lane == nres) { res_a = (uint32_t)i; res_b = (uint32_t)b; res_1 = r1; res_2 = r2; }
+                                if (++nres == 32) flush_results();
                             }
-                            const uint32_t r1 = __reduce_add_sync(FULL, c1);
-                            const uint32_t r2 = __reduce_add_sync(FULL, c2);
-                            if (lane == nres) { res_i = (uint32_t)i; res_b = b; res_1 = r1; res_2 = r2; }
-                            if (++nres == 32) flush_results();
                         }
                     }
                     flush_results();
                 }
             }
         } else {
-            // ---- G: more than K labels in a plane tile: every owned voxel on its own, straight from the tile -------------
+            // ---- G: more than K labels in the brick: every owned voxel on its own, straight from the tile -------------------
             const int nvo = RW * OM * nown;
             for (int i = tid; i < nvo; i += NTHREADS) {
                 const int f = i % RW, m = (i / RW) % OM, s = i / (RW * OM);
                 if (F0 + f >= nf || M0 + m >= nm) continue;
-                const T* q = tile + ((s + 1) * TM + (m + 1)) * TRE + HV + f;
-                const uint32_t a = q[0];
+                const T* qv = tile + ((s + 1) * TM + (m + 1)) * TRE + HV + f;
+                const uint32_t a = qv[0];
                 if (do_mom) {
                     const uint32_t uf = f, um = m, us = s;
                     uint32_t v[LT_FIELDS] = {1u, uf, um, us, uf * uf, uf * um, uf * us, um * um, um * us, us * us, uf, um, us, uf, um, us};
                     label_add<T>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
                 }
                 if (do_p6) {
-                    const uint32_t n0 = q[1], n1 = q[TRE], n2 = q[PLANEE];
+                    const uint32_t n0 = qv[1], n1 = qv[TRE], n2 = qv[PLANEE];
                     if (n0 != a) pair_add<T>(sh, pt, a, n0, a < n0 ? 0 : 1, 1u);
                     if (n1 != a) pair_add<T>(sh, pt, a, n1, a < n1 ? 2 : 3, 1u);
                     if (n2 != a) pair_add<T>(sh, pt, a, n2, a < n2 ? 4 : 5, 1u);
@@ -497,10 +548,10 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 if (do_w18) {
 #pragma unroll 1
                     for (int k = 0; k < 18; ++k) {
-                        const uint32_t b = q[neighbour_offset<TRE, PLANEE>(k)];
+                        const uint32_t b = qv[neighbour_offset<TRE, PLANEE>(k)];
                         if (b == a) continue;
                         bool seen = false;
-                        for (int kk = 0; kk < k; ++kk) seen |= ((uint32_t)q[neighbour_offset<TRE, PLANEE>(kk)] == b);
+                        for (int kk = 0; kk < k; ++kk) seen |= ((uint32_t)qv[neighbour_offset<TRE, PLANEE>(kk)] == b);
                         if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
                     }
                 }
@@ -534,11 +585,13 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 sh.pt_key[i] = Vox<T>::PEMPTY;
             }
         }
+        // No barrier here: the next brick's P1 touches neither these tables nor this brick's label list (the list and the
+        // overflow flag are ping-pong), and the barrier after it comes before anything that does.
+        if (tid < K) blab[tid] = TA_EMPTY32;
         if (tid == 0) {
-            ctr[2] = 0u;
-            if (use_tma && !box_issued && next_brick < total) issue_box(next_brick);   // after G: the tile was in use until the barrier
+            ctr[2 + cur] = 0u;
+            if (use_tma && !box_issued && next_brick < total) issue_box(nxt);   // after G: the tile was in use until the barrier
         }
-        __syncthreads();
     }
     if (tid == 0 && carry->valid) global_apply(lt, pt.status, carry->label, carry->g, carry->bmn, carry->bmx);
 }
