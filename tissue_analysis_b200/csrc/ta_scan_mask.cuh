@@ -10,8 +10,8 @@
 //       sees ~7).  The lane rows are held in registers; the leader of the still uncovered voxels names a label L, the warp
 //       looks it up in the brick's label list (blab[K], lock-free append), every lane compares its row with L
 //       (VIADDMNMX.U16x2: packed subtract + min 1, then one IMAD per word gathers the bits) and stores
-//       masks[plane][slot][row] = (32 own bits, 2 halo bits).  Slots the block has not seen are stored as zero, and
-//       pres[plane][row] keeps the slots that are not.  More than K labels in one brick (noise, never tissue): the whole
+//       masks[plane][slot][row] = 32 own bits (all masks are zero when P1 starts: the flush clears the slots a brick has
+//       used), hwl / hwr[plane][row] = the slots in the two halo voxels, pres[plane][row] = the slots present in the row.  More than K labels in one brick (noise, never tissue): the whole
 //       brick takes the per-voxel path G.
 //   --  barrier; the tile is dead now: thread 0 issues the NEXT brick's box copy, it lands under P2.
 //   P2  warp w < 8 takes a block of 15 owned rows x 2 owned planes.  For every label b present in the rows around the
@@ -40,7 +40,7 @@ constexpr int ZB = 8;                     // owned planes per brick
 constexpr int TP = ZB + 2;                // tile planes = warps
 constexpr int NTHREADS = TP * 32;
 constexpr int K = 24;                     // label slots per brick
-constexpr int KB = 12;                    // labels of a P2 block held in registers at a time
+constexpr int KB = 8;                     // labels of a P2 block held in registers at a time
 constexpr int NW2 = 8;                    // warps with a P2 block (15 rows x 2 planes each)
 constexpr int MPLANE = K * 32 + 16;       // mask words per tile plane; + 16: the two half-warps of a P2 block (planes q, q + 1) use different banks
 
@@ -194,6 +194,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
     for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
     if (tid < 2 * K) ctr[16 + tid] = TA_EMPTY32;
+    for (int i = tid; i < TP * MPLANE; i += NTHREADS) masks[i] = 0u;       // invariant: every mask is zero when a brick's P1 starts
 
     uint64_t* tma_bar = reinterpret_cast<uint64_t*>(ctr + 4);
     uint32_t tma_parity = 0u;
@@ -361,9 +362,6 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                     all_ref = all_ref && (L == ref_label);
                     ++k;
                 }
-#pragma unroll
-                for (int sl = 0; sl < K; ++sl)
-                    if (!((mypres >> sl) & 1u)) mrow[sl * 32] = 0u;
                 pres[q * 32 + r] = mypres;
                 hwl[q * 32 + r] = myhl; hwr[q * 32 + r] = myhr;
                 one_label = (k == 1) && all_ref;
@@ -371,6 +369,11 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         }
         const bool uniform = __syncthreads_and(one_label) != 0;
         const bool overflow = ctr[2 + cur] != 0u;
+        int nlab;                                              // labels of the brick = mask slots written
+        {
+            const uint32_t e = lane < K ? blab[lane] : TA_EMPTY32;
+            nlab = __popc(__ballot_sync(FULL, e != TA_EMPTY32));
+        }
         const unsigned int next_brick = ctr[nxt];
         bool box_issued = false;
         if (use_tma && !overflow && next_brick < total) {
@@ -587,6 +590,12 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         }
         // No barrier here: the next brick's P1 touches neither these tables nor this brick's label list (the list and the
         // overflow flag are ping-pong), and the barrier after it comes before anything that does.
+        {
+            // back to all-zero masks: every thread clears the slots its own P1 row may have written (the same thread writes
+            // them again in the next P1, so program order is enough)
+            uint32_t* mrow = masks + (2 * (warp >> 1) + (lane >> 4)) * MPLANE + 16 * (warp & 1) + (lane & 15);
+            for (int sl = 0; sl < nlab; ++sl) mrow[sl * 32] = 0u;
+        }
         if (tid < K) blab[tid] = TA_EMPTY32;
         if (tid == 0) {
             ctr[2 + cur] = 0u;
