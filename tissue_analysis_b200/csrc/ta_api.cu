@@ -594,6 +594,16 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         for (int k = 0; k < 10; ++k) tot += (double)cyc[k];
         const char* nm[10] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush",
                               "R one-hot", "S stencil"};
+        if (use_mask_kernel()) {
+            const char* pn[6] = {"tile wait", "P1", "barrier 1", "P2", "barrier 2", "flush"};
+            for (int w = 0; w < 2; ++w) {
+                double t = 0;
+                for (int k = 0; k < 6; ++k) t += (double)cyc[8 * w + k];
+                fprintf(stderr, "[ta mask kernel, %s warp]", w ? "last" : "first");
+                for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.1f%%", pn[k], t > 0 ? 100.0 * cyc[8 * w + k] / t : 0.0);
+                fprintf(stderr, " | bricks %llu, one-label %llu, cycles per brick %.0f\n", cyc[8 * w + 7], cyc[8 * w + 6], cyc[8 * w + 7] ? t / cyc[8 * w + 7] : 0.0);
+            }
+        }
         fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
         for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
         fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[12], cyc[13]);

@@ -75,6 +75,16 @@ __device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b) {
 }
 #endif
 
+#ifdef TA_EMU_TMA
+inline int mk_tid() { return (int)threadIdx.x; }
+#else
+__device__ __forceinline__ int mk_tid() {
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
+}
+#endif
+
 // bit j set iff voxel j of the row equals L
 template <typename T> struct RowMask;
 template <> struct RowMask<uint16_t> {
@@ -102,7 +112,7 @@ template <> struct RowMask<uint32_t> {
 __device__ __forceinline__ void bit_moments(uint32_t M, uint32_t n, uint32_t& sf, uint32_t& sff) {
     const uint32_t lowbit = M & (0u - M);
     if (((M + lowbit) & M) == 0u) {                      // one run of bits [lo, lo + n)
-        const uint32_t lo = (uint32_t)__ffs(M) - 1u;     // M != 0 here
+        const uint32_t lo = 32u - (uint32_t)__clz(M) - n; // M != 0 here; one FLO (ffs would be BREV + FLO)
         const uint32_t t = n * (n - 1u);                 // 2 * sum_{i<n} i
         sf = n * lo + (t >> 1);
         sff = n * lo * lo + lo * t + (t * (2u * n - 1u)) / 6u;
@@ -177,7 +187,8 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     unsigned int* ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
     Carry* carry = reinterpret_cast<Carry*>(ctr + 16 + 2 * K + (2 * K) % 2 + 16);
 
-    const int tid = threadIdx.x;
+    // read once and kept: the compiler otherwise re-reads the special register (S2R, a slow-pipe instruction) inside the loops
+    const int tid = mk_tid();
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const T* vol = reinterpret_cast<const T*>(P.vol);
@@ -231,6 +242,16 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     }
     __syncthreads();
 
+#ifdef TA_WITH_PHASE_TIMING
+    // phase clocks of lane 0 of warp 0 ([0..6]) and of the last warp ([8..14]): tile wait, P1, barrier, P2, barrier, flush;
+    // [6] / [14]: one-label bricks altogether; [7]: bricks, [15]: one-label bricks
+    u64 tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u64 t_last = (u64)clock64();
+    const bool clocked = P.phase_cycles && lane == 0 && (warp == 0 || warp == TP - 1);
+#define MK_TICK(k) if (clocked) { const u64 now_ = (u64)clock64(); tk[k] += now_ - t_last; t_last = now_; }
+#else
+#define MK_TICK(k)
+#endif
     for (unsigned iter = 0;; ++iter) {
         const unsigned cur = iter & 1u, nxt = cur ^ 1u;
         const unsigned int brick = ctr[cur];
@@ -309,6 +330,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             __syncthreads();
         }
 
+        MK_TICK(0);
         // ---- P1: block of 16 rows x 2 planes: labels -> brick slots, row masks ------------------------------------------
         const uint32_t ref_label = tile[HV];               // plane 0, row 0, first owned column
         bool one_label = true;                             // this block: not needed, or all ref_label
@@ -331,20 +353,22 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 uint32_t cov = 0u, covh = 0u, mypres = 0u, myhl = 0u, myhr = 0u;
                 int k = 0;
                 bool all_ref = true;
+                // popc / ffs / clz / ballot / redux all cost 8 issue cycles of one slow pipe on this hardware (tools/ubench/ops.cu):
+                // one redux.min names the next label (the smallest label of a still uncovered voxel; any uncovered voxel of a
+                // lane will do as its candidate, the LAST one costs one FLO, the first one BREV + FLO)
                 for (;;) {
                     const uint32_t unc = ~cov;
-                    uint32_t cand = hl;
-                    if (unc) cand = row[HV + __ffs(unc) - 1];
-                    else if (covh & 1u) cand = hr;
-                    const unsigned bal = __ballot_sync(FULL, (unc != 0u) || (covh != 3u));
-                    if (!bal) break;
-                    const uint32_t L = __shfl_sync(FULL, cand, __ffs(bal) - 1);
-                    // slot of L in the brick's list: lanes l and l + 16 look at entry l; append with a CAS on the first free entry
+                    const uint32_t any_h = (covh & 1u) ? hr : hl;
+                    uint32_t cand = unc ? (uint32_t)row[HV + 31 - __clz(unc)] : any_h;
+                    if (!unc && covh == 3u) cand = TA_EMPTY32;
+                    const uint32_t L = __reduce_min_sync(FULL, cand);
+                    if (L == TA_EMPTY32) break;
+                    // slot of L in the brick's list: lane l looks at entry l; append with a CAS on the first free entry
                     int slot = -1;
                     for (;;) {
                         const uint32_t e = lane < K ? *((volatile uint32_t*)&blab[lane]) : TA_EMPTY32;
-                        const unsigned hit = __ballot_sync(FULL, e == L);
-                        if (hit) { slot = __ffs(hit) - 1; break; }
+                        const uint32_t hit = __reduce_min_sync(FULL, e == L ? (uint32_t)lane : 32u);
+                        if (hit < 32u) { slot = (int)hit; break; }
                         const int n = __popc(__ballot_sync(FULL, e != TA_EMPTY32));
                         if (n >= K) break;
                         uint32_t old = 0u;
@@ -367,7 +391,9 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 one_label = (k == 1) && all_ref;
             }
         }
+        MK_TICK(1);
         const bool uniform = __syncthreads_and(one_label) != 0;
+        MK_TICK(2);
         const bool overflow = ctr[2 + cur] != 0u;
         int nlab;                                              // labels of the brick = mask slots written
         {
@@ -433,8 +459,8 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                     uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, kx = 0, ky = 0, ks = 0;
                     const uint32_t up = ls ? 0xFFFFFFFFu : 0u;
                     int idx = 0;
-                    for (uint32_t rest = PC; rest; rest &= rest - 1u, ++idx) {
-                        const int i = __ffs(rest) - 1;
+                    for (int i = 0; i < nlab; ++i) {                      // a counter, not ffs: BREV + FLO are slow-pipe instructions
+                        if (!((PC >> i) & 1u)) continue;
                         const uint32_t M = mbase[i * 32] & fm;
                         const uint32_t n = (uint32_t)__popc(M);
                         uint32_t sf = 0u, sff = 0u;
@@ -449,6 +475,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                         const uint32_t rx = __reduce_or_sync(FULL, M);
                         const uint32_t ry = __ballot_sync(FULL, M != 0u);
                         if (lane == idx) { k1 = r1; k2 = r2; k3 = r3; k4 = r4; k5 = r5; k6 = r6; kx = rx; ky = ry; ks = (uint32_t)i; }
+                        ++idx;
                     }
                     if (lane < idx && kx) {
                         const uint32_t n = k1 & 0x3FFu, sf = k1 >> 10, nm_ = k2 & 0x7FFFu, sf1 = k2 >> 15;
@@ -493,8 +520,8 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                             slots |= (u64)i << (5 * j);
                             pcr &= pcr - 1u;
                         }
-                        for (uint32_t rest = PU; rest; rest &= rest - 1u) {
-                            const int b = __ffs(rest) - 1;
+                        for (int b = 0; b < nlab; ++b) {
+                            if (!((PU >> b) & 1u)) continue;
                             const uint32_t* qb = mbase + b * 32;
                             const uint32_t c0 = qb[-1], c1 = qb[0], c2 = qb[1];
                             const uint32_t d0 = qb[-MPLANE - 1], d1 = qb[-MPLANE], d2 = qb[-MPLANE + 1];
@@ -506,14 +533,14 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                             // labels of the round that meet Dn somewhere in the warp (b itself cannot: Dn excludes its voxels)
                             uint32_t ts = 0u;
 #pragma unroll
-                            for (int j = 0; j < KB; ++j) if (Ma[j] & Dn) ts |= 1u << j;
+                            for (int j = 0; j < KB; ++j) ts |= (Ma[j] & Dn) ? (1u << j) : 0u;
                             ts = __reduce_or_sync(FULL, ts);
                             if (!ts) continue;
                             const uint32_t Bf = (c1 >> 1) | (((hrc1 >> b) & 1u) << 31);                // b is the +f neighbour
-                            for (; ts; ts &= ts - 1u) {
-                                const int j = __ffs(ts) - 1;
-                                const int i = (int)((slots >> (5 * j)) & 31ull);
-                                const uint32_t Mo = mbase[i * 32] & fm;
+#pragma unroll
+                            for (int j = 0; j < KB; ++j) {
+                                if (!((ts >> j) & 1u)) continue;
+                                const uint32_t Mo = Ma[j];
                                 uint32_t cnt1 = do_w18 ? (uint32_t)__popc(Mo & Dn) : 0u, cnt2 = 0u;
                                 if (do_p6) {
                                     cnt1 |= (uint32_t)__popc(Mo & Bf) << 16;
@@ -521,7 +548,11 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                                 }
                                 const uint32_t r1 = __reduce_add_sync(FULL, cnt1);
                                 const uint32_t r2 = __reduce_add_sync(FULL, cnt2);
-                                if (lane == nres) { res_a = (uint32_t)i; res_b = (uint32_t)b; res_1 = r1; res_2 = r2; }
+                                const bool mine = lane == nres;
+                                res_a = mine ? (uint32_t)((slots >> (5 * j)) & 31ull) : res_a;
+                                res_b = mine ? (uint32_t)b : res_b;
+                                res_1 = mine ? r1 : res_1;
+                                res_2 = mine ? r2 : res_2;
                                 if (++nres == 32) flush_results();
                             }
                         }
@@ -560,7 +591,9 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 }
             }
         }
+        MK_TICK(3);
         __syncthreads();
+        MK_TICK(4);
 
         // ---- F: flush the per-brick tables ---------------------------------------------------------------------------------
         if (!uniform) {
@@ -601,7 +634,15 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             ctr[2 + cur] = 0u;
             if (use_tma && !box_issued && next_brick < total) issue_box(nxt);   // after G: the tile was in use until the barrier
         }
+        MK_TICK(5);
+#ifdef TA_WITH_PHASE_TIMING
+        if (clocked) { tk[7] += 1; if (uniform) tk[6] += 1; }
+#endif
     }
+#ifdef TA_WITH_PHASE_TIMING
+    if (clocked) for (int k = 0; k < 8; ++k) atomicAdd(&P.phase_cycles[(warp == 0 ? 0 : 8) + k], tk[k]);
+#endif
+#undef MK_TICK
     if (tid == 0 && carry->valid) global_apply(lt, pt.status, carry->label, carry->g, carry->bmn, carry->bmx);
 }
 
