@@ -117,7 +117,7 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     }
     bool ok = true;
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
-        if (which == MASK) ok = emu::run_block(block, 2, mk::NTHREADS, [&]() { mk::mask_kernel<T>(P, lt, pt, tmap); });
+        if (which == MASK) ok = emu::run_block(block, 2, mk::NTHREADS, [&]() { if (P.flags == 7u) mk::mask_kernel<T, 7>(P, lt, pt, tmap); else mk::mask_kernel<T, -1>(P, lt, pt, tmap); });
         else ok = emu::run_block(block, 2, NTHREADS, [&]() {
             scan_kernel<T, false>(P, lt, pt, tmap);
         });

@@ -104,8 +104,11 @@ static bool use_mask_kernel() {
     if (v < 0) { const char* e = getenv("TA_SCAN_KERNEL"); v = (e && !strcmp(e, "brick")) ? 0 : 1; }
     return v == 1;
 }
-static scan_kernel_fn mask_kernel_variant(int elem) {
-    return elem == 2 ? ta::mk::mask_kernel<uint16_t> : ta::mk::mask_kernel<uint32_t>;
+// full: all three accumulations (TA_PASS_ALL, what the product runs) with the flags folded at compile time; the other
+// instantiation reads them from the parameters
+static scan_kernel_fn mask_kernel_variant(int elem, bool full) {
+    if (full) return elem == 2 ? ta::mk::mask_kernel<uint16_t, 7> : ta::mk::mask_kernel<uint32_t, 7>;
+    return elem == 2 ? ta::mk::mask_kernel<uint16_t, -1> : ta::mk::mask_kernel<uint32_t, -1>;
 }
 static scan_kernel_fn scan_kernel_variant(int elem, bool timing) {
 #ifdef TA_WITH_PHASE_TIMING
@@ -160,10 +163,12 @@ int ta_ctx_create(ta_ctx** out, int device) {
             TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, tm != 0),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
-    TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(2), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::mk::smem_bytes<uint16_t>()));
-    TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(4), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ta::mk::smem_bytes<uint32_t>()));
+    for (int full = 0; full < 2; ++full) {
+        TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(2, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ta::mk::smem_bytes<uint16_t>()));
+        TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(4, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ta::mk::smem_bytes<uint32_t>()));
+    }
     guard.c = nullptr;
     *out = ctx;
     return TA_OK;
@@ -421,7 +426,7 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
         const int per_sm = ctx->elem == 2 ? 3 : 2;
         const int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * per_sm);
         const size_t smem = ctx->elem == 2 ? ta::mk::smem_bytes<uint16_t>() : ta::mk::smem_bytes<uint32_t>();
-        mask_kernel_variant(ctx->elem)<<<grid, ta::mk::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
+        mask_kernel_variant(ctx->elem, (P.flags & 7u) == 7u)<<<grid, ta::mk::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
         ctx->launches++;
         TA_CUDA(cudaGetLastError());
         return TA_OK;

@@ -195,6 +195,7 @@ __device__ __forceinline__ void label_add(const BrickShared<T>& sh, const LabelT
                                           uint32_t L, const uint32_t* v, u64 F0, u64 M0, u64 S0) {
     uint32_t slot = (L * 0x9E3779B1u) >> (32 - LT_BITS);
     int found = -1;
+#pragma unroll 1
     for (int probe = 0; probe < LT_SLOTS; ++probe) {
         uint32_t k = *((volatile uint32_t*)&sh.lt_key[slot]);
         if (k == L) { found = (int)slot; break; }
@@ -303,6 +304,7 @@ __device__ __forceinline__ void pair_add_packed(const BrickShared<T>& sh, const 
                                                 typename Vox<T>::PKey key, const uint32_t inc[PT_WORDS]) {
     typedef typename Vox<T>::PKey PKey;
     uint32_t slot = Vox<T>::hash(key);
+#pragma unroll 1
     for (int probe = 0; probe < PT_SLOTS; ++probe) {
         PKey k = *((volatile PKey*)&sh.pt_key[slot]);
         bool hit = (k == key);

@@ -1,32 +1,38 @@
 // The streaming pass, bit-mask formulation (sm_100a).  Same tables as scan_kernel (ta_scan.cuh), different arithmetic:
-// every comparison of a voxel with a label is made ONCE, packed two voxels per instruction, and turned into one bit;
-// everything after that -- 18-neighbourhood dilation, face tests, moments -- is boolean algebra and popcounts on 32-voxel
-// words, warp-uniform, without worklists.
+// a row of 32 voxels becomes one 32-bit mask per label it holds; everything after that -- 18-neighbourhood dilation, face
+// tests, moments -- is boolean algebra and popcounts on 32-voxel words, warp-uniform, without worklists.
 //
 // Work unit: a brick of RW x OM x ZB = 32 x 30 x 8 voxels, staged with a one-voxel halo as ONE TMA box of
 // (32 + 2 segments of 16 bytes) x 32 rows x 10 planes = 320 tile rows of 32 (+ 2 halo) voxels.  A lane owns a row.
 //
-//   P1  warp w takes a block of 16 rows x 2 planes of the tile (compact blocks see few labels: ~4 on C3, a whole plane
-//       sees ~7).  The lane rows are held in registers; the leader of the still uncovered voxels names a label L, the warp
-//       looks it up in the brick's label list (blab[K], lock-free append), every lane compares its row with L
-//       (VIADDMNMX.U16x2: packed subtract + min 1, then one IMAD per word gathers the bits) and stores
-//       masks[plane][slot][row] = 32 own bits (all masks are zero when P1 starts: the flush clears the slots a brick has
-//       used), hwl / hwr[plane][row] = the slots in the two halo voxels, pres[plane][row] = the slots present in the row.  More than K labels in one brick (noise, never tissue): the whole
+//   P1  warp w takes a block of 16 rows x 2 planes of the tile, one row per lane.  The lane finds the run starts of its
+//       row (one packed compare of the row with itself shifted by a voxel: SHF + LOP3 + VIMNMX.U16x2 + IMAD per two
+//       voxels) and walks its runs: label from the tile, slot = the label's place in the brick's open-addressing list
+//       (blab[K], CAS insert, no waiting), bits [j0, j1) OR-ed into masks[plane][slot][row] (all masks are zero when P1
+//       starts: the end of a brick clears the slots it used).  hwl / hwr[plane][row] = the slots of the two halo voxels,
+//       pres[plane][row] = the slots present in the row.  More than K labels in one brick (noise, small cells): the whole
 //       brick takes the per-voxel path G.
 //   --  barrier; the tile is dead now: thread 0 issues the NEXT brick's box copy, it lands under P2.
 //   P2  warp w < 8 takes a block of 15 owned rows x 2 owned planes.  For every label b present in the rows around the
 //       block (redux.or of the row presence words):
 //         D_b = dilation of b by the 18-neighbourhood, restricted to the lane's row -- ORs of the nine row masks around,
 //               two shifts for the f direction; Bf / Bm / Bs = b as the +f / +m / +s neighbour;
-//         the labels a of the block that meet D_b somewhere (16 masks in registers, one LOP3 + one predicated OR each,
-//         one redux.or) get wall18 += popc(M_a & D_b), faces += popc(M_a & Bf), popc(M_a & Bm), popc(M_a & Bs), two
+//         the labels a of the block that meet D_b somewhere (8 masks in registers per round, one LOP3 + one predicated OR
+//         each, one redux.or) get wall18 += popc(M_a & D_b), faces += popc(M_a & Bf), popc(M_a & Bm), popc(M_a & Bs), two
 //         full-mask redux per (a, b); the results wait in one lane each and go to the per-brick pair table in one SIMT pass.
 //       Moments: per label of the block n = popc(M), closed forms for sum f, sum f^2 of a run of bits, 6 redux, bounds from
 //       redux.or / ballot, one lane per label updates the per-brick label table.
+//       Warps 8 and 9 have no block: they flush the tables of the PREVIOUS brick meanwhile (F below; the per-brick tables
+//       are ping-pong).  Phase clocks before this: the flush was 17 % of warp 0's time per brick and made it late for the
+//       next P1, where the other warps then waited for it.
 //   G   (rare) every voxel of the brick against its 18 neighbours, straight from the tile.
-//   F   flush the per-brick tables (brick-local u32 sums -> shifted u64 global REDs; pair slots -> global hash).
+//   F   flush a set of per-brick tables (brick-local u32 sums -> shifted u64 global REDs; pair slots -> global hash).
 //   A brick whose tile is one label altogether (background, inside of a big cell) ends after P1 with closed-form moments;
-//   consecutive such bricks of one label are merged in shared memory before they touch the global table.
+//   consecutive such bricks of one label are merged in shared memory before they touch the global table.  It uses no
+//   tables, so a pending flush waits for the next brick that has a P2 to hide it behind.
+//   Everything rare (G, edge replication of a tile at the volume border, the closed form, the pair-table insert) is a
+//   __noinline__ function and the hash probe loops are not unrolled: the hot loop body has to stay near the 32 KB of
+//   instruction cache an SM has (ncu: 1.9 `no_instruction` stall cycles per issue with everything inlined, 0.5 now).
 #pragma once
 #include "ta_scan.cuh"
 
@@ -39,10 +45,11 @@ constexpr int TM = 32;                    // tile rows = lanes
 constexpr int ZB = 8;                     // owned planes per brick
 constexpr int TP = ZB + 2;                // tile planes = warps
 constexpr int NTHREADS = TP * 32;
-constexpr int K = 24;                     // label slots per brick
+constexpr int K = 24;                     // label slots per brick (16: C2 and C4 take the per-voxel path often, four times slower)
 constexpr int KB = 8;                     // labels of a P2 block held in registers at a time
 constexpr int NW2 = 8;                    // warps with a P2 block (15 rows x 2 planes each)
-constexpr int MPLANE = K * 32 + 16;       // mask words per tile plane; + 16: the two half-warps of a P2 block (planes q, q + 1) use different banks
+constexpr int MPLANE = K * 32 + 16;       // + 16: the two half-warps of a P2 block (planes q, q + 1) use different banks
+constexpr int PSTR = 32;
 
 template <typename T> struct Geo {
     static constexpr int HV = 16 / (int)sizeof(T);       // halo elements per side (one 16-byte segment)
@@ -53,21 +60,18 @@ template <typename T> struct Geo {
     static constexpr int TILE_BYTES = TP * TM * ROWB;
 };
 
+template <typename T> constexpr size_t table_bytes() {          // one set of per-brick tables: label keys / values, pair values / keys
+    return LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 + PT_SLOTS * PT_WORDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey);
+}
 template <typename T> constexpr size_t smem_bytes() {
-    return (size_t)Geo<T>::TILE_BYTES + (size_t)TP * MPLANE * 4 + (size_t)3 * TP * 32 * 4 + LT_SLOTS * 4 + LT_SLOTS * LT_FIELDS * 4 +
-           PT_SLOTS * PT_WORDS * 4 + PT_SLOTS * sizeof(typename Vox<T>::PKey) + 96 * 4 + 16 * 8 + 128;
+    return (size_t)Geo<T>::TILE_BYTES + (size_t)TP * MPLANE * 4 + (size_t)3 * TP * PSTR * 4 + 2 * table_bytes<T>() +
+           96 * 4 + 16 * 8 + 128;
 }
 
 // ---- packed compares ---------------------------------------------------------------------------------------------------
 #ifdef TA_EMU_TMA
-inline uint32_t add_u16x2(uint32_t a, uint32_t b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
 inline uint32_t min_u16x2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 #else
-__device__ __forceinline__ uint32_t add_u16x2(uint32_t a, uint32_t b) {
-    uint32_t r;
-    asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
 __device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b) {
     uint32_t r;
     asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -85,27 +89,37 @@ __device__ __forceinline__ int mk_tid() {
 }
 #endif
 
-// bit j set iff voxel j of the row equals L
-template <typename T> struct RowMask;
-template <> struct RowMask<uint16_t> {
-    static __device__ __forceinline__ uint32_t eq(const uint32_t (&w)[16], uint32_t L) {
-        const uint32_t NL = ((0u - L) & 0xFFFFu) * 0x10001u;       // -L in both halves: (v - L) mod 2^16 == 0 <=> v == L
+// bit j set iff voxel j of the row opens a run (differs from voxel j - 1); bit 0 is always set
+#ifdef TA_EMU_TMA
+inline uint32_t mk_funnel_l16(uint32_t lo, uint32_t hi) { return (hi << 16) | (lo >> 16); }
+inline uint32_t mk_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((u64)a * (u64)b) >> 32); }
+#else
+__device__ __forceinline__ uint32_t mk_funnel_l16(uint32_t lo, uint32_t hi) { return __funnelshift_l(lo, hi, 16); }
+__device__ __forceinline__ uint32_t mk_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#endif
+template <typename T> struct RunStarts;
+template <> struct RunStarts<uint16_t> {
+    // word j holds voxels 2j, 2j + 1; the funnel shift puts their left neighbours 2j - 1, 2j in the same halves
+    static __device__ __forceinline__ uint32_t of(const uint32_t (&w)[16]) {
         uint32_t a0 = 0u, a1 = 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a0 += min_u16x2(add_u16x2(w[j], NL), 0x00010001u) << (2 * j);
+        for (int j = 0; j < 8; ++j) a0 += min_u16x2(w[j] ^ mk_funnel_l16(w[j ? j - 1 : 0], w[j]), 0x00010001u) << (2 * j);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a1 += min_u16x2(add_u16x2(w[8 + j], NL), 0x00010001u) << (2 * j);
-        const uint32_t ne = ((a0 & 0x5555u) | ((a0 >> 15) & 0xAAAAu)) | (((a1 & 0x5555u) | ((a1 >> 15) & 0xAAAAu)) << 16);
-        return ~ne;
+        for (int j = 0; j < 8; ++j) a1 += min_u16x2(w[8 + j] ^ mk_funnel_l16(w[7 + j], w[8 + j]), 0x00010001u) << (2 * j);
+        return ((a0 & 0x5555u) | ((a0 >> 15) & 0xAAAAu)) | (((a1 & 0x5555u) | ((a1 >> 15) & 0xAAAAu)) << 16) | 1u;
     }
+    static __device__ __forceinline__ uint32_t first(const uint32_t (&w)[16]) { return w[0] & 0xFFFFu; }
+    static __device__ __forceinline__ uint32_t last(const uint32_t (&w)[16]) { return w[15] >> 16; }
 };
-template <> struct RowMask<uint32_t> {
-    static __device__ __forceinline__ uint32_t eq(const uint32_t (&w)[32], uint32_t L) {
-        uint32_t ne = 0u;
+template <> struct RunStarts<uint32_t> {
+    static __device__ __forceinline__ uint32_t of(const uint32_t (&w)[32]) {
+        uint32_t st = 1u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ne += min(w[j] - L, 1u) << j;
-        return ~ne;
+        for (int j = 1; j < 32; ++j) if (w[j] != w[j - 1]) st |= 1u << j;
+        return st;
     }
+    static __device__ __forceinline__ uint32_t first(const uint32_t (&w)[32]) { return w[0]; }
+    static __device__ __forceinline__ uint32_t last(const uint32_t (&w)[32]) { return w[31]; }
 };
 
 // sum of the bit positions and of their squares
@@ -160,7 +174,113 @@ struct Carry {
     uint32_t label, valid;
 };
 
+// ---- out-of-line pieces: the kernel's hot loop has to fit the 32 KB instruction cache of an SM (ncu: `no_instruction`
+// stalls grew from 0.3 to 1.9 cycles per issue when the loop body passed it), so everything rare is a call ----------------
+
+// thread 0: closed-form moments of a brick whose tile is one label; consecutive ones of the same label are merged
+__device__ __noinline__ void uniform_brick(Carry* carry, LabelTable lt, uint32_t* status, uint32_t label, uint32_t a, uint32_t b,
+                                           uint32_t c, u64 gF0, u64 gM0, u64 gS0) {
+    const uint32_t ta_ = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
+    const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6, qc = (c - 1) * c * (2 * c - 1) / 6;
+    uint32_t v[LT_FIELDS];
+    v[0] = a * b * c; v[1] = b * c * ta_; v[2] = a * c * tb; v[3] = a * b * tc;
+    v[4] = b * c * qa; v[5] = c * ta_ * tb; v[6] = b * ta_ * tc;
+    v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
+    v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
+    u64 g[10];
+    int bmn[3], bmx[3];
+    local_to_global(v, gF0, gM0, gS0, g, bmn, bmx);
+    if (carry->valid && carry->label != label) {
+        global_apply(lt, status, carry->label, carry->g, carry->bmn, carry->bmx);
+        carry->valid = 0u;
+    }
+    if (!carry->valid) {
+        carry->valid = 1u; carry->label = label;
+        for (int i = 0; i < 10; ++i) carry->g[i] = g[i];
+        for (int i = 0; i < 3; ++i) { carry->bmn[i] = bmn[i]; carry->bmx[i] = bmx[i]; }
+    } else {
+        for (int i = 0; i < 10; ++i) carry->g[i] += g[i];
+        for (int i = 0; i < 3; ++i) { carry->bmn[i] = min(carry->bmn[i], bmn[i]); carry->bmx[i] = max(carry->bmx[i], bmx[i]); }
+    }
+}
+
+// every thread of the CTA: elements of a box copy outside the buffer arrived as zeros; the tile wants replicated edge voxels
 template <typename T>
+__device__ __noinline__ void replicate_edges(T* tile, int tid, int F0, int M0, int S0, int nf, int nm, int ns) {
+    typedef Geo<T> G;
+    constexpr int HV = G::HV, TRE = G::TRE, ROWV = G::ROWV;
+    uint4* tilev = reinterpret_cast<uint4*>(tile);
+    const int xl = (F0 == 0) ? HV : 0;                        // elements [0, xl) <- element xl
+    const int xr = min(TRE, nf - F0 + HV);                    // elements [xr, TRE) <- element xr - 1
+    for (int r = tid; r < TP * TM; r += NTHREADS) {
+        T* row = tile + r * TRE;
+        if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
+        if (xr < TRE) { const T v = row[xr - 1]; for (int x = xr; x < TRE; ++x) row[x] = v; }
+    }
+    __syncthreads();
+    for (int i = tid; i < TP * TM * ROWV; i += NTHREADS) {
+        const int r = (i / ROWV) % TM;
+        const int m = M0 - 1 + r;
+        const int mc = min(max(m, 0), nm - 1);
+        if (mc != m) tilev[i] = tilev[i + (mc - m) * ROWV];
+    }
+    __syncthreads();
+    for (int i = tid; i < TP * TM * ROWV; i += NTHREADS) {
+        const int q = i / (TM * ROWV);
+        const int s = S0 - 1 + q;
+        const int sc = min(max(s, 0), ns - 1);
+        if (sc != s) tilev[i] = tilev[i + (sc - s) * (TM * ROWV)];
+    }
+    __syncthreads();
+}
+
+// one pair's packed increments into the per-brick table (both call sites of P2 share this copy)
+template <typename T>
+__device__ __noinline__ void pair_add_call(BrickShared<T> sh, PairTable pt, typename Vox<T>::PKey key, uint32_t i0, uint32_t i1,
+                                           uint32_t i2, uint32_t i3) {
+    const uint32_t inc[PT_WORDS] = {i0, i1, i2, i3};
+    pair_add_packed<T>(sh, pt, key, inc);
+}
+
+// G (rare): more than K labels in the brick: every owned voxel on its own, straight from the tile
+template <typename T>
+__device__ __noinline__ void brick_per_voxel(const T* tile, BrickShared<T> sh, LabelTable lt, PairTable pt, int tid, int nown, int F0,
+                                             int M0, int nf, int nm, u64 gF0, u64 gM0, u64 gS0, bool do_mom, bool do_p6, bool do_w18) {
+    typedef Geo<T> G;
+    constexpr int HV = G::HV, TRE = G::TRE;
+    constexpr int PLANEE = TM * TRE;
+    const int nvo = RW * OM * nown;
+    for (int i = tid; i < nvo; i += NTHREADS) {
+        const int f = i % RW, m = (i / RW) % OM, s = i / (RW * OM);
+        if (F0 + f >= nf || M0 + m >= nm) continue;
+        const T* qv = tile + ((s + 1) * TM + (m + 1)) * TRE + HV + f;
+        const uint32_t a = qv[0];
+        if (do_mom) {
+            const uint32_t uf = f, um = m, us = s;
+            uint32_t v[LT_FIELDS] = {1u, uf, um, us, uf * uf, uf * um, uf * us, um * um, um * us, us * us, uf, um, us, uf, um, us};
+            label_add<T>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
+        }
+        if (do_p6) {
+#pragma unroll 1
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t n = qv[d == 0 ? 1 : (d == 1 ? TRE : PLANEE)];
+                if (n != a) pair_add<T>(sh, pt, a, n, 2 * d + (a < n ? 0 : 1), 1u);
+            }
+        }
+        if (do_w18) {
+#pragma unroll 1
+            for (int k = 0; k < 18; ++k) {
+                const uint32_t b = qv[neighbour_offset<TRE, PLANEE>(k)];
+                if (b == a) continue;
+                bool seen = false;
+                for (int kk = 0; kk < k; ++kk) seen |= ((uint32_t)qv[neighbour_offset<TRE, PLANEE>(kk)] == b);
+                if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
+            }
+        }
+    }
+}
+
+template <typename T, int FLAGS = -1>                      // FLAGS >= 0: the pass flags at compile time (the full pass of the product)
 __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 2 ? 3 : 2))
 mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::PKey PKey;
@@ -175,16 +295,22 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     uint4* tilev = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + G::TILE_BYTES);            // [TP][MPLANE]: own bits of (slot, row)
     uint32_t* pres = masks + TP * MPLANE;                                                // [TP][32]: slots with a bit in the row
-    uint32_t* hwl = pres + TP * 32;                                                      // [TP][32]: slots in the left halo voxel of the row
-    uint32_t* hwr = hwl + TP * 32;                                                       // [TP][32]: slots in the right halo voxel
-    BrickShared<T> sh{};
-    sh.lt_key = hwr + TP * 32;
-    sh.lt_val = sh.lt_key + LT_SLOTS;
-    sh.pt_val = sh.lt_val + LT_SLOTS * LT_FIELDS;
-    sh.pt_key = reinterpret_cast<PKey*>(sh.pt_val + PT_SLOTS * PT_WORDS);
+    uint32_t* hwl = pres + TP * PSTR;                                                      // [TP][32]: slots in the left halo voxel of the row
+    uint32_t* hwr = hwl + TP * PSTR;                                                       // [TP][32]: slots in the right halo voxel
+    constexpr int TBLW = LT_SLOTS + LT_SLOTS * LT_FIELDS + PT_SLOTS * PT_WORDS + PT_SLOTS * (int)sizeof(PKey) / 4;   // words of one set (table_bytes)
+    constexpr int NSETS = 2;                                       // ping-pong: see the deferred flush below
+    uint32_t* const tables = hwr + TP * PSTR;
+    auto table_set = [&](unsigned which) {
+        BrickShared<T> x{};
+        x.lt_key = tables + which * TBLW;
+        x.lt_val = x.lt_key + LT_SLOTS;
+        x.pt_val = x.lt_val + LT_SLOTS * LT_FIELDS;
+        x.pt_key = reinterpret_cast<PKey*>(x.pt_val + PT_SLOTS * PT_WORDS);
+        return x;
+    };
     // ctr: [0..1] brick index ping-pong, [2..3] overflow flag ping-pong, [4..5] mbarrier, [8..10] / [12..14] brick origin
     // ping-pong, [16 .. 16 + 2 K) the brick's label list, ping-pong
-    unsigned int* ctr = reinterpret_cast<unsigned int*>(sh.pt_key + PT_SLOTS);
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(tables + NSETS * TBLW);
     Carry* carry = reinterpret_cast<Carry*>(ctr + 16 + 2 * K + (2 * K) % 2 + 16);
 
     // read once and kept: the compiler otherwise re-reads the special register (S2R, a slow-pipe instruction) inside the loops
@@ -193,17 +319,51 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     const int warp = tid >> 5;
     const T* vol = reinterpret_cast<const T*>(P.vol);
     const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
-    const bool do_mom = P.flags & 1u, do_p6 = P.flags & 2u, do_w18 = P.flags & 4u;
+    const uint32_t pflags = FLAGS >= 0 ? (uint32_t)FLAGS : P.flags;
+    const bool do_mom = pflags & 1u, do_p6 = pflags & 2u, do_w18 = pflags & 4u;
     const bool do_pairs = do_p6 || do_w18;
     const int nf = (int)P.nf, nm = (int)P.nm, ns = (int)P.ns;
 
-    for (int i = tid; i < LT_SLOTS; i += NTHREADS) sh.lt_key[i] = TA_EMPTY32;
-    for (int i = tid; i < LT_SLOTS * LT_FIELDS; i += NTHREADS) {
-        const int f = i % LT_FIELDS;
-        sh.lt_val[i] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+    for (unsigned which = 0; which < (unsigned)NSETS; ++which) {
+        const BrickShared<T> x = table_set(which);
+        for (int i = tid; i < LT_SLOTS; i += NTHREADS) x.lt_key[i] = TA_EMPTY32;
+        for (int i = tid; i < LT_SLOTS * LT_FIELDS; i += NTHREADS) {
+            const int f = i % LT_FIELDS;
+            x.lt_val[i] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+        }
+        for (int i = tid; i < PT_SLOTS; i += NTHREADS) x.pt_key[i] = Vox<T>::PEMPTY;
+        for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) x.pt_val[i] = 0u;
     }
-    for (int i = tid; i < PT_SLOTS; i += NTHREADS) sh.pt_key[i] = Vox<T>::PEMPTY;
-    for (int i = tid; i < PT_SLOTS * PT_WORDS; i += NTHREADS) sh.pt_val[i] = 0u;
+    // F: one set of per-brick tables -> the global tables (brick-local u32 sums -> shifted u64 global REDs; pair slots ->
+    // global hash), by threads first .. first + count - 1 of the CTA; leaves the set empty
+    auto flush_tables = [&](const BrickShared<T>& x, u64 oF, u64 oM, u64 oS, int first, int count) {
+        for (int i = tid - first; i < LT_SLOTS; i += count) {
+            const uint32_t L = x.lt_key[i];
+            if (L == TA_EMPTY32) continue;
+            uint32_t* d = &x.lt_val[i * LT_FIELDS];
+            label_to_global(lt, pt.status, L, d, oF, oM, oS);
+#pragma unroll
+            for (int f = 0; f < LT_FIELDS; ++f) d[f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
+            x.lt_key[i] = TA_EMPTY32;
+        }
+        for (int i = tid - first; i < PT_SLOTS; i += count) {
+            const PKey key = x.pt_key[i];
+            if (key == Vox<T>::PEMPTY) continue;
+            uint32_t* d = &x.pt_val[i * PT_WORDS];
+            const int slot = ta_pair_slot(pt, Vox<T>::key64(key));
+#pragma unroll
+            for (int idx = 0; idx < 7; ++idx) {
+                const uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+                if (n && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + (idx == 0 ? 6 : idx - 1)], n);
+            }
+#pragma unroll
+            for (int w2 = 0; w2 < PT_WORDS; ++w2) d[w2] = 0u;
+            x.pt_key[i] = Vox<T>::PEMPTY;
+        }
+    };
+    bool pending = false;                                  // deferred flush: the other set holds the previous brick's sums
+    u64 pF0 = 0, pM0 = 0, pS0 = 0;                         // ... taken at this origin
+    unsigned tset = 0u;                                    // the set the next brick that is not one label will use; the pending one is the other
     if (tid < 2 * K) ctr[16 + tid] = TA_EMPTY32;
     for (int i = tid; i < TP * MPLANE; i += NTHREADS) masks[i] = 0u;       // invariant: every mask is zero when a brick's P1 starts
 
@@ -295,30 +455,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             tma_parity ^= 1u;
             // elements outside the buffer arrived as zeros; the tile wants replicated edge voxels
             const bool edge = (F0 == 0) | (F0 + RW + HV > nf) | (M0 == 0) | (M0 + TM - 1 > nm) | (S0 < 1) | (S0 + ZB + 1 > ns);
-            if (edge) {
-                const int xl = (F0 == 0) ? HV : 0;                        // elements [0, xl) <- element xl
-                const int xr = min(TRE, nf - F0 + HV);                    // elements [xr, TRE) <- element xr - 1
-                for (int r = tid; r < TP * TM; r += NTHREADS) {
-                    T* row = tile + r * TRE;
-                    if (xl) { const T v = row[xl]; for (int x = 0; x < xl; ++x) row[x] = v; }
-                    if (xr < TRE) { const T v = row[xr - 1]; for (int x = xr; x < TRE; ++x) row[x] = v; }
-                }
-                __syncthreads();
-                for (int i = tid; i < TP * TM * ROWV; i += NTHREADS) {
-                    const int r = (i / ROWV) % TM;
-                    const int m = M0 - 1 + r;
-                    const int mc = min(max(m, 0), nm - 1);
-                    if (mc != m) tilev[i] = tilev[i + (mc - m) * ROWV];
-                }
-                __syncthreads();
-                for (int i = tid; i < TP * TM * ROWV; i += NTHREADS) {
-                    const int q = i / (TM * ROWV);
-                    const int s = S0 - 1 + q;
-                    const int sc = min(max(s, 0), ns - 1);
-                    if (sc != s) tilev[i] = tilev[i + (sc - s) * (TM * ROWV)];
-                }
-                __syncthreads();
-            }
+            if (edge) replicate_edges<T>(tile, tid, F0, M0, S0, nf, nm, ns);
         } else {
             for (int i = tid; i < TP * TM * TRE; i += NTHREADS) {
                 const int e = i % TRE, r = (i / TRE) % TM, q = i / PLANEE;
@@ -331,75 +468,67 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         }
 
         MK_TICK(0);
-        // ---- P1: block of 16 rows x 2 planes: labels -> brick slots, row masks ------------------------------------------
+        // ---- P1: block of 16 rows x 2 planes: runs of the lane's row -> brick slots, row masks ---------------------------
         const uint32_t ref_label = tile[HV];               // plane 0, row 0, first owned column
+        const int q1 = 2 * (warp >> 1) + (lane >> 4);      // tile plane of the lane
+        const int r1 = 16 * (warp & 1) + (lane & 15);      // tile row of the lane
+        const bool needed = 2 * (warp >> 1) <= nown + 1;   // the block has a plane somebody needs (uniform per warp)
         bool one_label = true;                             // this block: not needed, or all ref_label
-        {
-            const int q = 2 * (warp >> 1) + (lane >> 4);   // tile plane of the lane
-            const int r = 16 * (warp & 1) + (lane & 15);   // tile row of the lane
-            if (2 * (warp >> 1) <= nown + 1) {             // the block has a plane somebody needs (uniform per warp)
-                const T* row = tile + (q * TM + r) * TRE;
-                uint32_t w[NW];
-                {
-                    const uint4* rv = reinterpret_cast<const uint4*>(row + HV);
+        if (needed) {
+            const T* row = tile + (q1 * TM + r1) * TRE;
+            uint32_t w[NW];
+            {
+                const uint4* rv = reinterpret_cast<const uint4*>(row + HV);
 #pragma unroll
-                    for (int x = 0; x < NW / 4; ++x) {
-                        const uint4 v = rv[x];
-                        w[4 * x] = v.x; w[4 * x + 1] = v.y; w[4 * x + 2] = v.z; w[4 * x + 3] = v.w;
-                    }
+                for (int x = 0; x < NW / 4; ++x) {
+                    const uint4 v = rv[x];
+                    w[4 * x] = v.x; w[4 * x + 1] = v.y; w[4 * x + 2] = v.z; w[4 * x + 3] = v.w;
                 }
-                const uint32_t hl = row[HV - 1], hr = row[HV + RW];
-                uint32_t* mrow = masks + q * MPLANE + r;
-                uint32_t cov = 0u, covh = 0u, mypres = 0u, myhl = 0u, myhr = 0u;
-                int k = 0;
-                bool all_ref = true;
-                // popc / ffs / clz / ballot / redux all cost 8 issue cycles of one slow pipe on this hardware (tools/ubench/ops.cu):
-                // one redux.min names the next label (the smallest label of a still uncovered voxel; any uncovered voxel of a
-                // lane will do as its candidate, the LAST one costs one FLO, the first one BREV + FLO)
-                for (;;) {
-                    const uint32_t unc = ~cov;
-                    const uint32_t any_h = (covh & 1u) ? hr : hl;
-                    uint32_t cand = unc ? (uint32_t)row[HV + 31 - __clz(unc)] : any_h;
-                    if (!unc && covh == 3u) cand = TA_EMPTY32;
-                    const uint32_t L = __reduce_min_sync(FULL, cand);
-                    if (L == TA_EMPTY32) break;
-                    // slot of L in the brick's list: lane l looks at entry l; append with a CAS on the first free entry
-                    int slot = -1;
-                    for (;;) {
-                        const uint32_t e = lane < K ? *((volatile uint32_t*)&blab[lane]) : TA_EMPTY32;
-                        const uint32_t hit = __reduce_min_sync(FULL, e == L ? (uint32_t)lane : 32u);
-                        if (hit < 32u) { slot = (int)hit; break; }
-                        const int n = __popc(__ballot_sync(FULL, e != TA_EMPTY32));
-                        if (n >= K) break;
-                        uint32_t old = 0u;
-                        if (lane == 0) old = atomicCAS(&blab[n], TA_EMPTY32, L);
-                        old = __shfl_sync(FULL, old, 0);
-                        if (old == TA_EMPTY32 || old == L) { slot = n; break; }
-                    }
-                    if (slot < 0) { if (lane == 0) ctr[2 + cur] = 1u; break; }
-                    const uint32_t M = RowMask<T>::eq(w, L);
-                    const uint32_t el = (hl == L) ? 1u : 0u, er = (hr == L) ? 1u : 0u;
-                    cov |= M; covh |= el | (er << 1);
-                    mrow[slot * 32] = M;
-                    myhl |= el << slot; myhr |= er << slot;
-                    if (M | el | er) mypres |= 1u << slot;
-                    all_ref = all_ref && (L == ref_label);
-                    ++k;
-                }
-                pres[q * 32 + r] = mypres;
-                hwl[q * 32 + r] = myhl; hwr[q * 32 + r] = myhr;
-                one_label = (k == 1) && all_ref;
             }
+            const uint32_t hl = row[HV - 1], hr = row[HV + RW];
+            uint32_t* mrow = masks + q1 * MPLANE + r1;
+            // slot of a label = its place in the brick's open-addressing list (K entries, CAS insert; every lane that
+            // looks for the same label walks the same places, so nobody waits for anybody)
+            auto find_slot = [&](uint32_t L) -> int {
+                uint32_t h = mk_umulhi(L * 0x9E3779B1u, (uint32_t)K);
+#pragma unroll 1
+                for (int probe = 0; probe < K; ++probe) {
+                    uint32_t e = *((volatile uint32_t*)&blab[h]);
+                    if (e == TA_EMPTY32) e = atomicCAS(&blab[h], TA_EMPTY32, L);
+                    if (e == L || e == TA_EMPTY32) return (int)h;
+                    h = (h + 1u == (uint32_t)K) ? 0u : h + 1u;
+                }
+                return -1;
+            };
+            // the runs of the row, last one first (the highest set bit costs one FLO): label from the tile, bits [j0, j1)
+            const uint32_t v0 = RunStarts<T>::first(w), v31 = RunStarts<T>::last(w);
+            uint32_t rem = RunStarts<T>::of(w);
+            one_label = (rem == 1u) && (v0 == ref_label) && (hl == v0) && (hr == v0);
+            uint32_t mypres = 0u;
+            int j1 = 32, slot_first = 0, slot_last = -1;
+            bool ok = true;
+            while (rem) {
+                const int j0 = 31 - __clz(rem);
+                rem ^= 1u << j0;
+                const int slot = find_slot((uint32_t)row[HV + j0]);
+                if (slot < 0) { ok = false; break; }
+                mrow[slot * 32] |= (FULL >> (32 - j1)) & (FULL << j0);
+                mypres |= 1u << slot;
+                if (slot_last < 0) slot_last = slot;
+                slot_first = slot;
+                j1 = j0;
+            }
+            int sl = slot_first, sr = slot_last;
+            if (ok && hl != v0) sl = find_slot(hl);
+            if (ok && hr != v31) sr = find_slot(hr);
+            if (!ok || sl < 0 || sr < 0) { ctr[2 + cur] = 1u; sl = 0; sr = 0; }
+            pres[q1 * PSTR + r1] = mypres | (1u << sl) | (1u << sr);
+            hwl[q1 * PSTR + r1] = 1u << sl; hwr[q1 * PSTR + r1] = 1u << sr;
         }
         MK_TICK(1);
         const bool uniform = __syncthreads_and(one_label) != 0;
         MK_TICK(2);
         const bool overflow = ctr[2 + cur] != 0u;
-        int nlab;                                              // labels of the brick = mask slots written
-        {
-            const uint32_t e = lane < K ? blab[lane] : TA_EMPTY32;
-            nlab = __popc(__ballot_sync(FULL, e != TA_EMPTY32));
-        }
         const unsigned int next_brick = ctr[nxt];
         bool box_issued = false;
         if (use_tma && !overflow && next_brick < total) {
@@ -407,33 +536,14 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             box_issued = true;
         }
 
+        // the warps without a P2 block empty the tables of the last brick that used them while the others work on this brick's
+        // (a one-label brick uses no tables: nothing to hide the flush behind, so it waits for the next brick that does)
+        const BrickShared<T> sh = table_set(tset);
+        if (pending && !uniform && warp >= NW2) flush_tables(table_set(tset ^ 1u), pF0, pM0, pS0, NW2 * 32, NTHREADS - NW2 * 32);
         if (uniform) {
             // the whole tile (brick + halo) is one label: closed-form moments, no pairs
-            if (tid == 0 && do_mom) {
-                const uint32_t a = (uint32_t)fvalid_n, b = (uint32_t)min(OM, nm - M0), c = (uint32_t)nown;
-                const uint32_t ta_ = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
-                const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6, qc = (c - 1) * c * (2 * c - 1) / 6;
-                uint32_t v[LT_FIELDS];
-                v[0] = a * b * c; v[1] = b * c * ta_; v[2] = a * c * tb; v[3] = a * b * tc;
-                v[4] = b * c * qa; v[5] = c * ta_ * tb; v[6] = b * ta_ * tc;
-                v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
-                v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
-                u64 g[10];
-                int bmn[3], bmx[3];
-                local_to_global(v, gF0, gM0, gS0, g, bmn, bmx);
-                if (carry->valid && carry->label != ref_label) {
-                    global_apply(lt, pt.status, carry->label, carry->g, carry->bmn, carry->bmx);
-                    carry->valid = 0u;
-                }
-                if (!carry->valid) {
-                    carry->valid = 1u; carry->label = ref_label;
-                    for (int i = 0; i < 10; ++i) carry->g[i] = g[i];
-                    for (int i = 0; i < 3; ++i) { carry->bmn[i] = bmn[i]; carry->bmx[i] = bmx[i]; }
-                } else {
-                    for (int i = 0; i < 10; ++i) carry->g[i] += g[i];
-                    for (int i = 0; i < 3; ++i) { carry->bmn[i] = min(carry->bmn[i], bmn[i]); carry->bmx[i] = max(carry->bmx[i], bmx[i]); }
-                }
-            }
+            if (tid == 0 && do_mom)
+                uniform_brick(carry, lt, pt.status, ref_label, (uint32_t)fvalid_n, (uint32_t)min(OM, nm - M0), (uint32_t)nown, gF0, gM0, gS0);
         } else if (!overflow) {
             // ---- P2: block of 15 owned rows x 2 owned planes ---------------------------------------------------------------
             if (warp < NW2 && 1 + 2 * (warp >> 1) <= nown) {
@@ -445,13 +555,13 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                 const uint32_t fm = own_row ? fvalid : 0u;
                 const uint32_t ml = (uint32_t)(15 * wm + lm);               // brick-local row
                 const uint32_t* mbase = masks + q * MPLANE + r;             // + slot * 32; rows +-1, planes +- MPLANE
-                const uint32_t* hlb = hwl + q * 32 + r;
-                const uint32_t* hrb = hwr + q * 32 + r;
+                const uint32_t* hlb = hwl + q * PSTR + r;
+                const uint32_t* hrb = hwr + q * PSTR + r;
                 const uint32_t hrc1 = hrb[0];
                 // halo slots of the five rows with an f-shifted neighbour
-                const uint32_t hlall = hlb[-1] | hlb[0] | hlb[1] | hlb[-32] | hlb[32], hrall = hrb[-1] | hrc1 | hrb[1] | hrb[-32] | hrb[32];
-                const uint32_t* pbase = pres + q * 32 + r;
-                uint32_t pn = pbase[-33] | pbase[-32] | pbase[-31] | pbase[-1] | pbase[0] | pbase[1] | pbase[31] | pbase[32] | pbase[33];
+                const uint32_t hlall = hlb[-1] | hlb[0] | hlb[1] | hlb[-PSTR] | hlb[PSTR], hrall = hrb[-1] | hrc1 | hrb[1] | hrb[-PSTR] | hrb[PSTR];
+                const uint32_t* pbase = pres + q * PSTR + r;
+                uint32_t pn = pbase[-PSTR - 1] | pbase[-PSTR] | pbase[-PSTR + 1] | pbase[-1] | pbase[0] | pbase[1] | pbase[PSTR - 1] | pbase[PSTR] | pbase[PSTR + 1];
                 const uint32_t PU = __reduce_or_sync(FULL, own_row ? pn : 0u);       // labels around the block
                 const uint32_t PC = __reduce_or_sync(FULL, own_row ? pbase[0] : 0u);  // labels in the block
 
@@ -459,8 +569,9 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                     uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, kx = 0, ky = 0, ks = 0;
                     const uint32_t up = ls ? 0xFFFFFFFFu : 0u;
                     int idx = 0;
-                    for (int i = 0; i < nlab; ++i) {                      // a counter, not ffs: BREV + FLO are slow-pipe instructions
-                        if (!((PC >> i) & 1u)) continue;
+                    for (uint32_t rest = PC; rest;) {                     // the slots are places in a hashed list: not dense
+                        const int i = 31 - __clz(rest);
+                        rest ^= 1u << i;
                         const uint32_t M = mbase[i * 32] & fm;
                         const uint32_t n = (uint32_t)__popc(M);
                         uint32_t sf = 0u, sff = 0u;
@@ -505,7 +616,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                             inc[1] = (lo ? 0u : ff) | (lo ? fmm << 16 : 0u);
                             inc[2] = (lo ? 0u : fmm) | (lo ? fss << 16 : 0u);
                             inc[3] = lo ? 0u : fss;
-                            pair_add_packed<T>(sh, pt, Vox<T>::key(a, b), inc);
+                            pair_add_call<T>(sh, pt, Vox<T>::key(a, b), inc[0], inc[1], inc[2], inc[3]);
                         }
                         nres = 0;
                     };
@@ -520,8 +631,9 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
                             slots |= (u64)i << (5 * j);
                             pcr &= pcr - 1u;
                         }
-                        for (int b = 0; b < nlab; ++b) {
-                            if (!((PU >> b) & 1u)) continue;
+                        for (uint32_t rest = PU; rest;) {
+                            const int b = 31 - __clz(rest);
+                            rest ^= 1u << b;
                             const uint32_t* qb = mbase + b * 32;
                             const uint32_t c0 = qb[-1], c1 = qb[0], c2 = qb[1];
                             const uint32_t d0 = qb[-MPLANE - 1], d1 = qb[-MPLANE], d2 = qb[-MPLANE + 1];
@@ -562,72 +674,29 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             }
         } else {
             // ---- G: more than K labels in the brick: every owned voxel on its own, straight from the tile -------------------
-            const int nvo = RW * OM * nown;
-            for (int i = tid; i < nvo; i += NTHREADS) {
-                const int f = i % RW, m = (i / RW) % OM, s = i / (RW * OM);
-                if (F0 + f >= nf || M0 + m >= nm) continue;
-                const T* qv = tile + ((s + 1) * TM + (m + 1)) * TRE + HV + f;
-                const uint32_t a = qv[0];
-                if (do_mom) {
-                    const uint32_t uf = f, um = m, us = s;
-                    uint32_t v[LT_FIELDS] = {1u, uf, um, us, uf * uf, uf * um, uf * us, um * um, um * us, us * us, uf, um, us, uf, um, us};
-                    label_add<T>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
-                }
-                if (do_p6) {
-                    const uint32_t n0 = qv[1], n1 = qv[TRE], n2 = qv[PLANEE];
-                    if (n0 != a) pair_add<T>(sh, pt, a, n0, a < n0 ? 0 : 1, 1u);
-                    if (n1 != a) pair_add<T>(sh, pt, a, n1, a < n1 ? 2 : 3, 1u);
-                    if (n2 != a) pair_add<T>(sh, pt, a, n2, a < n2 ? 4 : 5, 1u);
-                }
-                if (do_w18) {
-#pragma unroll 1
-                    for (int k = 0; k < 18; ++k) {
-                        const uint32_t b = qv[neighbour_offset<TRE, PLANEE>(k)];
-                        if (b == a) continue;
-                        bool seen = false;
-                        for (int kk = 0; kk < k; ++kk) seen |= ((uint32_t)qv[neighbour_offset<TRE, PLANEE>(kk)] == b);
-                        if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
-                    }
-                }
-            }
+            brick_per_voxel<T>(tile, sh, lt, pt, tid, nown, F0, M0, nf, nm, gF0, gM0, gS0, do_mom, do_p6, do_w18);
         }
         MK_TICK(3);
+        // (skipping this barrier for a one-label brick costs registers: ptxas spills 188 bytes instead of 84 around it)
         __syncthreads();
         MK_TICK(4);
 
         // ---- F: flush the per-brick tables ---------------------------------------------------------------------------------
-        if (!uniform) {
-            for (int i = tid; i < LT_SLOTS; i += NTHREADS) {
-                const uint32_t L = sh.lt_key[i];
-                if (L == TA_EMPTY32) continue;
-                uint32_t* d = &sh.lt_val[i * LT_FIELDS];
-                label_to_global(lt, pt.status, L, d, gF0, gM0, gS0);
-#pragma unroll
-                for (int f = 0; f < LT_FIELDS; ++f) d[f] = (f >= 10 && f < 13) ? 0xFFFFFFFFu : 0u;
-                sh.lt_key[i] = TA_EMPTY32;
-            }
-            for (int i = tid; i < PT_SLOTS; i += NTHREADS) {
-                const PKey key = sh.pt_key[i];
-                if (key == Vox<T>::PEMPTY) continue;
-                uint32_t* d = &sh.pt_val[i * PT_WORDS];
-                const int slot = ta_pair_slot(pt, Vox<T>::key64(key));
-#pragma unroll
-                for (int idx = 0; idx < 7; ++idx) {
-                    const uint32_t n = (d[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
-                    if (n && slot >= 0) atomicAdd(&pt.vals[(size_t)slot * TA_PAIR_STRIDE + (idx == 0 ? 6 : idx - 1)], n);
-                }
-#pragma unroll
-                for (int w2 = 0; w2 < PT_WORDS; ++w2) d[w2] = 0u;
-                sh.pt_key[i] = Vox<T>::PEMPTY;
-            }
-        }
+        if (!uniform) { pending = true; tset ^= 1u; pF0 = gF0; pM0 = gM0; pS0 = gS0; }   // left to a later iteration (or to the end of the kernel)
         // No barrier here: the next brick's P1 touches neither these tables nor this brick's label list (the list and the
         // overflow flag are ping-pong), and the barrier after it comes before anything that does.
         {
             // back to all-zero masks: every thread clears the slots its own P1 row may have written (the same thread writes
             // them again in the next P1, so program order is enough)
-            uint32_t* mrow = masks + (2 * (warp >> 1) + (lane >> 4)) * MPLANE + 16 * (warp & 1) + (lane & 15);
-            for (int sl = 0; sl < nlab; ++sl) mrow[sl * 32] = 0u;
+            const int q = 2 * (warp >> 1) + (lane >> 4), r = 16 * (warp & 1) + (lane & 15);   // as in P1
+            if (2 * (warp >> 1) <= nown + 1) {
+                uint32_t* mrow = masks + q * MPLANE + r;
+                for (uint32_t mine = pres[q * PSTR + r]; mine;) {
+                    const int sl = 31 - __clz(mine);
+                    mine ^= 1u << sl;
+                    mrow[sl * 32] = 0u;
+                }
+            }
         }
         if (tid < K) blab[tid] = TA_EMPTY32;
         if (tid == 0) {
@@ -643,6 +712,11 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     if (clocked) for (int k = 0; k < 8; ++k) atomicAdd(&P.phase_cycles[(warp == 0 ? 0 : 8) + k], tk[k]);
 #endif
 #undef MK_TICK
+    // the last brick's tables (`pending` is CTA-uniform)
+    if (pending) {
+        __syncthreads();
+        flush_tables(table_set(tset ^ 1u), pF0, pM0, pS0, 0, NTHREADS);
+    }
     if (tid == 0 && carry->valid) global_apply(lt, pt.status, carry->label, carry->g, carry->bmn, carry->bmx);
 }
 
