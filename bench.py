@@ -41,12 +41,13 @@ UNIT = "Gvoxel/s"
 
 
 def ncu_traffic_bytes(config, world):
-    """DRAM bytes per scan-kernel launch from the committed `ncu --set full` capture (profiles/), when one exists
+    """DRAM bytes per scan (its three launches: the two pre-pass kernels and the mask kernel) from the committed
+    `ncu --set full` capture (profiles/), when one exists
     for this workload; None otherwise (never measured live: a number taken under a profiler is not a bench value)."""
     if config != "C3" or world != 1:
         return None
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_scan_c3_metrics.json")))["dram_bytes_per_launch"])
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_scan_c3_metrics.json")))["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -357,7 +358,8 @@ def main():
     own_vox = (scan.g_hi - scan.g_lo) * Y * X
     achieved = own_vox * elem / (scan_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_bytes(args.config, world), "kernel": "ta::scan_kernel", "kernel_ms": scan_ms_avg,
+                "traffic": ncu_traffic_bytes(args.config, world), "kernel": "ta::mk::mask_kernel (with its pre-pass ta::pp::classify_cores_kernel + decide_kernel: the scan's launches)",
+                "kernel_ms": scan_ms_avg,
                 "kernel_ms_per_rank": scan_ms_per_rank, "algorithmic_bytes_per_voxel": elem, "peak_source": peak_src}
 
     # ---- parity of the sharded result: merged tables == one GPU scanning the whole volume (outside the timed region) ------

@@ -212,6 +212,11 @@ template <typename V> inline V __shfl_sync(unsigned mask, V var, int src, int wi
     // and the one after that needs all lanes to arrive first, i.e. to have left this function
     return o;
 }
+template <typename V> inline V __shfl_xor_sync(unsigned mask, V var, int lane_mask, int width = 32) {
+    return __shfl_sync(mask, var, emu::lane() ^ lane_mask, width);
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0u; }
 template <typename V> inline V __shfl_up_sync(unsigned mask, V var, unsigned delta, int width = 32) {
     const int ln = emu::lane();
     const V got = __shfl_sync(mask, var, ln >= (int)delta ? ln - (int)delta : ln, width);

@@ -11,6 +11,7 @@ static unsigned long long g_user_stat[16];
 
 #include "../../tissue_analysis_b200/csrc/ta_scan.cuh"
 #include "../../tissue_analysis_b200/csrc/ta_scan_mask.cuh"
+#include "../../tissue_analysis_b200/csrc/ta_prepass.cuh"
 
 namespace ta { alignas(128) unsigned char smem_raw[160 * 1024]; namespace mk { alignas(128) unsigned char smem_raw[160 * 1024]; } }
 void ta::ta_emu_yield() { emu::g_progress = true; emu::yield(); }
@@ -52,8 +53,9 @@ static void add_voxel(const Vol& V, int f, int m, int s, long slow_offset, Label
 }
 
 static long g_wm = 2, g_ws = 3;      // metric weights of the blob volumes (mid, slow axis); --stats uses 1, 1 (round cells)
-enum Which { PRODUCT, MASK, NWHICH };
-static const char* which_name[] = {"scan_kernel<T,false>", "mk::mask_kernel<T>"};
+static unsigned long g_skipped = 0, g_pp_bricks = 0;      // bricks the pre-pass took out of the queue / saw
+enum Which { PRODUCT, MASK, MASK_PP, NWHICH };      // MASK_PP: the pre-pass (ta_prepass.cuh) in front of the mask kernel
+static const char* which_name[] = {"scan_kernel<T,false>", "mk::mask_kernel<T>", "pp:: pre-pass + mk::mask_kernel<T>"};
 
 template <typename T>
 static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_hi, long slow_offset, int nlabels, int mode,
@@ -66,6 +68,15 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     if (sizeof(T) == 2 && nlabels >= 3 && (seed & 1u)) names[1] = 0xFFFFu;      // the uint16 value that doubles as the MIXED code
     if (mode == 0) {
         for (auto& v : V.d) v = names[rng() % nlabels];
+    } else if (mode == 3) {          // background with a few balls in it: whole regions of one-label bricks (the pre-pass's case)
+        for (auto& v : V.d) v = names[0];
+        for (int k = 1; k < nlabels; ++k) {
+            const int cx = rng() % nf, cy = rng() % nm, cz = rng() % nbuf, rad = 4 + rng() % 9;
+            for (int s = std::max(0, cz - rad); s < std::min(nbuf, cz + rad + 1); ++s)
+                for (int m = std::max(0, cy - rad); m < std::min(nm, cy + rad + 1); ++m)
+                    for (int f = std::max(0, cx - rad); f < std::min(nf, cx + rad + 1); ++f)
+                        if ((f - cx) * (f - cx) + (m - cy) * (m - cy) + (s - cz) * (s - cz) <= rad * rad) V.d[((size_t)s * nm + m) * nf + f] = names[k];
+        }
     } else if (mode == 2) {          // one label almost everywhere: every lane of a warp carries a nearly full block of it
         for (auto& v : V.d) v = names[rng() % 97 == 0 ? rng() % nlabels : 0];
     } else {
@@ -104,20 +115,37 @@ static int run_case(Which which, int nf, int nm, int nbuf, int own_lo, int own_h
     P.vol = vol.data(); P.nf = nf; P.nm = nm; P.ns = nbuf; P.own_lo = own_lo; P.own_hi = own_hi; P.slow_offset = slow_offset;
     const int seg = 16 / (int)sizeof(T);
     P.nbf = (nf + NFS * seg - 1) / (NFS * seg); P.nbm = (nm + BM - 1) / BM; P.nbs = (own_hi - own_lo + BS - 1) / BS;
-    if (which == MASK) { P.nbf = (nf + mk::RW - 1) / mk::RW; P.nbm = (nm + mk::OM - 1) / mk::OM; P.nbs = (own_hi - own_lo + mk::ZB - 1) / mk::ZB; }
+    if (which != PRODUCT) { P.nbf = (nf + mk::RW - 1) / mk::RW; P.nbm = (nm + mk::OM - 1) / mk::OM; P.nbs = (own_hi - own_lo + mk::ZB - 1) / mk::ZB; }
     P.flags = 7u; P.vec_ok = 0; P.use_tma = use_tma; P.brick_counter = &brick_counter; P.phase_cycles = nullptr; P.diag = nullptr;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     {
         // what ta_api.cu encodes for the kernels: the bound buffer, one box = tile (brick + halo)
         ta::EmuTmap em{vol.data(), nf, nm, nbuf, (int)sizeof(T), ROWV * seg, BM + 2, BS + 2};
-        if (which == MASK) { em.box0 = mk::Geo<T>::TRE; em.box1 = mk::TM; em.box2 = mk::TP; }
+        if (which != PRODUCT) { em.box0 = mk::Geo<T>::TRE; em.box1 = mk::TM; em.box2 = mk::TP; }
         static_assert(sizeof(ta::EmuTmap) <= sizeof(CUtensorMap), "the emulated map lives in the bytes of the real one");
         memcpy(&tmap, &em, sizeof em);
     }
     bool ok = true;
+    // the pre-pass needs rows of whole 16-byte vectors (the host checks vec_ok); other shapes run the mask kernel alone
+    std::vector<uint32_t> core;
+    std::vector<unsigned int> work_list;
+    unsigned int work_count = 0;
+    if (which == MASK_PP && nf % seg == 0) {
+        const unsigned total = (unsigned)P.nbf * P.nbm * P.nbs;
+        core.assign(total, 0u); work_list.assign(total, 0u);
+        pp::PrepassParams Q{};
+        Q.vol = vol.data(); Q.nf = nf; Q.nm = nm; Q.ns = nbuf; Q.own_lo = own_lo; Q.own_hi = own_hi; Q.slow_offset = slow_offset;
+        Q.nbf = P.nbf; Q.nbm = P.nbm; Q.nbs = P.nbs; Q.core = core.data(); Q.work_list = work_list.data(); Q.work_count = &work_count;
+        Q.do_mom = 1u;
+        ok = emu::run_block(0, 1, 256, [&]() { pp::classify_cores_kernel<T>(Q); });
+        for (unsigned block = 0; block < (total + 255) / 256 && ok; ++block)
+            ok = emu::run_block(block, (total + 255) / 256, 256, [&]() { pp::decide_kernel(Q, lt, status.data()); });
+        P.work_list = work_list.data(); P.work_count = &work_count;
+        g_skipped += total - work_count; g_pp_bricks += total;
+    }
     for (unsigned block = 0; block < 2 && ok; ++block) {           // the second block finds the brick counter exhausted
-        if (which == MASK) ok = emu::run_block(block, 2, mk::NTHREADS, [&]() { if (P.flags == 7u) mk::mask_kernel<T, 7>(P, lt, pt, tmap); else mk::mask_kernel<T, -1>(P, lt, pt, tmap); });
+        if (which != PRODUCT) ok = emu::run_block(block, 2, mk::NTHREADS, [&]() { if (P.flags == 7u) mk::mask_kernel<T, 7>(P, lt, pt, tmap); else mk::mask_kernel<T, -1>(P, lt, pt, tmap); });
         else ok = emu::run_block(block, 2, NTHREADS, [&]() {
             scan_kernel<T, false>(P, lt, pt, tmap);
         });
@@ -200,7 +228,9 @@ int main(int argc, char** argv) {
         const Which which = only >= 0 ? (Which)only : (Which)(c % NWHICH);
         const bool wide = (c / NWHICH) % 3 == 2;                                   // every third round: uint32 labels
         const int maxf = wide ? 150 : 300;
-        const int nf = 1 + rng() % maxf, nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
+        int nf = 1 + rng() % maxf;
+        const int nm = 1 + rng() % 36, nbuf = 1 + rng() % 19;
+        if (which == MASK_PP) nf = (nf + 7) / 8 * 8;                               // the pre-pass wants rows of whole 16-byte vectors
         int lo = 0, hi = nbuf; long off = 0;
         if (c % 5 == 1 && nbuf >= 3) { lo = 1; hi = nbuf - 1; off = 1000 + rng() % 5000; }
         // c % 11 == 3: hundreds of labels in noise -- the per-brick label and pair tables fill up and spill to the global ones
@@ -211,6 +241,14 @@ int main(int argc, char** argv) {
                     : run_case<uint16_t>(which, nf, nm, nbuf, lo, hi, off, nl, mode, seed, use_tma);
         ++ran;
     }
+    if (only < 0 || only == MASK_PP) {
+        // background with balls, several bricks each way: one launch, a slab in the middle (halo planes owned by nobody), uint32
+        bad += run_case<uint16_t>(MASK_PP, 136, 95, 26, 0, 26, 0, 4, 3, rng(), 1);
+        bad += run_case<uint16_t>(MASK_PP, 104, 64, 30, 3, 27, 4000, 3, 3, rng(), 0);
+        bad += run_case<uint32_t>(MASK_PP, 100, 70, 20, 0, 20, 0, 3, 3, rng(), 1);
+        ran += 3;
+    }
+    printf("pre-pass: %lu of %lu bricks left the queue\n", g_skipped, g_pp_bricks);
     printf("kernel_emu_check: %d kernel runs on the CPU emulation, %d mismatches\n", ran, bad);
     return bad ? 1 : 0;
 }

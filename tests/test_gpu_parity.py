@@ -416,3 +416,47 @@ def test_kernel_variants_give_the_same_tables(monkeypatch, capfd):
             for a, b in zip(got, want):
                 assert np.array_equal(a, b), (env, flags)
     capfd.readouterr()        # the phase shares go to stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["uint16", "uint32"])
+def test_prepass_leaves_the_tables_unchanged(monkeypatch, dtype):
+    """The one-label pre-pass (ta_prepass.cuh: bricks whose neighbourhood is one label leave the scan's queue and get their
+    closed-form moments from decide_kernel) against the scan on its own, on a dome with thick background around it, ragged
+    bricks on every side, as one launch and as three slabs; and against the CPU oracle."""
+    from tissue_analysis_b200 import _native
+    from tissue_analysis_b200.engine import memory_layout
+    from oracle import c_onepass
+    img = tissue_image((200, 130, 77), 60, seed=5, dome=True, dtype=dtype)
+    view = np.ascontiguousarray(memory_layout(img)[0])
+
+    def tables(prepass, ranges=None):
+        with monkeypatch.context() as m:
+            m.setenv("TA_PREPASS", prepass)
+            ctx = _native.Context()
+            ctx.bind_host(view)
+            if ranges is None:
+                ctx.run_pass(_native.PASS_ALL, int(view.max()) if dtype == "uint32" else 0)
+            else:
+                ctx.run_pass_ranges(ranges, [None] * len(ranges), _native.PASS_ALL, int(view.max()) if dtype == "uint32" else 0)
+            out = ctx.label_table() + ctx.pair_table()
+            ctx.close()
+        return out
+
+    want = tables("0")
+    got = tables("1")
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    ns = view.shape[0]
+    got3 = tables("1", [(0, 24), (24, 56), (56, ns)])
+    for a, b in zip(got3, want):
+        assert np.array_equal(a, b)
+    nrows = got[0].size
+    ref = c_onepass.onepass(view, nrows=nrows)
+    count, s1, s2, bbox, lo, hi, faces, wall18 = got
+    for a, k in ((count, "count"), (s1, "s1"), (s2, "s2"), (lo, "lo"), (hi, "hi"), (faces, "faces"), (wall18, "wall18")):
+        assert np.array_equal(a, ref[k]), k
+    present = ref["count"] > 0
+    assert np.array_equal(bbox[present], ref["bbox"][present])
+

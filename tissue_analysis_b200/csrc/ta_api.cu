@@ -14,6 +14,7 @@
 #include "ta_kernels.cuh"
 #include "ta_scan.cuh"
 #include "ta_scan_mask.cuh"
+#include "ta_prepass.cuh"
 #include "ta_second_pass.cuh"
 
 struct ta_ctx {
@@ -54,6 +55,9 @@ struct ta_ctx {
     double* d_evecs = nullptr;
     size_t eig_alloc_rows = 0;
     u64* phase_cycles = nullptr;
+    uint32_t* brick_core = nullptr;      // pre-pass (ta_prepass.cuh): one-label cores, then the scan's work list
+    unsigned int* work_list = nullptr;
+    size_t prepass_alloc = 0;            // bricks both have room for
     u64* diag_host = nullptr;         // host-mapped [8], survives a kernel trap
     u64* diag_dev = nullptr;
 
@@ -185,6 +189,7 @@ int ta_ctx_destroy(ta_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->sort_keys[i]); cudaFree(ctx->sort_vals[i]); }
     cudaFree(ctx->cub_temp); cudaFree(ctx->records);
     cudaFree(ctx->d_evals); cudaFree(ctx->d_evecs); cudaFree(ctx->phase_cycles); cudaFree(ctx->fetch_scratch);
+    cudaFree(ctx->brick_core); cudaFree(ctx->work_list);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->diag_host) cudaFreeHost(ctx->diag_host);
@@ -423,6 +428,32 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
     if (total == 0) return TA_OK;
     TA_CUDA(cudaMemsetAsync(&ctx->counters[0], 0, sizeof(unsigned int), st));
     if (mask) {
+        // The pre-pass takes the interior of one-label regions (background) out of the queue.  TA_PREPASS=0 / 1 forces it off /
+        // on; by default it runs from 4096 bricks up (it costs a fifth of a read of an all-tissue volume, a full read of
+        // background, and two launches).
+        const char* pe = getenv("TA_PREPASS");
+        const bool prepass = P.vec_ok && (pe ? atoi(pe) != 0 : total >= 4096);
+        if (prepass) {
+            if (ctx->prepass_alloc < total) {
+                cudaFree(ctx->brick_core); cudaFree(ctx->work_list);
+                ctx->brick_core = nullptr; ctx->work_list = nullptr; ctx->prepass_alloc = 0;
+                TA_CUDA(cudaMalloc(&ctx->brick_core, total * sizeof(uint32_t)));
+                TA_CUDA(cudaMalloc(&ctx->work_list, total * sizeof(unsigned int)));
+                ctx->prepass_alloc = total;
+            }
+            TA_CUDA(cudaMemsetAsync(&ctx->counters[3], 0, sizeof(unsigned int), st));
+            ta::pp::PrepassParams Q{};
+            Q.vol = P.vol; Q.nf = (int)P.nf; Q.nm = (int)P.nm; Q.ns = (int)P.ns; Q.own_lo = (int)own_lo; Q.own_hi = (int)own_hi;
+            Q.slow_offset = P.slow_offset; Q.nbf = P.nbf; Q.nbm = P.nbm; Q.nbs = P.nbs;
+            Q.core = ctx->brick_core; Q.work_list = ctx->work_list; Q.work_count = &ctx->counters[3]; Q.do_mom = P.flags & 1u;
+            const int cgrid = (int)std::min<size_t>((total + 7) / 8, (size_t)ctx->num_sms * 8);
+            if (ctx->elem == 2) ta::pp::classify_cores_kernel<uint16_t><<<cgrid, 256, 0, st>>>(Q);
+            else ta::pp::classify_cores_kernel<uint32_t><<<cgrid, 256, 0, st>>>(Q);
+            ta::pp::decide_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, ctx->lt, ctx->pt.status);
+            ctx->launches += 2;
+            TA_CUDA(cudaGetLastError());
+            P.work_list = ctx->work_list; P.work_count = &ctx->counters[3];
+        }
         const int per_sm = ctx->elem == 2 ? 3 : 2;
         const int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * per_sm);
         const size_t smem = ctx->elem == 2 ? ta::mk::smem_bytes<uint16_t>() : ta::mk::smem_bytes<uint32_t>();
@@ -606,7 +637,9 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
                 for (int k = 0; k < 6; ++k) t += (double)cyc[8 * w + k];
                 fprintf(stderr, "[ta mask kernel, %s warp]", w ? "last" : "first");
                 for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.1f%%", pn[k], t > 0 ? 100.0 * cyc[8 * w + k] / t : 0.0);
-                fprintf(stderr, " | bricks %llu, one-label %llu, cycles per brick %.0f\n", cyc[8 * w + 7], cyc[8 * w + 6], cyc[8 * w + 7] ? t / cyc[8 * w + 7] : 0.0);
+                if (w == 0) fprintf(stderr, " | bricks %llu, one-label %llu, cycles per brick %.0f\n", cyc[7], cyc[6], cyc[7] ? t / cyc[7] : 0.0);
+                else fprintf(stderr, " | cycles per one-label brick %.0f, per other brick %.0f\n", cyc[6] ? (double)cyc[14] / cyc[6] : 0.0,
+                             cyc[7] > cyc[6] ? (t - (double)cyc[14]) / (cyc[7] - cyc[6]) : 0.0);
             }
         }
         fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");

@@ -54,6 +54,8 @@ struct ScanParams {
     int vec_ok;                  // rows are 16-byte aligned: 128-bit loads allowed
     int use_tma;                 // the tile (brick + halo) is one TMA box copy (needs vec_ok and a tensor map)
     unsigned int* brick_counter; // dynamic brick scheduler
+    const unsigned int* work_list;   // optional: the bricks to scan, in this order (mask kernel; ta_prepass.cuh) ...
+    const unsigned int* work_count;  // ... and how many
     u64* phase_cycles;           // optional [16]: per-phase clock64 totals of thread 0 of every CTA (profiling aid)
     u64* diag;                   // [8] host-mapped: what a CTA was doing when it gave up waiting for a tile copy
 };

@@ -499,7 +499,6 @@ scan_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     typedef typename Vox<T>::Code Code;
     typedef typename Vox<T>::PKey PKey;
     constexpr int SEG = Vox<T>::SEG;
-    constexpr int LOG_SEG = Vox<T>::LOG_SEG;
     constexpr uint32_t MIXED = Vox<T>::MIXED;
     constexpr int ROWE = ROWV * SEG;               // elements per tile row
     constexpr int PLANEE = (BM + 2) * ROWE;        // elements per tile plane

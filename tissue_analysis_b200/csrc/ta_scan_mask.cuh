@@ -80,6 +80,12 @@ __device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b) {
 #endif
 
 #ifdef TA_EMU_TMA
+inline uint4 mk_ld128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+#else
+__device__ __forceinline__ uint4 mk_ld128(const void* p) { return ld_stream_128(p); }
+#endif
+
+#ifdef TA_EMU_TMA
 inline int mk_tid() { return (int)threadIdx.x; }
 #else
 __device__ __forceinline__ int mk_tid() {
@@ -178,15 +184,19 @@ struct Carry {
 // stalls grew from 0.3 to 1.9 cycles per issue when the loop body passed it), so everything rare is a call ----------------
 
 // thread 0: closed-form moments of a brick whose tile is one label; consecutive ones of the same label are merged
-__device__ __noinline__ void uniform_brick(Carry* carry, LabelTable lt, uint32_t* status, uint32_t label, uint32_t a, uint32_t b,
-                                           uint32_t c, u64 gF0, u64 gM0, u64 gS0) {
+// brick-local sums of an a x b x c box of one label at the brick's origin
+__device__ __forceinline__ void one_label_sums(uint32_t a, uint32_t b, uint32_t c, uint32_t v[LT_FIELDS]) {
     const uint32_t ta_ = a * (a - 1) / 2, tb = b * (b - 1) / 2, tc = c * (c - 1) / 2;
     const uint32_t qa = (a - 1) * a * (2 * a - 1) / 6, qb = (b - 1) * b * (2 * b - 1) / 6, qc = (c - 1) * c * (2 * c - 1) / 6;
-    uint32_t v[LT_FIELDS];
     v[0] = a * b * c; v[1] = b * c * ta_; v[2] = a * c * tb; v[3] = a * b * tc;
     v[4] = b * c * qa; v[5] = c * ta_ * tb; v[6] = b * ta_ * tc;
     v[7] = a * c * qb; v[8] = a * tb * tc; v[9] = a * b * qc;
     v[10] = 0; v[11] = 0; v[12] = 0; v[13] = a - 1; v[14] = b - 1; v[15] = c - 1;
+}
+__device__ __noinline__ void uniform_brick(Carry* carry, LabelTable lt, uint32_t* status, uint32_t label, uint32_t a, uint32_t b,
+                                           uint32_t c, u64 gF0, u64 gM0, u64 gS0) {
+    uint32_t v[LT_FIELDS];
+    one_label_sums(a, b, c, v);
     u64 g[10];
     int bmn[3], bmx[3];
     local_to_global(v, gF0, gM0, gS0, g, bmn, bmx);
@@ -285,14 +295,13 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 2 ? 3 : 2))
 mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Vox<T>::PKey PKey;
     typedef Geo<T> G;
-    constexpr int HV = G::HV, TRE = G::TRE, NW = G::NW, ROWV = G::ROWV;
+    constexpr int HV = G::HV, TRE = G::TRE, NW = G::NW;
     constexpr int PLANEE = TM * TRE;
     constexpr uint32_t FULL = 0xffffffffu;
     static_assert(K <= 32 && 5 * KB <= 64, "lane l looks at blab[l]; the slots of a round are packed 5 bits each");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
-    uint4* tilev = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + G::TILE_BYTES);            // [TP][MPLANE]: own bits of (slot, row)
     uint32_t* pres = masks + TP * MPLANE;                                                // [TP][32]: slots with a bit in the row
     uint32_t* hwl = pres + TP * PSTR;                                                      // [TP][32]: slots in the left halo voxel of the row
@@ -308,7 +317,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         x.pt_key = reinterpret_cast<PKey*>(x.pt_val + PT_SLOTS * PT_WORDS);
         return x;
     };
-    // ctr: [0..1] brick index ping-pong, [2..3] overflow flag ping-pong, [4..5] mbarrier, [8..10] / [12..14] brick origin
+    // ctr: [0..1] brick index ping-pong, [2..3] overflow flag ping-pong, [4..5] mbarrier, [6] moment queue, [8..10] / [12..14] brick origin
     // ping-pong, [16 .. 16 + 2 K) the brick's label list, ping-pong
     unsigned int* ctr = reinterpret_cast<unsigned int*>(tables + NSETS * TBLW);
     Carry* carry = reinterpret_cast<Carry*>(ctr + 16 + 2 * K + (2 * K) % 2 + 16);
@@ -318,7 +327,8 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const T* vol = reinterpret_cast<const T*>(P.vol);
-    const unsigned int total = (unsigned int)P.nbf * P.nbm * P.nbs;
+    // the queue: every brick of the launch, or the work list the pre-pass left (ta_prepass.cuh)
+    const unsigned int total = P.work_list ? *P.work_count : (unsigned int)P.nbf * P.nbm * P.nbs;
     const uint32_t pflags = FLAGS >= 0 ? (uint32_t)FLAGS : P.flags;
     const bool do_mom = pflags & 1u, do_p6 = pflags & 2u, do_w18 = pflags & 4u;
     const bool do_pairs = do_p6 || do_w18;
@@ -376,7 +386,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             TA_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         carry->valid = 0u;
-        ctr[2] = 0u; ctr[3] = 0u;
+        ctr[2] = 0u; ctr[3] = 0u; ctr[6] = 0u;
     }
 
     // thread 0: origin of a brick into its ping-pong slot (the divisions are made once per brick, not once per thread)
@@ -396,7 +406,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         const unsigned int b0 = atomicAdd(P.brick_counter, 1u);
         ctr[0] = b0;
         if (b0 < total) {
-            set_origin(b0, 0u);
+            set_origin(P.work_list ? P.work_list[b0] : b0, 0u);
             if (use_tma) issue_box(0u);
         }
     }
@@ -404,7 +414,7 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
 
 #ifdef TA_WITH_PHASE_TIMING
     // phase clocks of lane 0 of warp 0 ([0..6]) and of the last warp ([8..14]): tile wait, P1, barrier, P2, barrier, flush;
-    // [6] / [14]: one-label bricks altogether; [7]: bricks, [15]: one-label bricks
+    // [6]: one-label bricks, [14]: cycles the last warp spent in them; [7], [15]: bricks
     u64 tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     u64 t_last = (u64)clock64();
     const bool clocked = P.phase_cycles && lane == 0 && (warp == 0 || warp == TP - 1);
@@ -414,13 +424,16 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
 #endif
     for (unsigned iter = 0;; ++iter) {
         const unsigned cur = iter & 1u, nxt = cur ^ 1u;
+#ifdef TA_WITH_PHASE_TIMING
+        const u64 t_iter0 = (u64)clock64();
+#endif
         const unsigned int brick = ctr[cur];
         if (brick >= total) break;
         uint32_t* blab = ctr + 16 + K * cur;
         if (tid == 0) {
             const unsigned int nb = atomicAdd(P.brick_counter, 1u);
             ctr[nxt] = nb;
-            if (nb < total) set_origin(nb, nxt);
+            if (nb < total) set_origin(P.work_list ? P.work_list[nb] : nb, nxt);
         }
         const int F0 = (int)ctr[8 + 4 * cur], M0 = (int)ctr[9 + 4 * cur], S0 = (int)ctr[10 + 4 * cur];
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
@@ -468,6 +481,15 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         }
 
         MK_TICK(0);
+#ifdef TA_WITH_PHASE_TIMING
+        // measurement aid of the timing build (flag 0x800): staging only -- every tile is fetched and dropped, which times the
+        // box copies on their own, one in flight per CTA
+        if (FLAGS < 0 && (pflags & 0x800u)) {
+            __syncthreads();
+            if (tid == 0 && use_tma && ctr[nxt] < total) issue_box(nxt);
+            continue;
+        }
+#endif
         // ---- P1: block of 16 rows x 2 planes: runs of the lane's row -> brick slots, row masks ---------------------------
         const uint32_t ref_label = tile[HV];               // plane 0, row 0, first owned column
         const int q1 = 2 * (warp >> 1) + (lane >> 4);      // tile plane of the lane
@@ -545,132 +567,146 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             if (tid == 0 && do_mom)
                 uniform_brick(carry, lt, pt.status, ref_label, (uint32_t)fvalid_n, (uint32_t)min(OM, nm - M0), (uint32_t)nown, gF0, gM0, gS0);
         } else if (!overflow) {
-            // ---- P2: block of 15 owned rows x 2 owned planes ---------------------------------------------------------------
-            if (warp < NW2 && 1 + 2 * (warp >> 1) <= nown) {
-                const int wm = warp & 1, s0 = 2 * (warp >> 1);              // s0: brick-local plane of the lower half-warp
-                const int lm = lane & 15, ls = lane >> 4;
-                const bool own_row = (lm < 15) && (s0 + ls < nown) && (M0 + 15 * wm + lm < nm);
-                const int r = own_row ? 1 + 15 * wm + lm : 1;               // idle lanes look at a harmless row
-                const int q = own_row ? 1 + s0 + ls : 1;
-                const uint32_t fm = own_row ? fvalid : 0u;
-                const uint32_t ml = (uint32_t)(15 * wm + lm);               // brick-local row
-                const uint32_t* mbase = masks + q * MPLANE + r;             // + slot * 32; rows +-1, planes +- MPLANE
-                const uint32_t* hlb = hwl + q * PSTR + r;
-                const uint32_t* hrb = hwr + q * PSTR + r;
-                const uint32_t hrc1 = hrb[0];
-                // halo slots of the five rows with an f-shifted neighbour
-                const uint32_t hlall = hlb[-1] | hlb[0] | hlb[1] | hlb[-PSTR] | hlb[PSTR], hrall = hrb[-1] | hrc1 | hrb[1] | hrb[-PSTR] | hrb[PSTR];
-                const uint32_t* pbase = pres + q * PSTR + r;
-                uint32_t pn = pbase[-PSTR - 1] | pbase[-PSTR] | pbase[-PSTR + 1] | pbase[-1] | pbase[0] | pbase[1] | pbase[PSTR - 1] | pbase[PSTR] | pbase[PSTR + 1];
-                const uint32_t PU = __reduce_or_sync(FULL, own_row ? pn : 0u);       // labels around the block
-                const uint32_t PC = __reduce_or_sync(FULL, own_row ? pbase[0] : 0u);  // labels in the block
-
-                if (do_mom) {
-                    uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, kx = 0, ky = 0, ks = 0;
-                    const uint32_t up = ls ? 0xFFFFFFFFu : 0u;
-                    int idx = 0;
-                    for (uint32_t rest = PC; rest;) {                     // the slots are places in a hashed list: not dense
-                        const int i = 31 - __clz(rest);
-                        rest ^= 1u << i;
-                        const uint32_t M = mbase[i * 32] & fm;
-                        const uint32_t n = (uint32_t)__popc(M);
-                        uint32_t sf = 0u, sff = 0u;
-                        if (M) bit_moments(M, n, sf, sff);
-                        const uint32_t nml = n * ml;
-                        const uint32_t r1 = __reduce_add_sync(FULL, n | (sf << 10));                 // n < 2^10, sum f < 2^15
-                        const uint32_t r2 = __reduce_add_sync(FULL, nml | ((sf & up) << 15));        // sum n m < 2^15, upper sum f < 2^14
-                        const uint32_t r3 = __reduce_add_sync(FULL, sff);
-                        const uint32_t r4 = __reduce_add_sync(FULL, nml * ml);
-                        const uint32_t r5 = __reduce_add_sync(FULL, sf * ml);
-                        const uint32_t r6 = __reduce_add_sync(FULL, (n & up) | ((nml & up) << 10));  // upper n < 2^9, upper sum n m < 2^14
-                        const uint32_t rx = __reduce_or_sync(FULL, M);
-                        const uint32_t ry = __ballot_sync(FULL, M != 0u);
-                        if (lane == idx) { k1 = r1; k2 = r2; k3 = r3; k4 = r4; k5 = r5; k6 = r6; kx = rx; ky = ry; ks = (uint32_t)i; }
-                        ++idx;
-                    }
-                    if (lane < idx && kx) {
-                        const uint32_t n = k1 & 0x3FFu, sf = k1 >> 10, nm_ = k2 & 0x7FFFu, sf1 = k2 >> 15;
-                        const uint32_t n1 = k6 & 0x3FFu, nm1 = k6 >> 10;
-                        const uint32_t rows = (ky | (ky >> 16)) & 0x7FFFu;
-                        const uint32_t u0 = (uint32_t)s0;
-                        uint32_t v[LT_FIELDS];
-                        v[0] = n; v[1] = sf; v[2] = nm_; v[3] = u0 * n + n1;
-                        v[4] = k3; v[5] = k5; v[6] = u0 * sf + sf1;
-                        v[7] = k4; v[8] = u0 * nm_ + nm1; v[9] = u0 * u0 * n + (2u * u0 + 1u) * n1;
-                        v[10] = (uint32_t)__ffs(kx) - 1u; v[11] = 15u * wm + (uint32_t)__ffs(rows) - 1u; v[12] = (ky & 0xFFFFu) ? u0 : u0 + 1u;
-                        v[13] = 31u - (uint32_t)__clz(kx); v[14] = 15u * wm + 31u - (uint32_t)__clz(rows); v[15] = (ky >> 16) ? u0 + 1u : u0;
-                        label_add<T>(sh, lt, pt.status, blab[ks], v, gF0, gM0, gS0);
-                    }
+            // ---- P2: blocks of 15 owned rows x 2 owned planes.  Warp w < 8 does the PAIRS of block w; the MOMENTS of the eight
+            // blocks are items of a queue (ctr[6]) that every warp draws from when it has nothing else to do: warps 8 and 9
+            // after their flush, the others after their pairs (blocks differ in their number of labels, so the warps do
+            // not finish together: phase clocks had the slowest at 1.4 times the mean).
+            int blk = warp;
+            bool pairs_turn = warp < NW2;
+            for (;;) {
+                if (!pairs_turn) {
+                    if (!do_mom) break;
+                    unsigned int it = 0u;
+                    if (lane == 0) it = atomicAdd(&ctr[6], 1u);
+                    blk = (int)__shfl_sync(FULL, it, 0);
+                    if (blk >= NW2) break;
                 }
-
-                if (do_pairs) {
-                    int nres = 0;
-                    uint32_t res_a = 0, res_b = 0, res_1 = 0, res_2 = 0;
-                    auto flush_results = [&]() {
-                        if (lane < nres) {
-                            const uint32_t a = blab[res_a], b = blab[res_b];
-                            const bool lo = a < b;
-                            const uint32_t w18 = res_1 & 0xFFFFu, ff = res_1 >> 16, fmm = res_2 & 0xFFFFu, fss = res_2 >> 16;
-                            uint32_t inc[PT_WORDS];
-                            inc[0] = w18 | (lo ? ff << 16 : 0u);
-                            inc[1] = (lo ? 0u : ff) | (lo ? fmm << 16 : 0u);
-                            inc[2] = (lo ? 0u : fmm) | (lo ? fss << 16 : 0u);
-                            inc[3] = lo ? 0u : fss;
-                            pair_add_call<T>(sh, pt, Vox<T>::key(a, b), inc[0], inc[1], inc[2], inc[3]);
-                        }
-                        nres = 0;
-                    };
-                    // rounds of up to KB labels of the block: their own-row masks in registers, their slots packed 5 bits each
-                    for (uint32_t pcr = PC; pcr;) {
-                        uint32_t Ma[KB];
-                        u64 slots = 0ull;
-#pragma unroll
-                        for (int j = 0; j < KB; ++j) {
-                            const int i = pcr ? __ffs(pcr) - 1 : 0;
-                            Ma[j] = pcr ? (mbase[i * 32] & fm) : 0u;
-                            slots |= (u64)i << (5 * j);
-                            pcr &= pcr - 1u;
-                        }
-                        for (uint32_t rest = PU; rest;) {
-                            const int b = 31 - __clz(rest);
-                            rest ^= 1u << b;
-                            const uint32_t* qb = mbase + b * 32;
-                            const uint32_t c0 = qb[-1], c1 = qb[0], c2 = qb[1];
-                            const uint32_t d0 = qb[-MPLANE - 1], d1 = qb[-MPLANE], d2 = qb[-MPLANE + 1];
-                            const uint32_t u0 = qb[MPLANE - 1], u1 = qb[MPLANE], u2 = qb[MPLANE + 1];
-                            const uint32_t Y = c0 | c1 | c2 | d0 | d1 | d2 | u0 | u1 | u2;
-                            const uint32_t Pm = c0 | c1 | c2 | d1 | u1;
-                            const uint32_t PH = ((hlall >> b) & 1u) | (((hrall >> b) & 1u) << 31);   // b in a left / right halo voxel of the five rows
-                            const uint32_t Dn = (Y | (Pm << 1) | (Pm >> 1) | PH) & fm & ~c1;          // not-b voxels with a b in their N18
-                            // labels of the round that meet Dn somewhere in the warp (b itself cannot: Dn excludes its voxels)
-                            uint32_t ts = 0u;
-#pragma unroll
-                            for (int j = 0; j < KB; ++j) ts |= (Ma[j] & Dn) ? (1u << j) : 0u;
-                            ts = __reduce_or_sync(FULL, ts);
-                            if (!ts) continue;
-                            const uint32_t Bf = (c1 >> 1) | (((hrc1 >> b) & 1u) << 31);                // b is the +f neighbour
-#pragma unroll
-                            for (int j = 0; j < KB; ++j) {
-                                if (!((ts >> j) & 1u)) continue;
-                                const uint32_t Mo = Ma[j];
-                                uint32_t cnt1 = do_w18 ? (uint32_t)__popc(Mo & Dn) : 0u, cnt2 = 0u;
-                                if (do_p6) {
-                                    cnt1 |= (uint32_t)__popc(Mo & Bf) << 16;
-                                    cnt2 = (uint32_t)__popc(Mo & c2) | ((uint32_t)__popc(Mo & u1) << 16);
+                if (1 + 2 * (blk >> 1) <= nown) {
+                    const int wm = blk & 1, s0 = 2 * (blk >> 1);                // s0: brick-local plane of the lower half-warp
+                    const int lm = lane & 15, ls = lane >> 4;
+                    const bool own_row = (lm < 15) && (s0 + ls < nown) && (M0 + 15 * wm + lm < nm);
+                    const int r = own_row ? 1 + 15 * wm + lm : 1;               // idle lanes look at a harmless row
+                    const int q = own_row ? 1 + s0 + ls : 1;
+                    const uint32_t fm = own_row ? fvalid : 0u;
+                    const uint32_t ml = (uint32_t)(15 * wm + lm);               // brick-local row
+                    const uint32_t* mbase = masks + q * MPLANE + r;             // + slot * 32; rows +-1, planes +- MPLANE
+                    const uint32_t* pbase = pres + q * PSTR + r;
+                    const uint32_t PC = __reduce_or_sync(FULL, own_row ? pbase[0] : 0u);  // labels in the block
+                    if (pairs_turn) {
+                        const uint32_t* hlb = hwl + q * PSTR + r;
+                        const uint32_t* hrb = hwr + q * PSTR + r;
+                        const uint32_t hrc1 = hrb[0];
+                        // halo slots of the five rows with an f-shifted neighbour
+                        const uint32_t hlall = hlb[-1] | hlb[0] | hlb[1] | hlb[-PSTR] | hlb[PSTR], hrall = hrb[-1] | hrc1 | hrb[1] | hrb[-PSTR] | hrb[PSTR];
+                        uint32_t pn = pbase[-PSTR - 1] | pbase[-PSTR] | pbase[-PSTR + 1] | pbase[-1] | pbase[0] | pbase[1] | pbase[PSTR - 1] | pbase[PSTR] | pbase[PSTR + 1];
+                        const uint32_t PU = __reduce_or_sync(FULL, own_row ? pn : 0u);       // labels around the block
+                        if (do_pairs) {
+                            int nres = 0;
+                            uint32_t res_a = 0, res_b = 0, res_1 = 0, res_2 = 0;
+                            auto flush_results = [&]() {
+                                if (lane < nres) {
+                                    const uint32_t a = blab[res_a], b = blab[res_b];
+                                    const bool lo = a < b;
+                                    const uint32_t w18 = res_1 & 0xFFFFu, ff = res_1 >> 16, fmm = res_2 & 0xFFFFu, fss = res_2 >> 16;
+                                    uint32_t inc[PT_WORDS];
+                                    inc[0] = w18 | (lo ? ff << 16 : 0u);
+                                    inc[1] = (lo ? 0u : ff) | (lo ? fmm << 16 : 0u);
+                                    inc[2] = (lo ? 0u : fmm) | (lo ? fss << 16 : 0u);
+                                    inc[3] = lo ? 0u : fss;
+                                    pair_add_call<T>(sh, pt, Vox<T>::key(a, b), inc[0], inc[1], inc[2], inc[3]);
                                 }
-                                const uint32_t r1 = __reduce_add_sync(FULL, cnt1);
-                                const uint32_t r2 = __reduce_add_sync(FULL, cnt2);
-                                const bool mine = lane == nres;
-                                res_a = mine ? (uint32_t)((slots >> (5 * j)) & 31ull) : res_a;
-                                res_b = mine ? (uint32_t)b : res_b;
-                                res_1 = mine ? r1 : res_1;
-                                res_2 = mine ? r2 : res_2;
-                                if (++nres == 32) flush_results();
+                                nres = 0;
+                            };
+                            // rounds of up to KB labels of the block: their own-row masks in registers, their slots packed 5 bits each
+                            for (uint32_t pcr = PC; pcr;) {
+                                uint32_t Ma[KB];
+                                u64 slots = 0ull;
+#pragma unroll
+                                for (int j = 0; j < KB; ++j) {
+                                    const int i = pcr ? __ffs(pcr) - 1 : 0;
+                                    Ma[j] = pcr ? (mbase[i * 32] & fm) : 0u;
+                                    slots |= (u64)i << (5 * j);
+                                    pcr &= pcr - 1u;
+                                }
+                                for (uint32_t rest = PU; rest;) {
+                                    const int b = 31 - __clz(rest);
+                                    rest ^= 1u << b;
+                                    const uint32_t* qb = mbase + b * 32;
+                                    const uint32_t c0 = qb[-1], c1 = qb[0], c2 = qb[1];
+                                    const uint32_t d0 = qb[-MPLANE - 1], d1 = qb[-MPLANE], d2 = qb[-MPLANE + 1];
+                                    const uint32_t u0 = qb[MPLANE - 1], u1 = qb[MPLANE], u2 = qb[MPLANE + 1];
+                                    const uint32_t Y = c0 | c1 | c2 | d0 | d1 | d2 | u0 | u1 | u2;
+                                    const uint32_t Pm = c0 | c1 | c2 | d1 | u1;
+                                    const uint32_t PH = ((hlall >> b) & 1u) | (((hrall >> b) & 1u) << 31);   // b in a left / right halo voxel of the five rows
+                                    const uint32_t Dn = (Y | (Pm << 1) | (Pm >> 1) | PH) & fm & ~c1;          // not-b voxels with a b in their N18
+                                    // labels of the round that meet Dn somewhere in the warp (b itself cannot: Dn excludes its voxels)
+                                    uint32_t ts = 0u;
+#pragma unroll
+                                    for (int j = 0; j < KB; ++j) ts |= (Ma[j] & Dn) ? (1u << j) : 0u;
+                                    ts = __reduce_or_sync(FULL, ts);
+                                    if (!ts) continue;
+                                    const uint32_t Bf = (c1 >> 1) | (((hrc1 >> b) & 1u) << 31);                // b is the +f neighbour
+#pragma unroll
+                                    for (int j = 0; j < KB; ++j) {
+                                        if (!((ts >> j) & 1u)) continue;
+                                        const uint32_t Mo = Ma[j];
+                                        uint32_t cnt1 = do_w18 ? (uint32_t)__popc(Mo & Dn) : 0u, cnt2 = 0u;
+                                        if (do_p6) {
+                                            cnt1 |= (uint32_t)__popc(Mo & Bf) << 16;
+                                            cnt2 = (uint32_t)__popc(Mo & c2) | ((uint32_t)__popc(Mo & u1) << 16);
+                                        }
+                                        const uint32_t r1 = __reduce_add_sync(FULL, cnt1);
+                                        const uint32_t r2 = __reduce_add_sync(FULL, cnt2);
+                                        const bool mine = lane == nres;
+                                        res_a = mine ? (uint32_t)((slots >> (5 * j)) & 31ull) : res_a;
+                                        res_b = mine ? (uint32_t)b : res_b;
+                                        res_1 = mine ? r1 : res_1;
+                                        res_2 = mine ? r2 : res_2;
+                                        if (++nres == 32) flush_results();
+                                    }
+                                }
                             }
+                            flush_results();
+                        }
+                    } else {
+                        uint32_t k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, kx = 0, ky = 0, ks = 0;
+                        const uint32_t up = ls ? 0xFFFFFFFFu : 0u;
+                        int idx = 0;
+                        for (uint32_t rest = PC; rest;) {                     // the slots are places in a hashed list: not dense
+                            const int i = 31 - __clz(rest);
+                            rest ^= 1u << i;
+                            const uint32_t M = mbase[i * 32] & fm;
+                            const uint32_t n = (uint32_t)__popc(M);
+                            uint32_t sf = 0u, sff = 0u;
+                            if (M) bit_moments(M, n, sf, sff);
+                            const uint32_t nml = n * ml;
+                            const uint32_t r1 = __reduce_add_sync(FULL, n | (sf << 10));                 // n < 2^10, sum f < 2^15
+                            const uint32_t r2 = __reduce_add_sync(FULL, nml | ((sf & up) << 15));        // sum n m < 2^15, upper sum f < 2^14
+                            const uint32_t r3 = __reduce_add_sync(FULL, sff);
+                            const uint32_t r4 = __reduce_add_sync(FULL, nml * ml);
+                            const uint32_t r5 = __reduce_add_sync(FULL, sf * ml);
+                            const uint32_t r6 = __reduce_add_sync(FULL, (n & up) | ((nml & up) << 10));  // upper n < 2^9, upper sum n m < 2^14
+                            const uint32_t rx = __reduce_or_sync(FULL, M);
+                            const uint32_t ry = __ballot_sync(FULL, M != 0u);
+                            if (lane == idx) { k1 = r1; k2 = r2; k3 = r3; k4 = r4; k5 = r5; k6 = r6; kx = rx; ky = ry; ks = (uint32_t)i; }
+                            ++idx;
+                        }
+                        if (lane < idx && kx) {
+                            const uint32_t n = k1 & 0x3FFu, sf = k1 >> 10, nm_ = k2 & 0x7FFFu, sf1 = k2 >> 15;
+                            const uint32_t n1 = k6 & 0x3FFu, nm1 = k6 >> 10;
+                            const uint32_t rows = (ky | (ky >> 16)) & 0x7FFFu;
+                            const uint32_t u0 = (uint32_t)s0;
+                            uint32_t v[LT_FIELDS];
+                            v[0] = n; v[1] = sf; v[2] = nm_; v[3] = u0 * n + n1;
+                            v[4] = k3; v[5] = k5; v[6] = u0 * sf + sf1;
+                            v[7] = k4; v[8] = u0 * nm_ + nm1; v[9] = u0 * u0 * n + (2u * u0 + 1u) * n1;
+                            v[10] = (uint32_t)__ffs(kx) - 1u; v[11] = 15u * wm + (uint32_t)__ffs(rows) - 1u; v[12] = (ky & 0xFFFFu) ? u0 : u0 + 1u;
+                            v[13] = 31u - (uint32_t)__clz(kx); v[14] = 15u * wm + 31u - (uint32_t)__clz(rows); v[15] = (ky >> 16) ? u0 + 1u : u0;
+                            label_add<T>(sh, lt, pt.status, blab[ks], v, gF0, gM0, gS0);
                         }
                     }
-                    flush_results();
                 }
+                pairs_turn = false;
             }
         } else {
             // ---- G: more than K labels in the brick: every owned voxel on its own, straight from the tile -------------------
@@ -700,12 +736,12 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         }
         if (tid < K) blab[tid] = TA_EMPTY32;
         if (tid == 0) {
-            ctr[2 + cur] = 0u;
+            ctr[2 + cur] = 0u; ctr[6] = 0u;
             if (use_tma && !box_issued && next_brick < total) issue_box(nxt);   // after G: the tile was in use until the barrier
         }
         MK_TICK(5);
 #ifdef TA_WITH_PHASE_TIMING
-        if (clocked) { tk[7] += 1; if (uniform) tk[6] += 1; }
+        if (clocked) { tk[7] += 1; if (uniform) tk[6] += (warp == 0) ? 1ull : (u64)clock64() - t_iter0; }   // [6]: count (first warp), cycles (last warp)
 #endif
     }
 #ifdef TA_WITH_PHASE_TIMING
