@@ -60,23 +60,27 @@ __global__ void __launch_bounds__(256) classify_cores_kernel(PrepassParams P) {
         const T* base = vol + ((size_t)S0 * P.nm + M0) * (size_t)P.nf + F0;
         const uint32_t ref = base[0];
         const uint32_t pat = sizeof(T) == 2 ? ref * 0x10001u : ref;
-        auto load = [&](int r) {
+        auto fetch = [&](int r) {
             uint4 v = make_uint4(pat, pat, pat, pat);
             if (fin && r < nrow) {
                 const int s = r / nrm, m = r - s * nrm;
                 v = mk::mk_ld128(base + ((size_t)s * P.nm + m) * (size_t)P.nf + vx * VE);
             }
-            return (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
+            return v;
         };
         // a look at the first rows settles most tissue bricks for 512 bytes; then six loads in flight per lane
-        uint32_t diff = load(rsub);
+        uint32_t diff;
+        {
+            const uint4 v = fetch(rsub);
+            diff = (v.x ^ pat) | (v.y ^ pat) | (v.z ^ pat) | (v.w ^ pat);
+        }
         bool mixed = __any_sync(0xffffffffu, diff != 0u);
         for (int r0 = RPW; r0 < nrow && !mixed; r0 += RPW * UNR) {
-            uint32_t d[UNR];
+            uint4 v[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) d[u] = load(r0 + u * RPW + rsub);
+            for (int u = 0; u < UNR; ++u) v[u] = fetch(r0 + u * RPW + rsub);
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) diff |= d[u];
+            for (int u = 0; u < UNR; ++u) diff |= (v[u].x ^ pat) | (v[u].y ^ pat) | (v[u].z ^ pat) | (v[u].w ^ pat);
             mixed = __any_sync(0xffffffffu, diff != 0u);
         }
         if (lane == 0) P.core[b] = mixed ? TA_EMPTY32 : ref;

@@ -409,6 +409,9 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
             set_origin(P.work_list ? P.work_list[b0] : b0, 0u);
             if (use_tma) issue_box(0u);
         }
+        const unsigned int b1 = atomicAdd(P.brick_counter, 1u);
+        ctr[1] = b1;
+        if (b1 < total) set_origin(P.work_list ? P.work_list[b1] : b1, 1u);
     }
     __syncthreads();
 
@@ -430,11 +433,6 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         const unsigned int brick = ctr[cur];
         if (brick >= total) break;
         uint32_t* blab = ctr + 16 + K * cur;
-        if (tid == 0) {
-            const unsigned int nb = atomicAdd(P.brick_counter, 1u);
-            ctr[nxt] = nb;
-            if (nb < total) set_origin(P.work_list ? P.work_list[nb] : nb, nxt);
-        }
         const int F0 = (int)ctr[8 + 4 * cur], M0 = (int)ctr[9 + 4 * cur], S0 = (int)ctr[10 + 4 * cur];
         const u64 gF0 = (u64)F0, gM0 = (u64)M0, gS0 = (u64)((long long)S0 + P.slow_offset);
         const int nown = min(ZB, (int)P.own_hi - S0);          // owned planes of this brick: tile planes 1 .. nown
@@ -556,6 +554,14 @@ mask_kernel(ScanParams P, LabelTable lt, PairTable pt, const __grid_constant__ C
         if (use_tma && !overflow && next_brick < total) {
             if (tid == 0) issue_box(nxt);
             box_issued = true;
+        }
+        // The queue index of the brick AFTER next goes into the slot this brick has just stopped needing (every thread read
+        // its origin before the barrier).  One lane of the last warp asks for it here, under P2: at the top of the loop the
+        // round trip of the global atomic made warp 0 late for P1 and the other warps waited for it at the barrier.
+        if (tid == (TP - 1) * 32) {
+            const unsigned int nb2 = atomicAdd(P.brick_counter, 1u);
+            ctr[cur] = nb2;
+            if (nb2 < total) set_origin(P.work_list ? P.work_list[nb2] : nb2, cur);
         }
 
         // the warps without a P2 block empty the tables of the last brick that used them while the others work on this brick's
