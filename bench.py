@@ -433,16 +433,19 @@ def main():
         img = SpatialImage(vol_np.transpose(2, 1, 0), voxelsize=cfg["voxelsize"])     # x fastest, as openalea's images
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            t0 = time.perf_counter()
-            an = SpatialImageAnalysis3D(img, background=1, device=local_rank)
-            ga = graph_arrays(an)
-            t_arrays = time.perf_counter() - t0
+            t_runs = []
+            for _ in range(2):       # the first run also pays the context's allocations (pinned staging, tables)
+                t0 = time.perf_counter()
+                an = SpatialImageAnalysis3D(img, background=1, device=local_rank)
+                ga = graph_arrays(an)
+                t_runs.append(time.perf_counter() - t0)
+            t_arrays = min(t_runs)
             t0 = time.perf_counter()
             nl = an.nb_labels()
             an.volume(); an.boundingbox(); an.center_of_mass(); an.neighbors(); an.wall_areas()
             an.cell_first_layer(); an.labels_at_stack_margins(); an.inertia_axis()
             t_dicts = time.perf_counter() - t0
-        api_e2e = {"graph_arrays_s": t_arrays, "value": nvox / t_arrays / 1e9, "unit": UNIT,
+        api_e2e = {"graph_arrays_s": t_arrays, "graph_arrays_s_runs": t_runs, "value": nvox / t_arrays / 1e9, "unit": UNIT,
                    "dict_methods_s": t_dicts, "labels": int(nl),
                    "note": "pageable numpy volume -> SpatialImageAnalysis3D (H2D + scan + D2H) -> graph_arrays (CSR + property "
                            "arrays); dict_methods_s: then volume, boundingbox, center_of_mass, neighbors, wall_areas, "
