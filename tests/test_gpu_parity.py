@@ -277,6 +277,8 @@ def test_mutators_and_property_image_on_the_gpu():
         assert np.array_equal(np.asarray(work), mutated)
         fresh = LoopOracle(mutated, voxelsize=img.voxelsize, background=1, ignoredlabels=[0])
         compare_api(prod, fresh, check_wall_voxels=False, real_modes=(True,))
+        with pytest.raises(ValueError):                          # a label the voxel type cannot hold must not wrap silently
+            prod.remove_labels_from_image([sorted(prod.labels())[0]], erase_value=70000, verbose=False)
 
 
 @pytest.mark.parametrize("shape", [(5, 3, 2), (17, 16, 8), (129, 17, 9), (131, 5, 3), (260, 40, 21)])

@@ -252,39 +252,72 @@ __device__ __noinline__ void pair_add_call(BrickShared<T> sh, PairTable pt, type
     pair_add_packed<T>(sh, pt, key, inc);
 }
 
-// G (rare): more than K labels in the brick: every owned voxel on its own, straight from the tile
+// G: more than K labels in the brick (noise; cells under ~20 voxels across: C1): every owned voxel on its own, straight
+// from the tile.  One thread per owned row: moments per RUN of a label (closed forms, one table update per run), the 18
+// neighbours of a voxel in registers (offsets are compile-time constants), a voxel whose neighbours all carry its own label
+// is done after 18 compares.
 template <typename T>
 __device__ __noinline__ void brick_per_voxel(const T* tile, BrickShared<T> sh, LabelTable lt, PairTable pt, int tid, int nown, int F0,
                                              int M0, int nf, int nm, u64 gF0, u64 gM0, u64 gS0, bool do_mom, bool do_p6, bool do_w18) {
     typedef Geo<T> G;
     constexpr int HV = G::HV, TRE = G::TRE;
     constexpr int PLANEE = TM * TRE;
-    const int nvo = RW * OM * nown;
-    for (int i = tid; i < nvo; i += NTHREADS) {
-        const int f = i % RW, m = (i / RW) % OM, s = i / (RW * OM);
-        if (F0 + f >= nf || M0 + m >= nm) continue;
-        const T* qv = tile + ((s + 1) * TM + (m + 1)) * TRE + HV + f;
-        const uint32_t a = qv[0];
-        if (do_mom) {
-            const uint32_t uf = f, um = m, us = s;
-            uint32_t v[LT_FIELDS] = {1u, uf, um, us, uf * uf, uf * um, uf * us, um * um, um * us, us * us, uf, um, us, uf, um, us};
-            label_add<T>(sh, lt, pt.status, a, v, gF0, gM0, gS0);
-        }
-        if (do_p6) {
-#pragma unroll 1
-            for (int d = 0; d < 3; ++d) {
-                const uint32_t n = qv[d == 0 ? 1 : (d == 1 ? TRE : PLANEE)];
-                if (n != a) pair_add<T>(sh, pt, a, n, 2 * d + (a < n ? 0 : 1), 1u);
+    const int nrows = OM * nown, nfv = min(RW, nf - F0);
+    for (int row = tid; row < nrows; row += NTHREADS) {
+        const int m = row % OM, s = row / OM;
+        if (M0 + m >= nm) continue;
+        const T* rowp = tile + ((s + 1) * TM + (m + 1)) * TRE + HV;
+        const uint32_t um = (uint32_t)m, us = (uint32_t)s;
+        uint32_t run_label = rowp[0];
+        int run_f0 = 0;
+        for (int f = 0; f <= nfv; ++f) {
+            const uint32_t a = f < nfv ? (uint32_t)rowp[f] : ~run_label;        // f == nfv: closes the last run
+            if (a != run_label) {
+                if (do_mom) {
+                    const uint32_t lo = (uint32_t)run_f0, n = (uint32_t)(f - run_f0), t = n * (n - 1u);
+                    const uint32_t sf = n * lo + (t >> 1), sff = n * lo * lo + lo * t + (t * (2u * n - 1u)) / 6u;
+                    uint32_t v[LT_FIELDS] = {n, sf, n * um, n * us, sff, sf * um, sf * us, n * um * um, n * um * us, n * us * us,
+                                             lo, um, us, (uint32_t)f - 1u, um, us};
+                    label_add<T>(sh, lt, pt.status, run_label, v, gF0, gM0, gS0);
+                }
+                run_label = a; run_f0 = f;
             }
-        }
-        if (do_w18) {
+            if (f == nfv) break;
+            const T* qv = rowp + f;
+            if (do_p6) {
 #pragma unroll 1
-            for (int k = 0; k < 18; ++k) {
-                const uint32_t b = qv[neighbour_offset<TRE, PLANEE>(k)];
-                if (b == a) continue;
-                bool seen = false;
-                for (int kk = 0; kk < k; ++kk) seen |= ((uint32_t)qv[neighbour_offset<TRE, PLANEE>(kk)] == b);
-                if (!seen) pair_add<T>(sh, pt, a, b, 6, 1u);
+                for (int d = 0; d < 3; ++d) {
+                    const uint32_t n = qv[d == 0 ? 1 : (d == 1 ? TRE : PLANEE)];
+                    if (n != a) pair_add<T>(sh, pt, a, n, 2 * d + (a < n ? 0 : 1), 1u);
+                }
+            }
+            if (do_w18) {
+                uint32_t nb[18];
+                uint32_t differ = 0u;
+                {
+                    int c = 0;
+#pragma unroll
+                    for (int ds = -1; ds <= 1; ++ds)
+#pragma unroll
+                        for (int dm = -1; dm <= 1; ++dm)
+#pragma unroll
+                            for (int df = -1; df <= 1; ++df) {
+                                const int l1 = (ds ? 1 : 0) + (dm ? 1 : 0) + (df ? 1 : 0);
+                                if (l1 >= 1 && l1 <= 2) { nb[c] = qv[ds * PLANEE + dm * TRE + df]; differ |= nb[c] ^ a; ++c; }
+                            }
+                }
+                if (differ) {
+                    uint32_t fresh = 0u;                               // bit k: neighbour k carries a label not seen at 0 .. k - 1
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) {
+                        bool fr = nb[k] != a;
+#pragma unroll
+                        for (int kk = 0; kk < k; ++kk) fr = fr && (nb[kk] != nb[k]);
+                        fresh |= fr ? (1u << k) : 0u;
+                    }
+#pragma unroll 1
+                    for (; fresh; fresh &= fresh - 1u) pair_add<T>(sh, pt, a, nb[__ffs(fresh) - 1], 6, 1u);
+                }
             }
         }
     }

@@ -173,6 +173,10 @@ class VolumeScan(object):
     def relabel(self, mapping):
         """Rewrite labels in place (device copy AND the caller's host image) and invalidate the tables.
         ``mapping``: {old label: new label}; other labels are kept."""
+        dmax = int(np.iinfo(self.view.dtype).max)
+        bad = [v for v in mapping.values() if not 0 <= int(v) <= dmax]
+        if bad:
+            raise ValueError("relabel: new label %r does not fit the image's %s voxels" % (bad[0], self.view.dtype))
         top = max(int(np.iinfo(self.view.dtype).max) + 1 if self.view.dtype == np.uint16 else 0,
                   max(mapping) + 1 if mapping else 0,
                   self.tables.nrows if self.tables is not None else int(self.view.max()) + 1)
