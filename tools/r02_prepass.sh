@@ -4,7 +4,7 @@ out=gpurun_out/${1:-r02_prepass}.txt
 : > $out
 for cfg in C2 C3 C4; do
   for pp in 0 1; do
-    t=$(TA_PREPASS=$pp timeout 300 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep "pass 2" | sed 's/pass 2: //')
+    t=$(TA_PREPASS=$pp timeout 300 python tools/profile_scan.py --config $cfg --passes 3 2>&1 | grep "pass 2:" | sed 's/pass 2: //')
     echo "$cfg prepass=$pp: $t" >> $out
   done
 done
