@@ -53,9 +53,9 @@ enum {
  * that buffer) and the status flags -- pair / record overflow, label range -- are checked by the first call that hands
  * results to the host (ta_*_size, ta_fetch_*, ta_pair_records_device), which returns the error then. */
 #define TA_PASS_DEFERRED 0x4000u
-/* Measurement switches, never needed for results (every combination fills identical tables, tests/test_gpu_parity.py):
- * 0x1000 launches the scan kernel's one-hot pair-counting instantiation, 0x800 forces the default per-voxel one;
- * 0x100 / 0x200 / 0x400 stop the kernel after staging / after the uniformity codes / before the table flush. */
+/* Measurement switches, never needed for results: 0x800, in a -DTA_WITH_PHASE_TIMING build only, makes the scan kernel fetch
+ * every tile and drop it (times the box copies on their own); 0x100 / 0x200 / 0x400 stop round 1's kernel (TA_SCAN_KERNEL=brick)
+ * after staging / after the uniformity codes / before the table flush. */
 
 const char* ta_version(void);
 

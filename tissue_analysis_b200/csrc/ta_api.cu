@@ -627,9 +627,8 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
         TA_CUDA(cudaMemcpyAsync(cyc, ctx->phase_cycles, sizeof cyc, cudaMemcpyDeviceToHost, st));
         TA_CUDA(cudaStreamSynchronize(st));
         double tot = 0;
-        for (int k = 0; k < 10; ++k) tot += (double)cyc[k];
-        const char* nm[10] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush",
-                              "R one-hot", "S stencil"};
+        for (int k = 0; k < 8; ++k) tot += (double)cyc[k];
+        const char* nm[8] = {"sched", "A stage", "B codes", "C1 march", "C2 flags", "D voxels", "D2 junctions", "F flush"};
         if (use_mask_kernel()) {
             const char* pn[6] = {"tile wait", "P1", "barrier 1", "P2", "barrier 2", "flush"};
             for (int w = 0; w < 2; ++w) {
@@ -642,9 +641,11 @@ static int run_pass_impl(ta_ctx* ctx, uint32_t flags, uint32_t max_label_hint, u
                              cyc[7] > cyc[6] ? (t - (double)cyc[14]) / (cyc[7] - cyc[6]) : 0.0);
             }
         }
-        fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
-        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
-        fprintf(stderr, "\n[ta] non-uniform bricks: %llu one-hot pair path, %llu per-voxel pair path\n", cyc[12], cyc[13]);
+        else {
+            fprintf(stderr, "[ta phase cycles, thread 0 of each CTA]");
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.1f%%", nm[k], tot > 0 ? 100.0 * cyc[k] / tot : 0.0);
+            fprintf(stderr, "\n");
+        }
     }
 
     if (flags & TA_PASS_DEFERRED) {
