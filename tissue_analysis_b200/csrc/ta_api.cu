@@ -991,15 +991,30 @@ int ta_map_labels(ta_ctx* ctx, const void* lut_host, int lut_elem_bytes, uint64_
     TA_CUDA(cudaMalloc(&out_buf.p, n * lut_elem_bytes));
     void *d_lut = lut_buf.p, *d_out = out_buf.p;
     TA_CUDA(cudaMemcpyAsync(d_lut, lut_host, n_lut * lut_elem_bytes, cudaMemcpyHostToDevice, st));
-    const int grid = ctx->num_sms * 16;
-    if (ctx->elem == 2 && lut_elem_bytes == 2)
-        ta::map_labels_kernel<uint16_t, uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)ctx->vol, (uint16_t*)d_out, (const uint16_t*)d_lut, n_lut, (uint16_t)fill, n);
-    else if (ctx->elem == 2)
-        ta::map_labels_kernel<uint16_t, uint32_t><<<grid, 256, 0, st>>>((const uint16_t*)ctx->vol, (uint32_t*)d_out, (const uint32_t*)d_lut, n_lut, fill, n);
-    else if (lut_elem_bytes == 2)
-        ta::map_labels_kernel<uint32_t, uint16_t><<<grid, 256, 0, st>>>((const uint32_t*)ctx->vol, (uint16_t*)d_out, (const uint16_t*)d_lut, n_lut, (uint16_t)fill, n);
-    else
-        ta::map_labels_kernel<uint32_t, uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)ctx->vol, (uint32_t*)d_out, (const uint32_t*)d_lut, n_lut, fill, n);
+    // the table in shared memory when it fits next to nothing else (one CTA of 1024 threads per SM), else through L1
+    {
+        const size_t lut_bytes = (size_t)n_lut * lut_elem_bytes;
+        const bool smem = lut_bytes <= 160 * 1024;
+        const int threads = smem ? 1024 : 256, grid = smem ? ctx->num_sms : ctx->num_sms * 16;
+        const size_t dyn = smem ? lut_bytes : 0;
+#define TA_MAP_LAUNCH(TI, TO)                                                                                                  \
+        do {                                                                                                                       \
+            if (smem) {                                                                                                            \
+                TA_CUDA(cudaFuncSetAttribute((const void*)ta::map_labels_kernel<TI, TO, true>,                                   \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                              \
+                ta::map_labels_kernel<TI, TO, true><<<grid, threads, dyn, st>>>((const TI*)ctx->vol, (TO*)d_out, (const TO*)d_lut, \
+                                                                                n_lut, (TO)fill, n);                               \
+            } else {                                                                                                               \
+                ta::map_labels_kernel<TI, TO, false><<<grid, threads, 0, st>>>((const TI*)ctx->vol, (TO*)d_out, (const TO*)d_lut,  \
+                                                                               n_lut, (TO)fill, n);                                \
+            }                                                                                                                      \
+        } while (0)
+        if (ctx->elem == 2 && lut_elem_bytes == 2) TA_MAP_LAUNCH(uint16_t, uint16_t);
+        else if (ctx->elem == 2) TA_MAP_LAUNCH(uint16_t, uint32_t);
+        else if (lut_elem_bytes == 2) TA_MAP_LAUNCH(uint32_t, uint16_t);
+        else TA_MAP_LAUNCH(uint32_t, uint32_t);
+#undef TA_MAP_LAUNCH
+    }
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     if (in_place) {
