@@ -46,7 +46,7 @@ constexpr int ZB = 8;                     // owned planes per brick
 constexpr int TP = ZB + 2;                // tile planes = warps
 constexpr int NTHREADS = TP * 32;
 constexpr int K = 24;                     // label slots per brick (16: C2 and C4 take the per-voxel path often, four times slower)
-constexpr int KB = 8;                     // labels of a P2 block held in registers at a time
+constexpr int KB = 6;                     // labels of a P2 block held in registers at a time (8: 3 % slower on C3, 5 % on C2; 4: 1 %)
 constexpr int NW2 = 8;                    // warps with a P2 block (15 rows x 2 planes each)
 constexpr int MPLANE = K * 32 + 16;       // + 16: the two half-warps of a P2 block (planes q, q + 1) use different banks
 constexpr int PSTR = 32;
