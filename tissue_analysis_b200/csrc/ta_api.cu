@@ -98,15 +98,18 @@ template <typename P> static int ensure(ta_ctx* ctx, P** ptr, size_t* have, size
     return TA_OK;
 }
 
-// The scan kernel's instantiations: label width, and -- only in a -DTA_WITH_PHASE_TIMING build -- the phase clocks
-// (TA_PHASE_TIMING=1).  The product library carries the two kernels it launches and nothing else.
+// The scan kernel is the bit-mask kernel (mk::mask_kernel, ta_scan_mask.cuh); the product library carries the kernels it
+// launches and nothing else.  A -DTA_WITH_BRICK_KERNEL build also carries round 1's worklist kernel (scan_kernel, ta_scan.cuh:
+// the A / B baseline, same tables) and launches it under TA_SCAN_KERNEL=brick; a -DTA_WITH_PHASE_TIMING build the phase clocks.
 typedef void (*scan_kernel_fn)(ScanParams, LabelTable, PairTable, const CUtensorMap);
-// TA_SCAN_KERNEL=brick selects the round-1 worklist kernel (scan_kernel, ta_scan.cuh); the default is the bit-mask kernel
-// (mk::mask_kernel, ta_scan_mask.cuh).  Both fill the same tables.
 static bool use_mask_kernel() {
+#ifdef TA_WITH_BRICK_KERNEL
     static int v = -1;
     if (v < 0) { const char* e = getenv("TA_SCAN_KERNEL"); v = (e && !strcmp(e, "brick")) ? 0 : 1; }
     return v == 1;
+#else
+    return true;
+#endif
 }
 // full: all three accumulations (TA_PASS_ALL, what the product runs) with the flags folded at compile time; the other
 // instantiation reads them from the parameters
@@ -114,6 +117,7 @@ static scan_kernel_fn mask_kernel_variant(int elem, bool full) {
     if (full) return elem == 2 ? ta::mk::mask_kernel<uint16_t, 7> : ta::mk::mask_kernel<uint32_t, 7>;
     return elem == 2 ? ta::mk::mask_kernel<uint16_t, -1> : ta::mk::mask_kernel<uint32_t, -1>;
 }
+#ifdef TA_WITH_BRICK_KERNEL
 static scan_kernel_fn scan_kernel_variant(int elem, bool timing) {
 #ifdef TA_WITH_PHASE_TIMING
     if (timing) return elem == 2 ? ta::scan_kernel<uint16_t, true> : ta::scan_kernel<uint32_t, true>;
@@ -121,6 +125,7 @@ static scan_kernel_fn scan_kernel_variant(int elem, bool timing) {
     (void)timing;
     return elem == 2 ? ta::scan_kernel<uint16_t, false> : ta::scan_kernel<uint32_t, false>;
 }
+#endif
 
 extern "C" {
 
@@ -162,11 +167,13 @@ int ta_ctx_create(ta_ctx** out, int device) {
     for (auto& e : ctx->ev) TA_CUDA(cudaEventCreate(&e));
     TA_CUDA(cudaMalloc((void**)&ctx->status, 8 * sizeof(uint32_t)));
     ctx->counters = ctx->status + 4;
+#ifdef TA_WITH_BRICK_KERNEL
     for (int e = 0; e < 2; ++e)
         for (int tm = 0; tm < 2; ++tm)
             TA_CUDA(cudaFuncSetAttribute((const void*)scan_kernel_variant(e ? 4 : 2, tm != 0),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(e ? ta::scan_smem_bytes<uint32_t>() : ta::scan_smem_bytes<uint16_t>())));
+#endif
     for (int full = 0; full < 2; ++full) {
         TA_CUDA(cudaFuncSetAttribute((const void*)mask_kernel_variant(2, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ta::mk::smem_bytes<uint16_t>()));
@@ -463,12 +470,16 @@ static int launch_scan(ta_ctx* ctx, ScanParams P, const CUtensorMap& tmap, long 
         TA_CUDA(cudaGetLastError());
         return TA_OK;
     }
+#ifdef TA_WITH_BRICK_KERNEL
     int grid = (int)std::min<size_t>(total, (size_t)ctx->num_sms * 3);
     const size_t smem = ctx->elem == 2 ? ta::scan_smem_bytes<uint16_t>() : ta::scan_smem_bytes<uint32_t>();
     scan_kernel_variant(ctx->elem, P.phase_cycles != nullptr)<<<grid, ta::NTHREADS, smem, st>>>(P, ctx->lt, ctx->pt, tmap);
     ctx->launches++;
     TA_CUDA(cudaGetLastError());
     return TA_OK;
+#else
+    return fail(ctx, TA_ERR_BAD_ARG, "round 1's scan kernel is not in this build (-DTA_WITH_BRICK_KERNEL)");
+#endif
 }
 
 // host_src != nullptr: the bound (context-owned) buffer is filled from host_src in chunks of `chunk_planes` planes on
